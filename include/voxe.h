@@ -1,0 +1,146 @@
+/*
+ * voxe.h -- C ABI of libvoxe_sm100a.so: the B200-native replacement for Vox-E's differentiable
+ *           SH-voxel-grid ray-marcher (the hot path behind `render_sh_voxel_grid`).
+ *
+ * Reference interface each entry point replaces (paths relative to the Vox-E tree):
+ *
+ *   voxe_render_fwd   the three stages bound by  thre3d_atom/thre3d_reprs/renderers.py:50-105  and run by
+ *                     thre3d_atom/rendering/volumetric/render_interface.py:140-171 :
+ *                       sampler      thre3d_atom/rendering/volumetric/sample.py:15-68, 71-184, 187-202
+ *                       processor    thre3d_atom/rendering/volumetric/process.py:20-96  (VoxelGrid.forward,
+ *                                    thre3d_atom/thre3d_reprs/voxels.py:287-342; SH ladder
+ *                                    thre3d_atom/rendering/volumetric/utils/spherical_harmonics.py:64-132)
+ *                       accumulator  thre3d_atom/rendering/volumetric/accumulate.py:31-113
+ *   voxe_render_bwd   the autograd backward of the above, triggered by `total_loss.backward()` at
+ *                     thre3d_atom/modules/trainers.py:350 and thre3d_atom/modules/sds_trainer.py:332
+ *   voxe_pack_grid /  the per-call full-grid passes of VoxelGrid.forward (voxels.py:303-305: `_densities *
+ *   voxe_unpack_grad  expected_density_scale`, pre-activation) and their backward: the kernels work on ONE packed
+ *                     channel-last volume [X,Y,Z,C] (C = features + density, padded to a multiple of 4) so a
+ *                     trilinear corner is one or more 16-byte vectors and a gradient scatter is a vector RED.
+ *   attn mode         VOXE_FLAG_ATTN selects the twin  renderers.py:108-163 / accumulate.py:115-198  (one colour
+ *                     channel, background term forced to zero).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer to fp32 data owned by the caller (torch allocations in the Python
+ *     binding); the library allocates nothing persistent and keeps no global state except a thread-local error
+ *     string and the optional tuning override;
+ *   - kernels are enqueued asynchronously on `stream`; the calls never synchronise;
+ *   - return value 0 = success, otherwise a VOXE_ERR_* code (or a cudaError_t offset by VOXE_ERR_CUDA_BASE);
+ *     `voxe_last_error()` describes the most recent failure on the calling thread;
+ *   - there is no CPU fallback: the calls fail when no sm_100-class device/kernel image is available.
+ */
+#ifndef VOXE_H_
+#define VOXE_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VOXE_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define VOXE_API __attribute__((visibility("default")))
+#else
+#define VOXE_API
+#endif
+
+/* opaque CUDA stream handle (binary compatible with cudaStream_t / CUstream) */
+typedef struct CUstream_st* voxe_stream_t;
+
+/* density pre-activation (applied to `densities * density_scale` at the voxels, voxels.py:303-305) */
+enum { VOXE_PREACT_IDENTITY = 0, VOXE_PREACT_ABS = 1 };
+/* density post-activation (applied to the interpolated density, voxels.py:320) */
+enum { VOXE_POSTACT_IDENTITY = 0, VOXE_POSTACT_RELU = 1, VOXE_POSTACT_SOFTPLUS = 2 };
+
+/* render flags == the boolean fields of SHVoxGridRenderConfig (renderers.py:29-47) */
+enum {
+  VOXE_FLAG_PERTURB = 1,           /* perturb_sampled_points: stratified jitter, needs `jitter` [R,S]      */
+  VOXE_FLAG_AABB_SAMPLING = 2,     /* optimized_sampling: per-ray slab test, misses fall back to near/far  */
+  VOXE_FLAG_DISPARITY_SAMPLING = 4,/* linear_disparity_sampling (ignored with AABB sampling, as upstream)  */
+  VOXE_FLAG_WHITE_BKGD = 8,        /* white_bkgd                                                           */
+  VOXE_FLAG_RENDER_DIFFUSE = 16,   /* render_diffuse: only the degree-0 SH coefficient                     */
+  VOXE_FLAG_ATTN = 32              /* attention-grid twin: n_colour == 1, no background term               */
+};
+
+enum {
+  VOXE_OK = 0,
+  VOXE_ERR_INVALID_ARGUMENT = 1,
+  VOXE_ERR_UNSUPPORTED = 2,       /* combination outside the fused set (e.g. SH degree > 3, S > 4096)       */
+  VOXE_ERR_NO_DEVICE = 3,
+  VOXE_ERR_CUDA_BASE = 1000       /* + cudaError_t */
+};
+
+/* Geometry + activations of a voxel grid (VoxelGrid, voxels.py:46-130). */
+typedef struct VoxeGridDesc {
+  int32_t dims[3];        /* X, Y, Z (width_x, depth_y, height_z); z is the fastest-varying axis            */
+  int32_t n_features;     /* F = n_colour * (sh_degree+1)^2                                                 */
+  int32_t channels;       /* packed channels per voxel: voxe_packed_channels(F) = roundup4(F + 1)           */
+  float aabb_lo[3];       /* fp32(grid_location - dims*voxel_size/2)   (voxels.py:198-223)                  */
+  float aabb_hi[3];
+  float norm_scale[3];    /* fp32(2)/(fp32(hi)-fp32(lo))               (imaging_utils.py:57-63)             */
+  float norm_bias[3];     /* fp32(-1) - fp32(lo)*norm_scale                                                 */
+  float density_scale;    /* expected_density_scale                                                         */
+  int32_t preact;         /* VOXE_PREACT_*                                                                  */
+  int32_t postact;        /* VOXE_POSTACT_*                                                                 */
+} VoxeGridDesc;
+
+/* One render call (SHVoxGridRenderConfig, renderers.py:29-47). */
+typedef struct VoxeRenderDesc {
+  int32_t num_samples;    /* S >= 2                                                                         */
+  float near;             /* camera_bounds.near                                                             */
+  float far;              /* camera_bounds.far                                                              */
+  int32_t flags;          /* VOXE_FLAG_*                                                                    */
+  int32_t sh_degree;      /* 0..3                                                                           */
+  int32_t n_colour;       /* 3 (RGB) or 1 (attn)                                                            */
+  float noise_std;        /* stochastic_density_noise_std; != 0 needs `noise` [R,S] (standard normal)       */
+} VoxeRenderDesc;
+
+VOXE_API int voxe_abi_version(void);
+VOXE_API const char* voxe_last_error(void);
+
+/* roundup4(n_features + 1): channel count of the packed volume. */
+VOXE_API int voxe_packed_channels(int n_features);
+
+/* packed[X,Y,Z,C] <- concat(features[X,Y,Z,F], densities[X,Y,Z,1], zero padding).  Values are copied verbatim;
+ * density scale and pre-activation are applied inside the render kernels at gather time. */
+VOXE_API int voxe_pack_grid(const VoxeGridDesc* grid, const float* densities, const float* features, float* packed,
+                   voxe_stream_t stream);
+
+/* Split a packed gradient volume into d_densities[X,Y,Z,1] and d_features[X,Y,Z,F].
+ * accumulate != 0: add into the outputs; == 0: overwrite.  Either output may be NULL (skipped). */
+VOXE_API int voxe_unpack_grad(const VoxeGridDesc* grid, const float* packed_grad, float* d_densities, float* d_features,
+                     int accumulate, voxe_stream_t stream);
+
+/* Forward render of R rays.
+ *   packed   [X,Y,Z,C]   from voxe_pack_grid
+ *   rays_o/d [R,3]       origins / (un-normalised) directions
+ *   jitter   [R,S] or NULL   the U[0,1) draws of sample.py:63 (required with VOXE_FLAG_PERTURB)
+ *   noise    [R,S] or NULL   the N(0,1) draws of accumulate.py:59-62 (required when noise_std != 0)
+ *   colour   [R,n_colour], depth [R], acc [R], disparity [R]   outputs (disparity may be NULL) */
+VOXE_API int voxe_render_fwd(const VoxeGridDesc* grid, const VoxeRenderDesc* render, const float* packed,
+                    const float* rays_o, const float* rays_d, const float* jitter, const float* noise,
+                    float* colour, float* depth, float* acc, float* disparity, int64_t num_rays,
+                    voxe_stream_t stream);
+
+/* Backward: recomputes the forward per ray (no O(R*S) activations are stored) and scatter-ADDS
+ * dL/d(packed) into `packed_grad` [X,Y,Z,C] (caller-zeroed; accumulate-into, so several ray batches or both
+ * renders of a training step can share one buffer).  g_depth / g_acc / g_disp may be NULL (treated as zero).
+ * The disparity gradient is applied only on rays whose disparity is finite (depth/acc > 1e-10). */
+VOXE_API int voxe_render_bwd(const VoxeGridDesc* grid, const VoxeRenderDesc* render, const float* packed,
+                    const float* rays_o, const float* rays_d, const float* jitter, const float* noise,
+                    const float* g_colour, const float* g_depth, const float* g_acc, const float* g_disp,
+                    float* packed_grad, int64_t num_rays, voxe_stream_t stream);
+
+/* Launch-shape override for tuning runs: samples per thread (4 or 8) and rays per CTA (power of two <= 32);
+ * 0 restores the built-in choice.  Does not change results beyond fp32 summation order. */
+VOXE_API int voxe_set_tuning(int samples_per_thread, int rays_per_cta);
+
+/* Number of kernels this library has launched on the calling process since load (for bench accounting). */
+VOXE_API int64_t voxe_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VOXE_H_ */

@@ -1,0 +1,208 @@
+// voxe_capi.cu -- the C ABI of libvoxe_sm100a.so (see include/voxe.h for the contract and the reference
+// interfaces each entry point replaces).  Plain pointers and sizes in, error codes out; no torch types.
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "voxe.h"
+#include "voxe_device.cuh"
+#include "voxe_launch.h"
+
+namespace {
+
+thread_local char g_error[512] = "";
+std::atomic<int64_t> g_launches{0};
+std::atomic<int> g_tune_l{0}, g_tune_rpc{0};
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_error, sizeof(g_error), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+  return fail(VOXE_ERR_CUDA_BASE + (int)e, "%s: %s (%s)", what, cudaGetErrorName(e), cudaGetErrorString(e));
+}
+
+int check_grid(const VoxeGridDesc* g) {
+  if (!g) return fail(VOXE_ERR_INVALID_ARGUMENT, "grid descriptor is NULL");
+  for (int a = 0; a < 3; ++a)
+    if (g->dims[a] < 1) return fail(VOXE_ERR_INVALID_ARGUMENT, "grid dims must be >= 1 (got %d on axis %d)", g->dims[a], a);
+  if (g->n_features < 1) return fail(VOXE_ERR_INVALID_ARGUMENT, "n_features must be >= 1");
+  if (g->channels != voxe_packed_channels(g->n_features))
+    return fail(VOXE_ERR_INVALID_ARGUMENT, "channels must be roundup4(n_features+1) = %d (got %d)",
+                voxe_packed_channels(g->n_features), g->channels);
+  const int64_t nvec = (int64_t)g->dims[0] * g->dims[1] * g->dims[2] * (g->channels / 4);
+  if (nvec >= (int64_t)1 << 31) return fail(VOXE_ERR_UNSUPPORTED, "packed grid has %lld 16-byte vectors; limit is 2^31", (long long)nvec);
+  if (g->preact != VOXE_PREACT_IDENTITY && g->preact != VOXE_PREACT_ABS)
+    return fail(VOXE_ERR_UNSUPPORTED, "density pre-activation %d is not in the fused set {identity, abs}", g->preact);
+  if (g->postact < VOXE_POSTACT_IDENTITY || g->postact > VOXE_POSTACT_SOFTPLUS)
+    return fail(VOXE_ERR_UNSUPPORTED, "density post-activation %d is not in the fused set {identity, relu, softplus}", g->postact);
+  return VOXE_OK;
+}
+
+int check_render(const VoxeGridDesc* g, const VoxeRenderDesc* r, const float* jitter, const float* noise) {
+  if (!r) return fail(VOXE_ERR_INVALID_ARGUMENT, "render descriptor is NULL");
+  if (r->num_samples < 2) return fail(VOXE_ERR_INVALID_ARGUMENT, "num_samples must be >= 2 (got %d)", r->num_samples);
+  if (r->sh_degree < 0 || r->sh_degree > 3)
+    return fail(VOXE_ERR_UNSUPPORTED, "only SH degrees 0..3 are supported (got %d)", r->sh_degree);
+  const bool attn = (r->flags & VOXE_FLAG_ATTN) != 0;
+  if (r->n_colour != (attn ? 1 : 3)) return fail(VOXE_ERR_INVALID_ARGUMENT, "n_colour must be %d", attn ? 1 : 3);
+  if (attn && r->sh_degree != 0) return fail(VOXE_ERR_UNSUPPORTED, "the attention render uses a single SH-0 channel");
+  const int k = (r->sh_degree + 1) * (r->sh_degree + 1);
+  if (g->n_features != r->n_colour * k)
+    return fail(VOXE_ERR_INVALID_ARGUMENT, "n_features %d does not match n_colour*(deg+1)^2 = %d", g->n_features, r->n_colour * k);
+  if ((r->flags & VOXE_FLAG_PERTURB) && !jitter)
+    return fail(VOXE_ERR_INVALID_ARGUMENT, "VOXE_FLAG_PERTURB needs the jitter buffer [R,S]");
+  if (r->noise_std != 0.f && !noise) return fail(VOXE_ERR_INVALID_ARGUMENT, "noise_std != 0 needs the noise buffer [R,S]");
+  return VOXE_OK;
+}
+
+// Launch shape: samples per thread L, sample segments per ray, rays per CTA.
+int pick_shape(int S, int& L, int& nseg, int& rpc) {
+  const int max_threads = voxe::max_threads_per_cta();
+  L = g_tune_l.load();
+  if (L != 4 && L != 8) L = (S <= 32) ? 4 : 8;
+  nseg = (S + L - 1) / L;
+  if (nseg > max_threads) return fail(VOXE_ERR_UNSUPPORTED, "num_samples %d exceeds the supported maximum %d", S, max_threads * L);
+  rpc = g_tune_rpc.load();
+  if (rpc <= 0 || rpc > 32 || (rpc & (rpc - 1))) rpc = 32;
+  while (rpc > 1 && rpc * nseg > max_threads) rpc >>= 1;
+  // keep at least ~2 CTAs' worth of threads per ray group small enough to balance over 148 SMs
+  if (g_tune_rpc.load() <= 0 && rpc * nseg > 512) rpc >>= 1;
+  return VOXE_OK;
+}
+
+int fill_params(const VoxeGridDesc* g, const VoxeRenderDesc* r, int64_t R, voxe::KParams& p, int& L) {
+  std::memset(&p, 0, sizeof(p));
+  p.R = (int)R;
+  p.S = r->num_samples;
+  p.X = g->dims[0];
+  p.Y = g->dims[1];
+  p.Z = g->dims[2];
+  for (int a = 0; a < 3; ++a) {
+    p.lo[a] = g->aabb_lo[a];
+    p.hi[a] = g->aabb_hi[a];
+    p.nscale[a] = g->norm_scale[a];
+    p.nbias[a] = g->norm_bias[a];
+  }
+  p.near = r->near;
+  p.far = r->far;
+  p.dscale = g->density_scale;
+  p.noise_std = r->noise_std;
+  p.lin_step = 1.0f / (float)(r->num_samples - 1);
+  p.flags = r->flags;
+  p.preact = g->preact;
+  p.postact = g->postact;
+  return pick_shape(p.S, L, p.nseg, p.rpc);
+}
+
+}  // namespace
+
+extern "C" {
+
+int voxe_abi_version(void) { return VOXE_ABI_VERSION; }
+
+const char* voxe_last_error(void) { return g_error; }
+
+int voxe_packed_channels(int n_features) { return ((n_features + 1 + 3) / 4) * 4; }
+
+int64_t voxe_launch_count(void) { return g_launches.load(); }
+
+int voxe_set_tuning(int samples_per_thread, int rays_per_cta) {
+  if (samples_per_thread != 0 && samples_per_thread != 4 && samples_per_thread != 8)
+    return fail(VOXE_ERR_INVALID_ARGUMENT, "samples_per_thread must be 0, 4 or 8");
+  if (rays_per_cta < 0 || rays_per_cta > 32 || (rays_per_cta & (rays_per_cta - 1)))
+    return fail(VOXE_ERR_INVALID_ARGUMENT, "rays_per_cta must be 0 or a power of two <= 32");
+  g_tune_l.store(samples_per_thread);
+  g_tune_rpc.store(rays_per_cta);
+  return VOXE_OK;
+}
+
+int voxe_pack_grid(const VoxeGridDesc* grid, const float* densities, const float* features, float* packed,
+                   voxe_stream_t stream) {
+  if (int rc = check_grid(grid)) return rc;
+  if (!densities || !features || !packed) return fail(VOXE_ERR_INVALID_ARGUMENT, "voxe_pack_grid: NULL buffer");
+  const int64_t nvox = (int64_t)grid->dims[0] * grid->dims[1] * grid->dims[2];
+  cudaError_t e = voxe::launch_pack_grid(densities, features, packed, nvox, grid->n_features, grid->channels,
+                                         (cudaStream_t)stream);
+  if (e != cudaSuccess) return cuda_fail(e, "voxe_pack_grid launch");
+  g_launches.fetch_add(1);
+  return VOXE_OK;
+}
+
+int voxe_unpack_grad(const VoxeGridDesc* grid, const float* packed_grad, float* d_densities, float* d_features,
+                     int accumulate, voxe_stream_t stream) {
+  if (int rc = check_grid(grid)) return rc;
+  if (!packed_grad) return fail(VOXE_ERR_INVALID_ARGUMENT, "voxe_unpack_grad: NULL packed_grad");
+  if (!d_densities && !d_features) return VOXE_OK;
+  const int64_t nvox = (int64_t)grid->dims[0] * grid->dims[1] * grid->dims[2];
+  cudaError_t e = voxe::launch_unpack_grad(packed_grad, d_densities, d_features, nvox, grid->n_features,
+                                           grid->channels, accumulate != 0, (cudaStream_t)stream);
+  if (e != cudaSuccess) return cuda_fail(e, "voxe_unpack_grad launch");
+  g_launches.fetch_add(1);
+  return VOXE_OK;
+}
+
+int voxe_render_fwd(const VoxeGridDesc* grid, const VoxeRenderDesc* render, const float* packed,
+                    const float* rays_o, const float* rays_d, const float* jitter, const float* noise,
+                    float* colour, float* depth, float* acc, float* disparity, int64_t num_rays,
+                    voxe_stream_t stream) {
+  if (int rc = check_grid(grid)) return rc;
+  if (int rc = check_render(grid, render, jitter, noise)) return rc;
+  if (num_rays < 0 || num_rays > 0x7fffffff) return fail(VOXE_ERR_INVALID_ARGUMENT, "num_rays out of range");
+  if (num_rays == 0) return VOXE_OK;
+  if (!packed || !rays_o || !rays_d || !colour || !depth || !acc)
+    return fail(VOXE_ERR_INVALID_ARGUMENT, "voxe_render_fwd: NULL buffer");
+  voxe::KParams p;
+  int L = 0;
+  if (int rc = fill_params(grid, render, num_rays, p, L)) return rc;
+  p.grid = reinterpret_cast<const float4*>(packed);
+  p.rays_o = rays_o;
+  p.rays_d = rays_d;
+  p.jitter = (render->flags & VOXE_FLAG_PERTURB) ? jitter : nullptr;
+  p.noise = (render->noise_std != 0.f) ? noise : nullptr;
+  p.colour = colour;
+  p.depth = depth;
+  p.acc = acc;
+  p.disp = disparity;
+  cudaError_t e = voxe::launch_render(p, render->sh_degree, render->n_colour, L, false, (cudaStream_t)stream);
+  if (e != cudaSuccess) return cuda_fail(e, "voxe_render_fwd launch");
+  g_launches.fetch_add(1);
+  return VOXE_OK;
+}
+
+int voxe_render_bwd(const VoxeGridDesc* grid, const VoxeRenderDesc* render, const float* packed,
+                    const float* rays_o, const float* rays_d, const float* jitter, const float* noise,
+                    const float* g_colour, const float* g_depth, const float* g_acc, const float* g_disp,
+                    float* packed_grad, int64_t num_rays, voxe_stream_t stream) {
+  if (int rc = check_grid(grid)) return rc;
+  if (int rc = check_render(grid, render, jitter, noise)) return rc;
+  if (num_rays < 0 || num_rays > 0x7fffffff) return fail(VOXE_ERR_INVALID_ARGUMENT, "num_rays out of range");
+  if (num_rays == 0) return VOXE_OK;
+  if (!packed || !rays_o || !rays_d || !g_colour || !packed_grad)
+    return fail(VOXE_ERR_INVALID_ARGUMENT, "voxe_render_bwd: NULL buffer");
+  voxe::KParams p;
+  int L = 0;
+  if (int rc = fill_params(grid, render, num_rays, p, L)) return rc;
+  p.grid = reinterpret_cast<const float4*>(packed);
+  p.grad = reinterpret_cast<float4*>(packed_grad);
+  p.rays_o = rays_o;
+  p.rays_d = rays_d;
+  p.jitter = (render->flags & VOXE_FLAG_PERTURB) ? jitter : nullptr;
+  p.noise = (render->noise_std != 0.f) ? noise : nullptr;
+  p.g_colour = g_colour;
+  p.g_depth = g_depth;
+  p.g_acc = g_acc;
+  p.g_disp = g_disp;
+  cudaError_t e = voxe::launch_render(p, render->sh_degree, render->n_colour, L, true, (cudaStream_t)stream);
+  if (e != cudaSuccess) return cuda_fail(e, "voxe_render_bwd launch");
+  g_launches.fetch_add(1);
+  return VOXE_OK;
+}
+
+}  // extern "C"

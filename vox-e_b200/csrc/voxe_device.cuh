@@ -1,0 +1,261 @@
+// voxe_device.cuh -- device-side building blocks of the fused ray-marcher (sm_100a).
+//
+// Semantics follow SURVEY.md 8.A, i.e. the reference's
+//   sample.py:15-68,71-184 (depths, slab test)      voxels.py:225-234,263-342 (normalise, inside test, trilinear)
+//   process.py:46-91 (SH colour, mask)              accumulate.py:49-88 (compositing)
+// Geometry (ray interval, depths, sample positions, inside test) is evaluated op for op in fp32 with explicit
+// round-to-nearest intrinsics (no FMA contraction): with AABB-bound sampling the first/last sample lies exactly
+// on a grid face and the reference's own fp32 rounding decides whether it is inside.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace voxe {
+
+constexpr float kZeroPlus = 1e-10f;   // thre3d_atom/utils/constants.py:8
+constexpr float kInfinity = 1e10f;    // thre3d_atom/utils/constants.py:9
+
+enum : int { kPerturb = 1, kAabb = 2, kDisparity = 4, kWhite = 8, kDiffuse = 16, kAttn = 32 };
+enum : int { kPreIdentity = 0, kPreAbs = 1 };
+enum : int { kPostIdentity = 0, kPostRelu = 1, kPostSoftplus = 2 };
+
+// Kernel parameter block (passed by value, lives in constant bank 0).
+struct KParams {
+  const float4* grid;   // packed [X*Y*Z][CV] float4
+  float4* grad;         // packed gradient (backward only)
+  const float* rays_o;
+  const float* rays_d;
+  const float* jitter;  // [R,S] or null
+  const float* noise;   // [R,S] or null
+  float* colour;        // fwd outputs
+  float* depth;
+  float* acc;
+  float* disp;
+  const float* g_colour;  // bwd inputs
+  const float* g_depth;
+  const float* g_acc;
+  const float* g_disp;
+  int R, S;
+  int X, Y, Z;
+  float lo[3], hi[3], nscale[3], nbias[3];
+  float near, far, dscale, noise_std, lin_step;
+  int flags, preact, postact;
+  int rpc, nseg;  // rays per CTA, sample segments per ray (threads = rpc * nseg rounded up to 32)
+};
+
+// ---------------------------------------------------------------------------------------------------------
+// depths
+// ---------------------------------------------------------------------------------------------------------
+// torch.linspace(0, 1, S): symmetric evaluation from both ends (exact 0 and 1 at the end points).
+__device__ __forceinline__ float lin_t(int i, int S, float step) {
+  return (i < (S >> 1)) ? __fmul_rn(step, (float)i) : __fsub_rn(1.0f, __fmul_rn(step, (float)(S - 1 - i)));
+}
+
+// Un-jittered depth of sample i (sample.py:46-54).  inv_near/inv_far are only read for disparity sampling.
+__device__ __forceinline__ float depth_plain(const KParams& p, float near, float far, float inv_near, float inv_far,
+                                             bool disparity, int i) {
+  const float t = lin_t(i, p.S, p.lin_step);
+  const float omt = __fsub_rn(1.0f, t);
+  if (disparity) return __fdiv_rn(1.0f, __fadd_rn(__fmul_rn(inv_near, omt), __fmul_rn(inv_far, t)));
+  return __fadd_rn(__fmul_rn(near, omt), __fmul_rn(far, t));
+}
+
+// Per-ray (near, far): camera bounds, or the slab test of sample.py:71-184 (misses keep the camera bounds,
+// hits ignore them; both ends clipped at 0).
+__device__ __forceinline__ void ray_interval(const KParams& p, const float (&o)[3], const float (&d)[3], float& near,
+                                             float& far) {
+  near = p.near;
+  far = p.far;
+  if (!(p.flags & kAabb)) return;
+  float lo = 0.f, hi = 0.f;
+  bool hit = true;
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    const float den = __fadd_rn(d[a], kZeroPlus);
+    const float t0 = __fdiv_rn(__fsub_rn(p.lo[a], o[a]), den);
+    const float t1 = __fdiv_rn(__fsub_rn(p.hi[a], o[a]), den);
+    const float alo = (t0 > t1) ? t1 : t0;
+    const float ahi = (t0 > t1) ? t0 : t1;
+    if (a == 0) {
+      lo = alo;
+      hi = ahi;
+    } else {
+      if (lo > ahi || alo > hi) hit = false;
+      lo = (alo > lo) ? alo : lo;
+      hi = (ahi < hi) ? ahi : hi;
+    }
+  }
+  if (hit) {
+    near = lo;
+    far = hi;
+  }
+  near = (near < 0.f) ? 0.f : near;  // torch.clip(min=0); NaN stays NaN
+  far = (far < 0.f) ? 0.f : far;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// SH basis with the reference's constants and signs (spherical_harmonics.py:33-50, 86-116)
+// ---------------------------------------------------------------------------------------------------------
+template <int DEG>
+__device__ __forceinline__ void sh_basis(float x, float y, float z, bool diffuse, float (&Y)[(DEG + 1) * (DEG + 1)]) {
+  Y[0] = 0.28209479177387814f;
+  if constexpr (DEG > 0) {
+    Y[1] = -0.4886025119029199f * y;
+    Y[2] = 0.4886025119029199f * z;
+    Y[3] = -0.4886025119029199f * x;
+  }
+  if constexpr (DEG > 1) {
+    const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+    Y[4] = 1.0925484305920792f * xy;
+    Y[5] = -1.0925484305920792f * yz;
+    Y[6] = 0.31539156525252005f * (2.0f * zz - xx - yy);
+    Y[7] = -1.0925484305920792f * xz;
+    Y[8] = 0.5462742152960396f * (xx - yy);
+    if constexpr (DEG > 2) {
+      Y[9] = -0.5900435899266435f * y * (3.f * xx - yy);
+      Y[10] = 2.890611442640554f * xy * z;
+      Y[11] = -0.4570457994644658f * y * (4.f * zz - xx - yy);
+      Y[12] = 0.3731763325901154f * z * (2.f * zz - 3.f * xx - 3.f * yy);
+      Y[13] = -0.4570457994644658f * x * (4.f * zz - xx - yy);
+      Y[14] = 1.445305721320277f * z * (xx - yy);
+      Y[15] = -0.5900435899266435f * x * (xx - 3.f * yy);
+    }
+  }
+  if (diffuse) {  // render_diffuse: only the degree-0 coefficient (process.py:59-63)
+#pragma unroll
+    for (int k = 1; k < (DEG + 1) * (DEG + 1); ++k) Y[k] = 0.f;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// trilinear corner set (grid_sample: bilinear, zeros padding, align_corners=False)
+// ---------------------------------------------------------------------------------------------------------
+struct Corners {
+  int idx[8];   // linear voxel index (clamped into range; weight is zero when the true corner is outside)
+  float w[8];
+};
+
+// Strict inside test on the world-space point (voxels.py:263-285).
+__device__ __forceinline__ bool inside_aabb(const KParams& p, float px, float py, float pz) {
+  return (px > p.lo[0]) & (px < p.hi[0]) & (py > p.lo[1]) & (py < p.hi[1]) & (pz > p.lo[2]) & (pz < p.hi[2]);
+}
+
+__device__ __forceinline__ void axis_setup(float pc, float scale, float bias, int N, int& i0, int& i1, float& w0,
+                                           float& w1) {
+  const float n = __fadd_rn(__fmul_rn(pc, scale), bias);   // voxels.py:225-234 (two rounded ops)
+  const float u = ((n + 1.0f) * (float)N - 1.0f) * 0.5f;   // grid_sampler unnormalize, align_corners=False
+  const float fl = floorf(u);
+  const float f = u - fl;
+  const int i = (int)fl;
+  w0 = (i >= 0 && i < N) ? (1.0f - f) : 0.f;
+  w1 = (i + 1 >= 0 && i + 1 < N) ? f : 0.f;
+  i0 = min(max(i, 0), N - 1);
+  i1 = min(max(i + 1, 0), N - 1);
+}
+
+__device__ __forceinline__ void make_corners(const KParams& p, float px, float py, float pz, Corners& c) {
+  int x0, x1, y0, y1, z0, z1;
+  float wx0, wx1, wy0, wy1, wz0, wz1;
+  axis_setup(px, p.nscale[0], p.nbias[0], p.X, x0, x1, wx0, wx1);
+  axis_setup(py, p.nscale[1], p.nbias[1], p.Y, y0, y1, wy0, wy1);
+  axis_setup(pz, p.nscale[2], p.nbias[2], p.Z, z0, z1, wz0, wz1);
+  const int r00 = (x0 * p.Y + y0) * p.Z, r01 = (x0 * p.Y + y1) * p.Z;
+  const int r10 = (x1 * p.Y + y0) * p.Z, r11 = (x1 * p.Y + y1) * p.Z;
+  c.idx[0] = r00 + z0; c.w[0] = wx0 * wy0 * wz0;
+  c.idx[1] = r00 + z1; c.w[1] = wx0 * wy0 * wz1;
+  c.idx[2] = r01 + z0; c.w[2] = wx0 * wy1 * wz0;
+  c.idx[3] = r01 + z1; c.w[3] = wx0 * wy1 * wz1;
+  c.idx[4] = r10 + z0; c.w[4] = wx1 * wy0 * wz0;
+  c.idx[5] = r10 + z1; c.w[5] = wx1 * wy0 * wz1;
+  c.idx[6] = r11 + z0; c.w[6] = wx1 * wy1 * wz0;
+  c.idx[7] = r11 + z1; c.w[7] = wx1 * wy1 * wz1;
+}
+
+__device__ __forceinline__ float f4_get(const float4& v, int k) {
+  return k == 0 ? v.x : (k == 1 ? v.y : (k == 2 ? v.z : v.w));
+}
+__device__ __forceinline__ void f4_set(float4& v, int k, float x) {
+  if (k == 0) v.x = x; else if (k == 1) v.y = x; else if (k == 2) v.z = x; else v.w = x;
+}
+
+// post-activation and its derivative w.r.t. the interpolated (pre-activated) density
+__device__ __forceinline__ float post_act(int kind, float x, float& dydx) {
+  if (kind == kPostRelu) {
+    dydx = (x > 0.f) ? 1.f : 0.f;
+    return fmaxf(x, 0.f);
+  }
+  if (kind == kPostSoftplus) {  // torch.nn.Softplus(beta=1, threshold=20)
+    if (x > 20.f) {
+      dydx = 1.f;
+      return x;
+    }
+    const float e = expf(x);
+    dydx = e / (1.f + e);
+    return log1pf(e);
+  }
+  dydx = 1.f;
+  return x;
+}
+
+// 16-byte vector reduction into global memory (REDG.E.ADD.F32x4 on sm_100a).
+__device__ __forceinline__ void red_add_v4(float4* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+// Everything a thread needs to know about its ray.
+struct RayCtx {
+  float o[3], d[3];
+  float near, far, inv_near, inv_far, dnorm;
+  bool disparity;
+};
+
+__device__ __forceinline__ void load_ray(const KParams& p, int ray, RayCtx& rc) {
+  const float* po = p.rays_o + 3 * (size_t)ray;
+  const float* pd = p.rays_d + 3 * (size_t)ray;
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    rc.o[a] = __ldg(po + a);
+    rc.d[a] = __ldg(pd + a);
+  }
+  ray_interval(p, rc.o, rc.d, rc.near, rc.far);
+  rc.disparity = (p.flags & kDisparity) && !(p.flags & kAabb);  // renderers.py:66-78
+  rc.inv_near = rc.inv_far = 0.f;
+  if (rc.disparity) {
+    rc.inv_near = __fdiv_rn(1.0f, __fadd_rn(rc.near, kZeroPlus));
+    rc.inv_far = __fdiv_rn(1.0f, rc.far);
+  }
+  rc.dnorm = sqrtf(rc.d[0] * rc.d[0] + rc.d[1] * rc.d[1] + rc.d[2] * rc.d[2]);
+}
+
+// Depths z'[0..L] of samples i0 .. i0+L (the extra one closes the last interval), with stratified jitter
+// when requested (sample.py:57-64).  Entries beyond S-1 are left at the last valid depth.
+template <int L>
+__device__ __forceinline__ void segment_depths(const KParams& p, const RayCtx& rc, int ray, int i0, float (&z)[L + 1]) {
+  const int S = p.S;
+  if (!(p.flags & kPerturb)) {
+#pragma unroll
+    for (int j = 0; j <= L; ++j) {
+      const int i = min(i0 + j, S - 1);
+      z[j] = depth_plain(p, rc.near, rc.far, rc.inv_near, rc.inv_far, rc.disparity, i);
+    }
+    return;
+  }
+  // plain depths i0-1 .. i0+L+1
+  float zp[L + 3];
+#pragma unroll
+  for (int j = 0; j < L + 3; ++j) {
+    const int i = min(max(i0 - 1 + j, 0), S - 1);
+    zp[j] = depth_plain(p, rc.near, rc.far, rc.inv_near, rc.inv_far, rc.disparity, i);
+  }
+  const float* u = p.jitter + (size_t)ray * S;
+#pragma unroll
+  for (int j = 0; j <= L; ++j) {
+    const int i = i0 + j;  // samples past S-1 get a finite but unused value
+    const float zi = zp[j + 1];
+    const float lower = (i == 0) ? zi : __fmul_rn(0.5f, __fadd_rn(zi, zp[j]));
+    const float upper = (i >= S - 1) ? zi : __fmul_rn(0.5f, __fadd_rn(zp[j + 2], zi));
+    z[j] = __fadd_rn(lower, __fmul_rn(__fsub_rn(upper, lower), __ldg(u + min(i, S - 1))));
+  }
+}
+
+}  // namespace voxe

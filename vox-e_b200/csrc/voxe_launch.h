@@ -1,0 +1,21 @@
+// voxe_launch.h -- host-side declarations shared by the translation units of libvoxe_sm100a.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace voxe {
+
+struct KParams;
+
+// fused ray-marcher (voxe_render.cu)
+cudaError_t launch_render(const KParams& p, int sh_degree, int n_colour, int samples_per_thread, bool backward,
+                          cudaStream_t stream);
+int max_threads_per_cta();
+
+// full-grid passes (voxe_grid_ops.cu)
+cudaError_t launch_pack_grid(const float* densities, const float* features, float* packed, int64_t n_voxels,
+                             int n_features, int channels, cudaStream_t stream);
+cudaError_t launch_unpack_grad(const float* packed_grad, float* d_densities, float* d_features, int64_t n_voxels,
+                               int n_features, int channels, bool accumulate, cudaStream_t stream);
+
+}  // namespace voxe

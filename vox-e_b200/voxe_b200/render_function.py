@@ -1,0 +1,243 @@
+"""Autograd bridge between torch tensors and the C ABI (``voxe_render_fwd`` / ``voxe_render_bwd``).
+
+``fused_render`` is what ``thre3d_atom.thre3d_reprs.renderers.render_sh_voxel_grid`` calls: it replaces the reference's
+sampler -> point processor -> accumulator chain (render_interface.py:140-171) and its autograd graph with one
+forward kernel and one backward kernel.  The backward recomputes the forward per ray, so nothing of size
+O(rays x samples) is kept between the two (the reference retains ~35 such tensors).
+
+Gradients w.r.t. ``densities`` [X,Y,Z,1] and ``features`` [X,Y,Z,F] are returned as dense tensors shaped like the
+parameters, as autograd would have produced.  Rays never receive gradients (they never require them upstream:
+``cast_rays`` builds them from poses, misc.py:30-50).
+"""
+from __future__ import annotations
+
+import dataclasses
+from typing import Optional, Tuple
+
+import numpy as np
+import torch
+from torch import Tensor
+
+from voxe_b200 import _native as nat
+
+
+@dataclasses.dataclass(frozen=True)
+class FusedGridSpec:
+    """Geometry + activations of a voxel grid in the form the kernels take (VoxeGridDesc of include/voxe.h)."""
+
+    dims: Tuple[int, int, int]
+    n_features: int
+    aabb: Tuple[Tuple[float, float], Tuple[float, float], Tuple[float, float]]  # python doubles, voxels.py:198-223
+    density_scale: float
+    preact: int
+    postact: int
+
+    @property
+    def channels(self) -> int:
+        return ((self.n_features + 1 + 3) // 4) * 4
+
+    def to_native(self) -> nat.VoxeGridDesc:
+        d = nat.VoxeGridDesc()
+        for a in range(3):
+            lo32, hi32 = np.float32(self.aabb[a][0]), np.float32(self.aabb[a][1])
+            # adjust_dynamic_range(..., drange_out=(-1, 1), slack=True): numpy fp32 arithmetic (imaging_utils.py:57-63)
+            scale = (np.float32(1.0) - np.float32(-1.0)) / (hi32 - lo32)
+            bias = np.float32(-1.0) - lo32 * scale
+            d.dims[a] = int(self.dims[a])
+            d.aabb_lo[a], d.aabb_hi[a] = float(lo32), float(hi32)
+            d.norm_scale[a], d.norm_bias[a] = float(scale), float(bias)
+        d.n_features = int(self.n_features)
+        d.channels = int(self.channels)
+        d.density_scale = float(self.density_scale)
+        d.preact, d.postact = int(self.preact), int(self.postact)
+        return d
+
+
+@dataclasses.dataclass(frozen=True)
+class FusedRenderSpec:
+    """One render call (VoxeRenderDesc of include/voxe.h)."""
+
+    num_samples: int
+    near: float
+    far: float
+    flags: int
+    sh_degree: int
+    n_colour: int
+    noise_std: float = 0.0
+
+    def to_native(self) -> nat.VoxeRenderDesc:
+        r = nat.VoxeRenderDesc()
+        r.num_samples, r.near, r.far = int(self.num_samples), float(self.near), float(self.far)
+        r.flags, r.sh_degree, r.n_colour, r.noise_std = int(self.flags), int(self.sh_degree), int(self.n_colour), float(self.noise_std)
+        return r
+
+
+def _ptr(t: Optional[Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _require_cuda(*tensors: Tensor) -> torch.device:
+    dev = tensors[0].device
+    if dev.type != "cuda":
+        raise RuntimeError(
+            "the fused Vox-E render path runs on CUDA only (tensors are on "
+            f"'{dev}'); there is deliberately no CPU fallback in this package"
+        )
+    for t in tensors:
+        if t.device != dev:
+            raise RuntimeError(f"all render inputs must live on one device (got {t.device} and {dev})")
+        if t.dtype != torch.float32:
+            raise TypeError(f"the render path computes in fp32 (got {t.dtype})")
+    return dev
+
+
+def _stream_ptr(dev: torch.device) -> int:
+    return torch.cuda.current_stream(dev).cuda_stream
+
+
+def pack_volume(spec: FusedGridSpec, densities: Tensor, features: Tensor, out: Optional[Tensor] = None) -> Tensor:
+    """packed[X,Y,Z,C] = concat(features, densities, 0-padding) via ``voxe_pack_grid``."""
+    dev = _require_cuda(densities, features)
+    lib = nat.load_library()
+    dens, feat = densities.detach().contiguous(), features.detach().contiguous()
+    if out is None:
+        out = torch.empty((*spec.dims, spec.channels), dtype=torch.float32, device=dev)
+    gd = spec.to_native()
+    with torch.cuda.device(dev):
+        nat.check(lib.voxe_pack_grid(gd, dens.data_ptr(), feat.data_ptr(), out.data_ptr(), _stream_ptr(dev)), "voxe_pack_grid")
+    return out
+
+
+class PackedVolumeCache:
+    """Keeps the packed volume of a (densities, features) pair until either tensor is replaced or written to.
+
+    Callers of the reference API both mutate parameters in place (optimiser steps, ``.data`` writes) and replace
+    them wholesale (voxels.py:145-163 setters; attn_grid_trainer.py:546-550), so staleness is detected from
+    ``data_ptr`` + ``_version`` of both tensors on every call.  ``.data`` writes do not bump ``_version``: callers that
+    do that must call :meth:`invalidate`.
+    """
+
+    def __init__(self) -> None:
+        self._key = None
+        self._packed: Optional[Tensor] = None
+
+    def invalidate(self) -> None:
+        self._key = None
+
+    def get(self, spec: FusedGridSpec, densities: Tensor, features: Tensor) -> Tensor:
+        key = (densities.data_ptr(), densities._version, features.data_ptr(), features._version, densities.device, spec)
+        if key != self._key or self._packed is None:
+            reuse = self._packed
+            if reuse is not None and (reuse.device != densities.device or reuse.shape != (*spec.dims, spec.channels)):
+                reuse = None
+            self._packed = pack_volume(spec, densities, features, out=reuse)
+            self._key = key
+        return self._packed
+
+
+class _FusedRender(torch.autograd.Function):
+    """colour, depth, acc, disparity = render(densities, features | rays, jitter, noise)."""
+
+    @staticmethod
+    def forward(ctx, densities, features, packed, rays_o, rays_d, jitter, noise, gspec: FusedGridSpec, rspec: FusedRenderSpec):
+        dev = _require_cuda(packed, rays_o, rays_d)
+        lib = nat.load_library()
+        R = rays_o.shape[0]
+        colour = torch.empty((R, rspec.n_colour), dtype=torch.float32, device=dev)
+        depth = torch.empty((R, 1), dtype=torch.float32, device=dev)
+        acc = torch.empty((R, 1), dtype=torch.float32, device=dev)
+        disp = torch.empty((R, 1), dtype=torch.float32, device=dev)
+        gd, rd = gspec.to_native(), rspec.to_native()
+        with torch.cuda.device(dev):
+            nat.check(
+                lib.voxe_render_fwd(gd, rd, packed.data_ptr(), rays_o.data_ptr(), rays_d.data_ptr(), _ptr(jitter), _ptr(noise),
+                                    colour.data_ptr(), depth.data_ptr(), acc.data_ptr(), disp.data_ptr(), R, _stream_ptr(dev)),
+                "voxe_render_fwd",
+            )
+        ctx.set_materialize_grads(False)
+        ctx.gspec, ctx.rspec = gspec, rspec
+        ctx.save_for_backward(densities, features, packed, rays_o, rays_d, jitter, noise)
+        return colour, depth, acc, disp
+
+    @staticmethod
+    def backward(ctx, g_colour, g_depth, g_acc, g_disp):
+        densities, features, packed, rays_o, rays_d, jitter, noise = ctx.saved_tensors
+        need_d, need_f = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        none9 = (None,) * 9
+        if not (need_d or need_f):
+            return none9
+        gspec, rspec = ctx.gspec, ctx.rspec
+        dev = packed.device
+        lib = nat.load_library()
+        R = rays_o.shape[0]
+        d_dens = torch.zeros_like(densities, memory_format=torch.contiguous_format) if need_d else None
+        d_feat = torch.zeros_like(features, memory_format=torch.contiguous_format) if need_f else None
+        if all(g is None for g in (g_colour, g_depth, g_acc, g_disp)):
+            return (d_dens, d_feat) + (None,) * 7
+        if g_colour is None:
+            g_colour = torch.zeros((R, rspec.n_colour), dtype=torch.float32, device=dev)
+        gs = [None if g is None else g.contiguous().float() for g in (g_colour, g_depth, g_acc, g_disp)]
+        packed_grad = torch.zeros_like(packed)
+        gd, rd = gspec.to_native(), rspec.to_native()
+        with torch.cuda.device(dev):
+            s = _stream_ptr(dev)
+            nat.check(
+                lib.voxe_render_bwd(gd, rd, packed.data_ptr(), rays_o.data_ptr(), rays_d.data_ptr(), _ptr(jitter), _ptr(noise),
+                                    _ptr(gs[0]), _ptr(gs[1]), _ptr(gs[2]), _ptr(gs[3]), packed_grad.data_ptr(), R, s),
+                "voxe_render_bwd",
+            )
+            nat.check(lib.voxe_unpack_grad(gd, packed_grad.data_ptr(), _ptr(d_dens), _ptr(d_feat), 0, s), "voxe_unpack_grad")
+        return (d_dens, d_feat) + (None,) * 7
+
+
+def _prep_rays(rays_o: Tensor, rays_d: Tensor) -> Tuple[Tensor, Tensor]:
+    assert rays_o.dim() == 2 and rays_d.dim() == 2, "Please note that the RENDER interface only works with FLAT RAYS!"
+    assert rays_o.shape == rays_d.shape and rays_o.shape[-1] == 3
+    return rays_o.detach().float().contiguous(), rays_d.detach().float().contiguous()
+
+
+def fused_render(
+    gspec: FusedGridSpec,
+    rspec: FusedRenderSpec,
+    densities: Tensor,
+    features: Tensor,
+    rays_o: Tensor,
+    rays_d: Tensor,
+    cache: Optional[PackedVolumeCache] = None,
+    jitter: Optional[Tensor] = None,
+    noise: Optional[Tensor] = None,
+    generator: Optional[torch.Generator] = None,
+) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+    """Render flat rays through the fused kernels.  Returns (colour [R,C], depth [R,1], acc [R,1], disparity [R,1]).
+
+    ``jitter`` / ``noise`` default to fresh ``torch.rand`` / ``torch.randn`` draws on the rays' device -- the same
+    generator, shapes and order as sample.py:63 and accumulate.py:59-62 -- when the render spec needs them.
+    """
+    dev = _require_cuda(densities, features, rays_o, rays_d)
+    rays_o, rays_d = _prep_rays(rays_o, rays_d)
+    R, S = rays_o.shape[0], rspec.num_samples
+    if rspec.flags & nat.FLAG_PERTURB:
+        if jitter is None:
+            jitter = torch.rand(R, S, dtype=torch.float32, device=dev, generator=generator)
+        assert jitter.shape == (R, S)
+        jitter = jitter.detach().float().contiguous()
+    else:
+        jitter = None
+    if rspec.noise_std != 0.0:
+        if noise is None:
+            noise = torch.randn(R, S, dtype=torch.float32, device=dev, generator=generator)
+        assert noise.shape == (R, S)
+        noise = noise.detach().float().contiguous()
+    else:
+        noise = None
+    packed = (cache or PackedVolumeCache()).get(gspec, densities, features)
+    if R == 0:
+        z = torch.zeros((0, 1), dtype=torch.float32, device=dev)
+        return torch.zeros((0, rspec.n_colour), dtype=torch.float32, device=dev), z, z.clone(), z.clone()
+    return _FusedRender.apply(densities, features, packed, rays_o, rays_d, jitter, noise, gspec, rspec)
+
+
+def fused_render_attn(*args, **kwargs):
+    """Attention-grid twin (renderers.py:108-163): same kernels with VOXE_FLAG_ATTN set in the render spec and the
+    1-channel attention volume passed as ``features``."""
+    return fused_render(*args, **kwargs)
