@@ -1,0 +1,552 @@
+#!/usr/bin/env python
+"""bench.py -- rays/s forward+backward of the fused ray-marcher on BASELINE.json's headline workload.
+
+Workload (``configs[1]`` of BASELINE.json, SURVEY.md 8d "cfg 2"): 160^3 SH-0 ReLU-field grid, U(-1,1) values (seed 42),
+density scale 33.333, world box [-1.5,1.5]^3; 400x400 pinhole camera f=555.5 on the r=4.0311 turn-table
+(``get_thre360_animation_poses(4.0311, 60, 9)`` -> 8 poses); S=256 samples on [1.8, 6.6], stratified jitter on, white
+background; every frame is rendered as 40 consecutive flat-index batches of <= 4096 rays, each batch forward AND backward
+(upstream gradient = a fixed dense dL/dcolour, i.e. loss = <colour, G>).
+
+A *step* is one frame = 160 000 rays = 40 x (jitter draw, forward kernel, backward kernel accumulating into the packed
+gradient volume) + one gradient zero-fill + one unpack of the packed gradient into d_densities / d_features (+ one NCCL
+all-reduce of the packed gradient when N > 1: each rank renders its own pose -- weak scaling).
+
+  value     device-resident throughput: the step above replayed as a CUDA graph over C-ABI launches, inputs in HBM
+  e2e       the same frame through the public API (``VolumetricModel.render_rays`` + ``.backward()``) with rays and
+            upstream gradients starting in pinned HOST memory and loss + colour read back every step
+  roofline  the backward kernel (dominant) timed alone with CUDA events: algorithmic bytes / duration vs measured HBM peak
+  cpu_baseline  the oracle port (PyTorch fp32, all host threads) on a bounded sample of the same batches
+
+``--impl reference`` times only the CPU leg (the reference is pure Python/PyTorch and does not travel to the GPU box;
+``oracle/voxe_oracle.py`` is its pinned restatement), one 4096-ray batch forward+backward per step.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+for _p in (ROOT, ROOT / "vox-e_b200"):
+    if str(_p) not in sys.path:
+        sys.path.insert(0, str(_p))
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+# ---------------------------------------------------------------------------------------------------------
+# workload definition (cfg 2)
+# ---------------------------------------------------------------------------------------------------------
+WL = dict(
+    name="cfg2: 160^3 SH-0 grid, 400x400 render, 4096-ray batches fwd+bwd, S=256",
+    dims=(160, 160, 160), sh_degree=0, world=(3.0, 3.0, 3.0), density_scale=33.333, preact="identity", postact="relu",
+    height=400, width=400, focal=555.5, radius=4.0311, pitch=60.0, num_poses=9, S=256, near=1.8, far=6.6,
+    batch=4096, perturb=True, white_bkgd=True, seed=42,
+)
+BYTES_PER_SAMPLE_FWD = 8 * 4 * 4          # 8 corners x (F+1)=4 channels x 4 B: the forward gather
+BYTES_PER_SAMPLE_BWD = 2 * 8 * 4 * 4      # backward re-gather + scatter-add payload
+BYTES_PER_RAY_FWD = 24 + 24               # ray read + outputs
+BYTES_PER_RAY_BWD = 24 + 24               # ray read + upstream gradients
+
+
+def measured_hbm_peak():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        return float(json.loads(p.read_text())["hbm_gbs"]), "of measured (MEASURED_PEAKS.json)"
+    return 6650.0, "of fallback (B200_PROFILING.md)"
+
+
+def make_grid_tensors(device):
+    g = torch.Generator().manual_seed(WL["seed"])
+    dens = (torch.rand((*WL["dims"], 1), generator=g) * 2 - 1).to(device)
+    feat = (torch.rand((*WL["dims"], 3), generator=g) * 2 - 1).to(device)
+    return dens, feat
+
+
+def make_poses():
+    from thre3d_atom.utils.imaging_utils import get_thre360_animation_poses
+
+    return get_thre360_animation_poses(WL["radius"], WL["pitch"], WL["num_poses"])
+
+
+def frame_rays(pose, device):
+    from thre3d_atom.rendering.volumetric.utils.misc import cast_rays, flatten_rays
+    from thre3d_atom.utils.imaging_utils import CameraIntrinsics
+
+    rays = flatten_rays(cast_rays(CameraIntrinsics(WL["height"], WL["width"], WL["focal"]), pose, device=device))
+    return rays.origins.contiguous(), rays.directions.contiguous()
+
+
+def count_inside_samples(rays_o, rays_d):
+    """S_in as SURVEY.md 8d defines it: in-AABB samples at the un-jittered depths (strict compare), per frame."""
+    t = torch.linspace(0.0, 1.0, WL["S"], device=rays_o.device)
+    z = WL["near"] * (1.0 - t) + WL["far"] * t
+    half = [w / 2 for w in WL["world"]]
+    total = 0
+    per_batch = []
+    for s in range(0, rays_o.shape[0], WL["batch"]):
+        o, d = rays_o[s : s + WL["batch"]], rays_d[s : s + WL["batch"]]
+        pts = o[:, None, :] + d[:, None, :] * z[None, :, None]
+        inside = torch.ones(pts.shape[:2], dtype=torch.bool, device=pts.device)
+        for a in range(3):
+            inside &= (pts[..., a] > -half[a]) & (pts[..., a] < half[a])
+        n = int(inside.sum().item())
+        per_batch.append(n)
+        total += n
+    return total, per_batch
+
+
+# ---------------------------------------------------------------------------------------------------------
+# clocks sampler (nvidia-smi during the timed region)
+# ---------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    QUERY = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, smax, power, reasons = [], None, [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.lines:
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                smax = float(parts[1])
+                power.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": smax, "power_w_max": max(power) if power else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ---------------------------------------------------------------------------------------------------------
+# CPU leg: the oracle port, PyTorch fp32 on the host cores
+# ---------------------------------------------------------------------------------------------------------
+def cpu_leg(steps, warmup, budget_s=None):
+    """One step = one 4096-ray batch of pose 0 forward+backward through the oracle in fp32.  Returns rays/s etc."""
+    from oracle.voxe_oracle import OracleConfig, OracleGrid, render_oracle_with_grads
+
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    dens, feat = make_grid_tensors("cpu")
+    rays_o, rays_d = frame_rays(make_poses()[0], torch.device("cpu"))
+    grid = OracleGrid(tuple(w / d for w, d in zip(WL["world"], WL["dims"])), density_scale=WL["density_scale"],
+                      preact=WL["preact"], postact=WL["postact"])
+    cfg = OracleConfig(num_samples=WL["S"], near=WL["near"], far=WL["far"], perturb=True, white_bkgd=True)
+    g = torch.Generator().manual_seed(1)
+    B = WL["batch"]
+    n_batches = rays_o.shape[0] // B
+    times = []
+    t_begin = time.perf_counter()
+    for k in range(warmup + steps):
+        b = (17 + k) % n_batches  # start mid-frame so the batches cross the object
+        o, d = rays_o[b * B : (b + 1) * B], rays_d[b * B : (b + 1) * B]
+        gcol = torch.randn(B, 3, generator=g)
+        t0 = time.perf_counter()
+        jitter = torch.rand(B, WL["S"], generator=g)
+        render_oracle_with_grads(dens, feat, grid, o, d, cfg, gcol, jitter=jitter, dtype=torch.float32)
+        dt = time.perf_counter() - t0
+        if k >= warmup:
+            times.append(dt)
+        if budget_s is not None and k >= warmup and time.perf_counter() - t_begin > budget_s:
+            break
+    total = sum(times)
+    return {"rays_per_s": B * len(times) / total, "ms_per_step": 1e3 * total / len(times), "steps": len(times), "cores": threads,
+            "sample": f"{len(times)} batches of {B} rays (pose 0, batches 17..) fwd+bwd, fp32, after {warmup} warm-up"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    r = cpu_leg(args.steps, args.warmup)
+    line = {
+        "impl": "reference", "metric": "rays/s fwd+bwd, 160^3 SH-0 grid, 400x400 render", "value": r["rays_per_s"], "unit": "rays/s",
+        "n_gpus": args.gpus, "steps": r["steps"], "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WL["name"], "step": "one 4096-ray batch fwd+bwd on the host CPU (bounded sample of the frame)"},
+        "cpu_baseline": {"value": r["rays_per_s"], "unit": "rays/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]},
+        "e2e": {"value": r["rays_per_s"], "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# GPU legs
+# ---------------------------------------------------------------------------------------------------------
+class DeviceBench:
+    """Drives the C ABI directly (ctypes) on device-resident inputs; frames are captured as CUDA graphs."""
+
+    N_GRID_COPIES = 3  # rotating copies: 3 x 65.5 MB of grid + 65.5 MB of gradients >> 126 MB L2
+
+    def __init__(self, device, rank, world, count_s_in=True):
+        from voxe_b200 import _native as nat
+        from voxe_b200.render_function import FusedGridSpec, FusedRenderSpec, pack_volume
+
+        self.nat, self.lib = nat, nat.load_library()
+        self.device, self.rank, self.world = device, rank, world
+        dens, feat = make_grid_tensors(device)
+        half = [w / 2 for w in WL["world"]]
+        self.gspec = FusedGridSpec(dims=WL["dims"], n_features=3, aabb=tuple((-h, h) for h in half), density_scale=WL["density_scale"],
+                                   preact=nat.PREACT_IDENTITY, postact=nat.POSTACT_RELU)
+        flags = nat.FLAG_WHITE_BKGD | (nat.FLAG_PERTURB if WL["perturb"] else 0)
+        self.rspec = FusedRenderSpec(num_samples=WL["S"], near=WL["near"], far=WL["far"], flags=flags, sh_degree=0, n_colour=3)
+        self.gd, self.rd = self.gspec.to_native(), self.rspec.to_native()
+        self.dens, self.feat = dens, feat
+        self.packed = [pack_volume(self.gspec, dens, feat) for _ in range(self.N_GRID_COPIES)]
+        self.packed_grad = torch.zeros_like(self.packed[0])
+        self.d_dens, self.d_feat = torch.empty_like(dens), torch.empty_like(feat)
+        self.poses = make_poses()
+        self.rays = [frame_rays(p, device) for p in self.poses]
+        self.R = self.rays[0][0].shape[0]
+        g = torch.Generator().manual_seed(7)
+        self.G = torch.randn(self.R, 3, generator=g).to(device)
+        self.colour = torch.empty(self.R, 3, device=device)
+        self.depth = torch.empty(self.R, device=device)
+        self.acc = torch.empty(self.R, device=device)
+        self.disp = torch.empty(self.R, device=device)
+        self.jitter2 = [torch.rand(WL["batch"], WL["S"], device=device) for _ in range(2)]
+        self.jitter = self.jitter2[0]
+        self.side = torch.cuda.Stream(device)
+        self.saved = torch.empty(int(self.lib.voxe_saved_floats(self.rd, WL["batch"])), device=device)
+        self.batches = [(s, min(s + WL["batch"], self.R)) for s in range(0, self.R, WL["batch"])]
+        self.s_in = [count_inside_samples(o, d) for (o, d) in self.rays] if count_s_in else None
+        self.kernels_per_step = 2 * len(self.batches) + 1
+
+    def _stream(self):
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def _fwd(self, pose, copy, b0, b1, saved):
+        o, d = self.rays[pose]
+        self.nat.check(self.lib.voxe_render_fwd(
+            self.gd, self.rd, self.packed[copy].data_ptr(), o[b0:b1].data_ptr(), d[b0:b1].data_ptr(),
+            self.jitter.data_ptr() if WL["perturb"] else None, None, self.colour[b0:b1].data_ptr(), self.depth[b0:b1].data_ptr(),
+            self.acc[b0:b1].data_ptr(), self.disp[b0:b1].data_ptr(), saved.data_ptr(), b1 - b0, self._stream()), "voxe_render_fwd")
+
+    def _bwd(self, pose, copy, b0, b1, saved):
+        o, d = self.rays[pose]
+        self.nat.check(self.lib.voxe_render_bwd(
+            self.gd, self.rd, self.packed[copy].data_ptr(), o[b0:b1].data_ptr(), d[b0:b1].data_ptr(),
+            self.jitter.data_ptr() if WL["perturb"] else None, None, saved.data_ptr(), self.G[b0:b1].data_ptr(), None, None, None,
+            self.packed_grad.data_ptr(), b1 - b0, self._stream()), "voxe_render_bwd")
+
+    def unpack(self):
+        self.nat.check(self.lib.voxe_unpack_grad(self.gd, self.packed_grad.data_ptr(), self.d_dens.data_ptr(), self.d_feat.data_ptr(), 0,
+                                                 self._stream()), "voxe_unpack_grad")
+
+    def frame_body(self, pose, copy, what="both", saved_set=None, refresh_jitter=True):
+        """One frame.  ``saved_set``: per-batch workspaces (needed when fwd and bwd of a batch are not adjacent).
+        The jitter draw of batch k+1 (torch.rand, sample.py:63) runs on a side stream while batch k renders; two jitter
+        buffers alternate."""
+        main = torch.cuda.current_stream(self.device)
+        draw = what == "both" and WL["perturb"] and refresh_jitter
+        if what == "both":
+            self.packed_grad.zero_()
+        if draw:
+            self.side.wait_stream(main)
+        done = {}
+        for k, (b0, b1) in enumerate(self.batches):
+            saved = self.saved if saved_set is None else saved_set[k]
+            if draw:
+                self.jitter = self.jitter2[k % 2]
+                with torch.cuda.stream(self.side):
+                    if k >= 2:
+                        self.side.wait_event(done[k - 2])
+                    self.jitter.uniform_()
+                    ready = torch.cuda.Event()
+                    ready.record(self.side)
+                main.wait_event(ready)
+            if what in ("both", "fwd"):
+                self._fwd(pose, copy, b0, b1, saved)
+            if what in ("both", "bwd"):
+                self._bwd(pose, copy, b0, b1, saved)
+            if draw:
+                done[k] = torch.cuda.Event()
+                done[k].record(main)
+        if draw:
+            main.wait_stream(self.side)
+
+    def capture(self, what="both", poses=None):
+        graphs = []
+        for n, pose in enumerate(poses if poses is not None else range(len(self.poses))):
+            copy = n % self.N_GRID_COPIES
+            saved_set = None
+            if what != "both":  # isolated kernels: fixed jitter, per-batch workspaces filled by a full pass first
+                saved_set = [torch.empty_like(self.saved) for _ in self.batches]
+                self.frame_body(pose, copy, "both", saved_set, refresh_jitter=False)
+            self.frame_body(pose, copy, what, saved_set)  # warm (lazy module load, allocator)
+            torch.cuda.synchronize(self.device)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self.frame_body(pose, copy, what, saved_set)
+            graphs.append(g)
+            self._keep = getattr(self, "_keep", []) + [saved_set]
+        return graphs
+
+    def time_graphs(self, graphs, steps, warmup, after_replay=None, barrier=None):
+        n = len(graphs)
+        for k in range(warmup):
+            graphs[(k * self.world + self.rank) % n].replay()
+            if after_replay:
+                after_replay()
+        start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if barrier:
+            barrier()
+        torch.cuda.synchronize(self.device)
+        start.record()
+        for k in range(steps):
+            graphs[((warmup + k) * self.world + self.rank) % n].replay()
+            if after_replay:
+                after_replay()
+        stop.record()
+        torch.cuda.synchronize(self.device)
+        if barrier:
+            barrier()
+        return start.elapsed_time(stop)  # ms
+
+
+def e2e_leg(device, rank, world, steps, warmup, dist):
+    """The frame through the public API, inputs starting in pinned host memory."""
+    from thre3d_atom.modules.volumetric_model import VolumetricModel
+    from thre3d_atom.rendering.volumetric.render_interface import Rays
+    from thre3d_atom.thre3d_reprs.renderers import SHVoxGridRenderConfig, render_sh_voxel_grid
+    from thre3d_atom.thre3d_reprs.voxels import VoxelGrid, VoxelSize
+    from thre3d_atom.utils.imaging_utils import CameraBounds
+
+    dens, feat = make_grid_tensors(device)
+    grid = VoxelGrid(dens, feat, VoxelSize(*(w / d for w, d in zip(WL["world"], WL["dims"]))), density_preactivation=torch.nn.Identity(),
+                     density_postactivation=torch.nn.ReLU(), expected_density_scale=WL["density_scale"], tunable=True)
+    vm = VolumetricModel(grid, render_sh_voxel_grid,
+                         SHVoxGridRenderConfig(num_samples_per_ray=WL["S"], camera_bounds=CameraBounds(WL["near"], WL["far"]),
+                                               white_bkgd=True, perturb_sampled_points=WL["perturb"]), device=device)
+    poses = make_poses()
+    host = []
+    g = torch.Generator().manual_seed(7)
+    for p in poses:
+        o, d = frame_rays(p, torch.device("cpu"))
+        host.append((o.pin_memory(), d.pin_memory(), torch.randn(o.shape[0], 3, generator=g).pin_memory()))
+    R, B = host[0][0].shape[0], WL["batch"]
+    colour_host = torch.empty(R, 3).pin_memory()
+    h2d = R * (12 + 12 + 12)
+    d2h = R * 12 + 4
+
+    def one_frame(idx):
+        o_h, d_h, g_h = host[idx % len(host)]
+        grid.densities.grad = None
+        grid.features.grad = None
+        loss_total = torch.zeros((), device=device)
+        for s in range(0, R, B):
+            o = o_h[s : s + B].to(device, non_blocking=True)
+            d = d_h[s : s + B].to(device, non_blocking=True)
+            gc = g_h[s : s + B].to(device, non_blocking=True)
+            out = vm.render_rays(Rays(o, d))
+            loss = (out.colour * gc).sum()
+            loss.backward()
+            loss_total += loss.detach()
+            colour_host[s : s + B].copy_(out.colour.detach(), non_blocking=True)
+        if world > 1:
+            dist.all_reduce(grid.densities.grad)
+            dist.all_reduce(grid.features.grad)
+        return float(loss_total.item())  # D2H of the step's result; also orders the colour copy
+
+    for k in range(warmup):
+        one_frame(k * world + rank)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(device)
+    t0 = time.perf_counter()
+    for k in range(steps):
+        one_frame((warmup + k) * world + rank)
+    torch.cuda.synchronize(device)
+    elapsed = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([elapsed], device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed = float(t.item())
+    return {"value": world * R * steps / elapsed, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+            "ms_per_step": 1e3 * elapsed / steps, "steps": steps, "api": "VolumetricModel.render_rays + backward, 4096-ray batches"}
+
+
+def run_ours(args):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback (use --impl reference for the CPU leg)")
+    device = torch.device(f"cuda:{local}")
+    torch.cuda.set_device(device)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=device)
+    torch.manual_seed(WL["seed"] + rank)
+
+    bench = DeviceBench(device, rank, world, count_s_in=not (args.ncu or args.sweep))
+    barrier = (lambda: dist.barrier()) if world > 1 else None
+
+    if args.ncu:  # profiler mode: eager launches of whole frames, nothing else (numbers printed here are NOT bench values)
+        bench.frame_body(0, 0, "both")  # warm-up outside the profiled range
+        torch.cuda.synchronize(device)
+        torch.cuda.profiler.start()     # use with: ncu --profile-from-start off
+        for k in range(args.steps):
+            bench.frame_body((k + 1) % len(bench.poses), (k + 1) % bench.N_GRID_COPIES, "both")
+            bench.unpack()
+        torch.cuda.synchronize(device)
+        torch.cuda.profiler.stop()
+        print(json.dumps({"ncu_mode": True, "frames": args.steps, "kernels_per_frame": bench.kernels_per_step}))
+        return
+
+    def after_replay():
+        if world > 1:
+            dist.all_reduce(bench.packed_grad)  # ONE all-reduce of the packed voxel gradients per step
+        bench.unpack()
+
+    if args.sweep:  # tuning mode: (L, rays per CTA, register cap) grid, isolated kernels + whole frame; not a bench line
+        from voxe_b200 import _native as nat
+
+        for cfg in args.sweep.split(";"):
+            l, rpc, cap = (int(x) for x in cfg.split(","))
+            try:
+                nat.set_tuning(l, rpc, cap)
+                bench.saved = torch.empty(int(bench.lib.voxe_saved_floats(bench.rd, WL["batch"])), device=device)
+                res = {}
+                for what in ("fwd", "bwd", "both"):
+                    gs = bench.capture(what, poses=[0, 3, 5])
+                    t_ms = bench.time_graphs(gs, 12, 3)
+                    res[what] = round(1e3 * t_ms / (12 * len(bench.batches)), 2)
+                    del gs
+                    bench._keep = []
+                print(json.dumps({"sweep": cfg, "us_per_batch": res}), flush=True)
+            except Exception as exc:  # noqa: BLE001
+                print(json.dumps({"sweep": cfg, "error": str(exc)[:200]}), flush=True)
+        return
+
+    graphs = bench.capture("both")
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms = bench.time_graphs(graphs, args.steps, args.warmup, after_replay=after_replay, barrier=barrier)
+    clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        t = torch.tensor([ms], device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    ms_per_step = ms / args.steps
+    rays_per_s = world * bench.R / (ms_per_step * 1e-3)
+
+    # dominant kernel alone (rank 0, N=1 semantics; other ranks idle-wait at the barrier below)
+    peak, peak_note = measured_hbm_peak()
+    roof = None
+    if rank == 0:
+        s_in_mean = sum(t for t, _ in bench.s_in) / len(bench.s_in)
+        out = {}
+        for what, bps, bpr in (("bwd", BYTES_PER_SAMPLE_BWD, BYTES_PER_RAY_BWD), ("fwd", BYTES_PER_SAMPLE_FWD, BYTES_PER_RAY_FWD)):
+            gs = bench.capture(what, poses=[0, 3, 5])
+            bench.world, saved = 1, bench.world
+            t_ms = bench.time_graphs(gs, max(8, args.steps), 3)
+            bench.world = saved
+            per_launch_us = 1e3 * t_ms / (max(8, args.steps) * len(bench.batches))
+            bytes_per_launch = (s_in_mean * bps + bench.R * bpr) / len(bench.batches)
+            out[what] = (per_launch_us, bytes_per_launch)
+        bwd_us, bwd_bytes = out["bwd"]
+        fwd_us, fwd_bytes = out["fwd"]
+        achieved = bwd_bytes / (bwd_us * 1e-6) / 1e9
+        step_bytes = s_in_mean * (BYTES_PER_SAMPLE_FWD + BYTES_PER_SAMPLE_BWD) + bench.R * 96
+        step_gbs = step_bytes / (ms_per_step * 1e-3) / 1e9
+        roof = {
+            "bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": None,
+            "peak_source": peak_note, "kernel": "render_bwd_kernel<DEG=0,NCOL=3,L=8>", "us_per_launch": round(bwd_us, 2),
+            "algorithmic_bytes_per_launch": round(bwd_bytes), "fwd_kernel": {"us_per_launch": round(fwd_us, 2),
+            "achieved": round(fwd_bytes / (fwd_us * 1e-6) / 1e9, 1), "frac": round(fwd_bytes / (fwd_us * 1e-6) / 1e9 / peak, 4)},
+            "step": {"achieved": round(step_gbs / world, 1), "frac": round(step_gbs / world / peak, 4),
+                     "bytes_per_ray": round(step_bytes / bench.R, 1), "s_in_per_ray": round(s_in_mean / bench.R, 2)},
+        }
+    if world > 1:
+        dist.barrier()
+
+    e2e = e2e_leg(device, rank, world, max(2, min(args.steps, args.e2e_steps)), min(args.warmup, 3), dist)
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        r = cpu_leg(steps=6, warmup=1, budget_s=25.0)
+        cpu = {"value": r["rays_per_s"], "unit": "rays/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]}
+
+    if rank == 0:
+        line = {
+            "metric": "rays/s fwd+bwd, 160^3 SH-0 grid, 400x400 render", "value": rays_per_s, "unit": "rays/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WL["name"], "step": "one 400x400 frame = 40 batches x (jitter, fwd, bwd) + grad zero-fill + unpack"
+                       + (" + 1 NCCL all-reduce of packed voxel grads" if world > 1 else ""),
+                       "l2": "3 rotating grid copies (197 MB) + 65.5 MB gradient volume > 126 MB L2; 8 poses rotate",
+                       "parallelism": f"ray/view data parallel x{world}", "timing": "CUDA events around K graph replays, max over ranks"},
+            "e2e": e2e, "gpu_launches": args.steps * bench.kernels_per_step, "roofline": roof, "clocks": clocks,
+        }
+        if cpu:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--e2e-steps", type=int, default=8)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--ncu", action="store_true", help="profiler mode: run --steps eager frames and exit")
+    ap.add_argument("--sweep", type=str, default="", help="tuning sweep: 'L,rpc,cap;L,rpc,cap;...'")
+    ap.add_argument("--tune", type=str, default="", help="L,rpc,regcap launch-shape override for tuning runs")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    if args.tune:
+        from voxe_b200 import _native as nat
+
+        nat.set_tuning(*(int(x) for x in args.tune.split(",")))
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

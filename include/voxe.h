@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define VOXE_ABI_VERSION 1
+#define VOXE_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define VOXE_API __attribute__((visibility("default")))
@@ -113,29 +113,38 @@ VOXE_API int voxe_pack_grid(const VoxeGridDesc* grid, const float* densities, co
 VOXE_API int voxe_unpack_grad(const VoxeGridDesc* grid, const float* packed_grad, float* d_densities, float* d_features,
                      int accumulate, voxe_stream_t stream);
 
+/* Number of floats of the `saved` workspace that links a forward call to its backward call:
+ * (n_colour + 3) per ray and per depth segment (the transmittance at the segment start and the segment's local sums
+ * of w*colour, w*z, w).  It replaces the O(R*S) activations autograd keeps for the reference (~35 floats per sample)
+ * with < 1 float per sample.  Depends on the current voxe_set_tuning() state: do not retune between the two calls. */
+VOXE_API int64_t voxe_saved_floats(const VoxeRenderDesc* render, int64_t num_rays);
+
 /* Forward render of R rays.
  *   packed   [X,Y,Z,C]   from voxe_pack_grid
  *   rays_o/d [R,3]       origins / (un-normalised) directions
  *   jitter   [R,S] or NULL   the U[0,1) draws of sample.py:63 (required with VOXE_FLAG_PERTURB)
  *   noise    [R,S] or NULL   the N(0,1) draws of accumulate.py:59-62 (required when noise_std != 0)
- *   colour   [R,n_colour], depth [R], acc [R], disparity [R]   outputs (disparity may be NULL) */
+ *   colour   [R,n_colour], depth [R], acc [R], disparity [R]   outputs (disparity may be NULL)
+ *   saved    voxe_saved_floats() floats, or NULL when no backward will follow (inference) */
 VOXE_API int voxe_render_fwd(const VoxeGridDesc* grid, const VoxeRenderDesc* render, const float* packed,
                     const float* rays_o, const float* rays_d, const float* jitter, const float* noise,
-                    float* colour, float* depth, float* acc, float* disparity, int64_t num_rays,
+                    float* colour, float* depth, float* acc, float* disparity, float* saved, int64_t num_rays,
                     voxe_stream_t stream);
 
-/* Backward: recomputes the forward per ray (no O(R*S) activations are stored) and scatter-ADDS
- * dL/d(packed) into `packed_grad` [X,Y,Z,C] (caller-zeroed; accumulate-into, so several ray batches or both
- * renders of a training step can share one buffer).  g_depth / g_acc / g_disp may be NULL (treated as zero).
- * The disparity gradient is applied only on rays whose disparity is finite (depth/acc > 1e-10). */
+/* Backward: re-gathers per sample (no O(R*S) activations are stored), and scatter-ADDS dL/d(packed) into
+ * `packed_grad` [X,Y,Z,C] (caller-zeroed; accumulate-into, so several ray batches or both renders of a training step
+ * can share one buffer).  `saved` is the workspace the matching forward call filled (same grid, rays, jitter, noise).
+ * g_depth / g_acc / g_disp may be NULL (treated as zero).  The disparity gradient is applied only on rays whose
+ * disparity is finite (depth/acc > 1e-10). */
 VOXE_API int voxe_render_bwd(const VoxeGridDesc* grid, const VoxeRenderDesc* render, const float* packed,
                     const float* rays_o, const float* rays_d, const float* jitter, const float* noise,
-                    const float* g_colour, const float* g_depth, const float* g_acc, const float* g_disp,
-                    float* packed_grad, int64_t num_rays, voxe_stream_t stream);
+                    const float* saved, const float* g_colour, const float* g_depth, const float* g_acc,
+                    const float* g_disp, float* packed_grad, int64_t num_rays, voxe_stream_t stream);
 
-/* Launch-shape override for tuning runs: samples per thread (4 or 8) and rays per CTA (power of two <= 32);
- * 0 restores the built-in choice.  Does not change results beyond fp32 summation order. */
-VOXE_API int voxe_set_tuning(int samples_per_thread, int rays_per_cta);
+/* Launch-shape override for tuning runs: samples per thread (1..64), rays per CTA (power of two <= 32) and the
+ * register budget of the kernel variant (64 or 128); 0 restores the built-in choice of that knob.  Does not change
+ * results beyond fp32 summation order. */
+VOXE_API int voxe_set_tuning(int samples_per_thread, int rays_per_cta, int register_cap);
 
 /* Number of kernels this library has launched on the calling process since load (for bench accounting). */
 VOXE_API int64_t voxe_launch_count(void);

@@ -298,6 +298,57 @@ def render_oracle(
     }
 
 
+def relu_kink_voxels(
+    densities: Tensor,
+    grid: OracleGrid,
+    rays_o: Tensor,
+    rays_d: Tensor,
+    cfg: OracleConfig,
+    jitter: Optional[Tensor] = None,
+    margin: float = 2e-3,
+) -> Tensor:
+    """Bool mask [X,Y,Z] of the voxels that are trilinear corners of an in-grid sample whose interpolated
+    (pre-activated) density lies within ``margin`` of 0.
+
+    With a ReLU post-activation such a sample's derivative is decided by fp32 rounding (the reference, the fp64 truth
+    and any re-ordered fp32 evaluation may disagree), and a flip changes only that sample's own scatter into its 8
+    corner voxels of d_densities -- forward values and every other gradient entry move by < margin * delta.  Parity
+    tests therefore compare d_densities on the complement of this mask at the tight tolerance."""
+    dtype = torch.float64
+    dims = tuple(densities.shape[:3])
+    aabb = aabb_of(dims, grid)
+    ro32, rd32 = rays_o.to(torch.float32), rays_d.to(torch.float32)
+    near, far = ray_intervals(ro32, rd32, cfg, aabb, torch.float32)
+    z32 = sample_depths(near, far, cfg, jitter, torch.float32)
+    pts32 = (ro32[:, None, :] + rd32[:, None, :] * z32[:, :, None]).reshape(-1, 3)
+    inside = torch.ones(pts32.shape[0], dtype=torch.bool)
+    for a in range(3):
+        inside &= (pts32[:, a] > aabb[a][0]) & (pts32[:, a] < aabb[a][1])
+    pts = pts32.to(dtype)
+    pre = _activate(densities.to(dtype) * grid.density_scale, grid.preact)
+    sraw = trilinear_fetch(pre, pts, aabb, dtype)[:, 0]
+    amb = inside & (sraw.abs() < margin)
+    mask = torch.zeros(dims, dtype=torch.bool)
+    if not amb.any():
+        return mask
+    p = pts[amb]
+    idx0 = []
+    for a in range(3):
+        lo32, hi32 = np.float32(aabb[a][0]), np.float32(aabb[a][1])
+        scale = (np.float32(1.0) - np.float32(-1.0)) / (hi32 - lo32)
+        bias = np.float32(-1.0) - lo32 * scale
+        u = ((p[:, a] * float(scale) + float(bias) + 1.0) * dims[a] - 1.0) / 2.0
+        idx0.append(torch.floor(u).long())
+    for dx in (0, 1):  # the 2x2x2 footprint (a corner reached only through u's rounding noise has weight ~1e-5)
+        for dy in (0, 1):
+            for dz in (0, 1):
+                ix = (idx0[0] + dx).clamp(0, dims[0] - 1)
+                iy = (idx0[1] + dy).clamp(0, dims[1] - 1)
+                iz = (idx0[2] + dz).clamp(0, dims[2] - 1)
+                mask[ix, iy, iz] = True
+    return mask
+
+
 def render_oracle_with_grads(
     densities: Tensor,
     features: Tensor,

@@ -22,7 +22,15 @@ def _grad_tol(postact):
     return (2e-4, 1e-3) if postact == "relu" else (1e-4, 1e-4)
 
 
-def _compare(got, want, postact, what):
+def _kink_mask(meta, a):
+    """Voxels whose d_densities entry depends on a ReLU derivative decided by rounding (see relu_kink_voxels)."""
+    from oracle.voxe_oracle import relu_kink_voxels
+
+    grid, cfg = oracle_grid_cfg(meta)
+    return relu_kink_voxels(a["densities"], grid, a["rays_o"], a["rays_d"], cfg, jitter=a.get("jitter"))
+
+
+def _compare(got, want, postact, what, kink_mask=None):
     assert (got["colour"] - want["colour"].float()).abs().max().item() <= PIXEL_TOL, what
     assert (got["depth"] - want["depth"].float()).abs().max().item() <= DEPTH_TOL, what
     assert (got["accumulated_weight"] - want["accumulated_weight"].float()).abs().max().item() <= ACC_TOL, what
@@ -34,7 +42,14 @@ def _compare(got, want, postact, what):
         assert rel.max().item() <= 1e-3, what
     l2_tol, inf_tol = _grad_tol(postact)
     for key in ("d_densities", "d_features"):
-        l2, linf = grad_errors(got[key], want[key])
+        g, w = got[key], want[key]
+        if key == "d_densities" and kink_mask is not None:
+            # ReLU: drop the few voxels fed by a sample sitting on the kink, then hold everything else to the tight bar
+            assert kink_mask.float().mean().item() < 0.02, "kink mask should be a tiny fraction of the grid"
+            keep = (~kink_mask)[..., None]
+            g, w = g * keep, w * keep
+            l2_tol, inf_tol = 1e-4, 1e-4
+        l2, linf = grad_errors(g, w)
         assert l2 <= l2_tol and linf <= inf_tol, f"{what} {key}: relL2 {l2:.2e} maxabs/inf {linf:.2e}"
 
 
@@ -47,7 +62,7 @@ def test_cuda_matches_reference_golden(name):
     _compare(got, a, meta["postact"], f"golden {name}")
 
 
-@pytest.mark.parametrize("tuning", [(4, 32), (8, 8), (4, 4), (8, 32)])
+@pytest.mark.parametrize("tuning", [(4, 32, 64), (8, 8, 128), (4, 4, 128), (16, 32, 64), (3, 16, 128), (64, 2, 64)])
 def test_launch_shapes_agree(tuning):
     """Every launch shape (samples per thread x rays per CTA) gives the same answer."""
     from _product import render_case_cuda
@@ -58,7 +73,7 @@ def test_launch_shapes_agree(tuning):
         nat.set_tuning(*tuning)
         got = render_case_cuda(meta, a)
     finally:
-        nat.set_tuning(0, 0)
+        nat.set_tuning(0, 0, 0)
     _compare(got, a, meta["postact"], f"tuning {tuning}")
 
 
@@ -99,7 +114,7 @@ def test_cuda_matches_oracle_seeded(dims, deg, S, hw, postact, perturb):
     meta, a = _seeded_case(dims, deg, S, hw[0], hw[1], 1.4 * hw[1], 37.0, 60.0, postact, perturb, True, seed=7)
     want = run_oracle_on_case(meta, a, dtype=torch.float64)
     got = render_case_cuda(meta, a)
-    _compare(got, want, postact, f"seeded {dims} deg{deg} S{S}")
+    _compare(got, want, postact, f"seeded {dims} deg{deg} S{S}", kink_mask=_kink_mask(meta, a) if postact == "relu" else None)
 
 
 @pytest.mark.parametrize("postact", ["relu", "softplus"])
@@ -156,15 +171,19 @@ def test_headline_shape_against_oracle_subset(postact):
     grid.features.grad = None
     out = render_sh_voxel_grid(grid, rays[sel.cuda()], cfg)
     (out.colour * g_col[sel.cuda()]).sum().backward()
-    # Gradients.  d_features is smooth -> fp64 oracle.  d_densities goes through the ReLU kink: on a U(-1,1)*33.3 grid a
-    # handful of the 2.5e5 samples have an interpolated density within fp32 rounding of 0 and flip their derivative, and
-    # with only 1650 sparse rays one flipped sample is ~6% of ||g||_inf (the fp32 and fp64 oracles differ by exactly
-    # that: relL2 7.9e-3, max 6.4e-2).  So d_densities is checked against the oracle evaluated in fp32, which rounds
-    # like the reference does; the Softplus twin of this test below checks it against fp64.
-    want32 = run_oracle_on_case(meta, sub, dtype=torch.float32) if postact == "relu" else want
-    for key, got, ref in (("d_densities", grid.densities.grad, want32), ("d_features", grid.features.grad, want)):
-        l2, linf = grad_errors(got.cpu(), ref[key])
-        assert l2 <= l2_tol and linf <= inf_tol, f"{key}: {l2:.2e} {linf:.2e}"
+    # Gradients against the fp64 oracle.  With ReLU on a U(-1,1)*33.3 grid a handful of the 2.5e5 samples have an
+    # interpolated density within fp32 rounding of 0 and flip their derivative; with only 1650 sparse rays one flipped
+    # sample is ~6% of ||g||_inf (the fp32 and fp64 oracles differ by exactly that), so the corner voxels of such
+    # samples are excluded from the d_densities comparison and everything else is held to 1e-4.
+    keep = torch.ones_like(want["d_densities"], dtype=torch.bool)
+    if postact == "relu":
+        kink = _kink_mask(meta, sub)
+        assert kink.float().mean().item() < 0.01
+        keep = (~kink)[..., None]
+    l2, linf = grad_errors(grid.densities.grad.cpu() * keep, want["d_densities"] * keep)
+    assert l2 <= 1e-4 and linf <= 1e-4, f"d_densities: {l2:.2e} {linf:.2e}"
+    l2, linf = grad_errors(grid.features.grad.cpu(), want["d_features"])
+    assert l2 <= l2_tol and linf <= inf_tol, f"d_features: {l2:.2e} {linf:.2e}"
 
 
 def test_backward_is_linear_in_upstream_gradient():
@@ -191,6 +210,7 @@ def test_noise_path_matches_oracle():
     meta, a = _seeded_case((24, 24, 24), 0, 64, 12, 12, 16.0, 80.0, 45.0, "softplus", False, True, seed=11, scale=4.0)
     R, S = a["rays_o"].shape[0], 64
     noise = torch.randn(R, S, generator=torch.Generator().manual_seed(5))
+    noise[:, -1] = noise[:, -1].abs()  # delta_last = 1e10: a negative density there makes alpha = -inf upstream too
     grid_o, cfg_o = oracle_grid_cfg(meta)
     cfg_o.noise_std = 0.05
     want = render_oracle_with_grads(a["densities"], a["features"], grid_o, a["rays_o"], a["rays_d"], cfg_o, a["g_colour"], noise=noise)

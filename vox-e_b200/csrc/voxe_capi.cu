@@ -14,7 +14,7 @@ namespace {
 
 thread_local char g_error[512] = "";
 std::atomic<int64_t> g_launches{0};
-std::atomic<int> g_tune_l{0}, g_tune_rpc{0};
+std::atomic<int> g_tune_l{0}, g_tune_rpc{0}, g_tune_reg{0};
 
 int fail(int code, const char* fmt, ...) {
   va_list ap;
@@ -62,22 +62,28 @@ int check_render(const VoxeGridDesc* g, const VoxeRenderDesc* r, const float* ji
   return VOXE_OK;
 }
 
-// Launch shape: samples per thread L, sample segments per ray, rays per CTA.
-int pick_shape(int S, int& L, int& nseg, int& rpc) {
-  const int max_threads = voxe::max_threads_per_cta();
+// Launch shape: samples per thread L, sample segments per ray, rays per CTA, register budget of the kernel variant.
+// Measured on B200 at S=256 (profiles/): small CTAs (about four warps: 4 rays x 32 segments) balance best over the 148
+// SMs because rays through the middle of the grid cost several times more than rays that miss it; the 64-register
+// variant keeps a whole 4096-ray batch resident at SH-0, higher SH degrees need the 128-register one (no spills).
+int pick_shape(int S, int sh_degree, int& L, int& nseg, int& rpc, int& regcap) {
+  regcap = g_tune_reg.load();
+  if (regcap != 64 && regcap != 128) regcap = (sh_degree == 0) ? 64 : 128;
+  const int max_threads = voxe::max_threads_per_cta(regcap);
   L = g_tune_l.load();
-  if (L != 4 && L != 8) L = (S <= 32) ? 4 : 8;
+  if (L < 1 || L > 64) L = (S <= 32) ? 4 : 8;
+  while ((S + L - 1) / L > max_threads) L *= 2;  // very long rays: more samples per thread
   nseg = (S + L - 1) / L;
-  if (nseg > max_threads) return fail(VOXE_ERR_UNSUPPORTED, "num_samples %d exceeds the supported maximum %d", S, max_threads * L);
   rpc = g_tune_rpc.load();
-  if (rpc <= 0 || rpc > 32 || (rpc & (rpc - 1))) rpc = 32;
+  if (rpc <= 0 || rpc > 32 || (rpc & (rpc - 1))) {
+    rpc = 32;
+    while (rpc > 1 && rpc * nseg > 128) rpc >>= 1;
+  }
   while (rpc > 1 && rpc * nseg > max_threads) rpc >>= 1;
-  // keep at least ~2 CTAs' worth of threads per ray group small enough to balance over 148 SMs
-  if (g_tune_rpc.load() <= 0 && rpc * nseg > 512) rpc >>= 1;
   return VOXE_OK;
 }
 
-int fill_params(const VoxeGridDesc* g, const VoxeRenderDesc* r, int64_t R, voxe::KParams& p, int& L) {
+int fill_params(const VoxeGridDesc* g, const VoxeRenderDesc* r, int64_t R, voxe::KParams& p, int& regcap) {
   std::memset(&p, 0, sizeof(p));
   p.R = (int)R;
   p.S = r->num_samples;
@@ -87,8 +93,9 @@ int fill_params(const VoxeGridDesc* g, const VoxeRenderDesc* r, int64_t R, voxe:
   for (int a = 0; a < 3; ++a) {
     p.lo[a] = g->aabb_lo[a];
     p.hi[a] = g->aabb_hi[a];
-    p.nscale[a] = g->norm_scale[a];
-    p.nbias[a] = g->norm_bias[a];
+    // u = ((p*scale + bias + 1) * N - 1) / 2 folded into one multiply-add
+    p.ua[a] = (float)(0.5 * (double)g->norm_scale[a] * g->dims[a]);
+    p.ub[a] = (float)(0.5 * (((double)g->norm_bias[a] + 1.0) * g->dims[a] - 1.0));
   }
   p.near = r->near;
   p.far = r->far;
@@ -98,7 +105,7 @@ int fill_params(const VoxeGridDesc* g, const VoxeRenderDesc* r, int64_t R, voxe:
   p.flags = r->flags;
   p.preact = g->preact;
   p.postact = g->postact;
-  return pick_shape(p.S, L, p.nseg, p.rpc);
+  return pick_shape(p.S, r->sh_degree, p.L, p.nseg, p.rpc, regcap);
 }
 
 }  // namespace
@@ -113,14 +120,24 @@ int voxe_packed_channels(int n_features) { return ((n_features + 1 + 3) / 4) * 4
 
 int64_t voxe_launch_count(void) { return g_launches.load(); }
 
-int voxe_set_tuning(int samples_per_thread, int rays_per_cta) {
-  if (samples_per_thread != 0 && samples_per_thread != 4 && samples_per_thread != 8)
-    return fail(VOXE_ERR_INVALID_ARGUMENT, "samples_per_thread must be 0, 4 or 8");
+int voxe_set_tuning(int samples_per_thread, int rays_per_cta, int register_cap) {
+  if (samples_per_thread < 0 || samples_per_thread > 64)
+    return fail(VOXE_ERR_INVALID_ARGUMENT, "samples_per_thread must be in 0..64");
   if (rays_per_cta < 0 || rays_per_cta > 32 || (rays_per_cta & (rays_per_cta - 1)))
     return fail(VOXE_ERR_INVALID_ARGUMENT, "rays_per_cta must be 0 or a power of two <= 32");
+  if (register_cap != 0 && register_cap != 64 && register_cap != 128)
+    return fail(VOXE_ERR_INVALID_ARGUMENT, "register_cap must be 0, 64 or 128");
   g_tune_l.store(samples_per_thread);
   g_tune_rpc.store(rays_per_cta);
+  g_tune_reg.store(register_cap);
   return VOXE_OK;
+}
+
+int64_t voxe_saved_floats(const VoxeRenderDesc* render, int64_t num_rays) {
+  if (!render || render->num_samples < 2 || num_rays < 0) return 0;
+  int L, nseg, rpc, regcap;
+  if (pick_shape(render->num_samples, render->sh_degree, L, nseg, rpc, regcap)) return 0;
+  return (int64_t)voxe::saved_floats_per_segment(render->n_colour) * nseg * num_rays;
 }
 
 int voxe_pack_grid(const VoxeGridDesc* grid, const float* densities, const float* features, float* packed,
@@ -150,7 +167,7 @@ int voxe_unpack_grad(const VoxeGridDesc* grid, const float* packed_grad, float* 
 
 int voxe_render_fwd(const VoxeGridDesc* grid, const VoxeRenderDesc* render, const float* packed,
                     const float* rays_o, const float* rays_d, const float* jitter, const float* noise,
-                    float* colour, float* depth, float* acc, float* disparity, int64_t num_rays,
+                    float* colour, float* depth, float* acc, float* disparity, float* saved, int64_t num_rays,
                     voxe_stream_t stream) {
   if (int rc = check_grid(grid)) return rc;
   if (int rc = check_render(grid, render, jitter, noise)) return rc;
@@ -159,18 +176,19 @@ int voxe_render_fwd(const VoxeGridDesc* grid, const VoxeRenderDesc* render, cons
   if (!packed || !rays_o || !rays_d || !colour || !depth || !acc)
     return fail(VOXE_ERR_INVALID_ARGUMENT, "voxe_render_fwd: NULL buffer");
   voxe::KParams p;
-  int L = 0;
-  if (int rc = fill_params(grid, render, num_rays, p, L)) return rc;
+  int regcap = 0;
+  if (int rc = fill_params(grid, render, num_rays, p, regcap)) return rc;
   p.grid = reinterpret_cast<const float4*>(packed);
   p.rays_o = rays_o;
   p.rays_d = rays_d;
   p.jitter = (render->flags & VOXE_FLAG_PERTURB) ? jitter : nullptr;
   p.noise = (render->noise_std != 0.f) ? noise : nullptr;
+  p.saved = saved;
   p.colour = colour;
   p.depth = depth;
   p.acc = acc;
   p.disp = disparity;
-  cudaError_t e = voxe::launch_render(p, render->sh_degree, render->n_colour, L, false, (cudaStream_t)stream);
+  cudaError_t e = voxe::launch_render(p, render->sh_degree, render->n_colour, regcap, false, (cudaStream_t)stream);
   if (e != cudaSuccess) return cuda_fail(e, "voxe_render_fwd launch");
   g_launches.fetch_add(1);
   return VOXE_OK;
@@ -178,17 +196,18 @@ int voxe_render_fwd(const VoxeGridDesc* grid, const VoxeRenderDesc* render, cons
 
 int voxe_render_bwd(const VoxeGridDesc* grid, const VoxeRenderDesc* render, const float* packed,
                     const float* rays_o, const float* rays_d, const float* jitter, const float* noise,
-                    const float* g_colour, const float* g_depth, const float* g_acc, const float* g_disp,
-                    float* packed_grad, int64_t num_rays, voxe_stream_t stream) {
+                    const float* saved, const float* g_colour, const float* g_depth, const float* g_acc,
+                    const float* g_disp, float* packed_grad, int64_t num_rays, voxe_stream_t stream) {
   if (int rc = check_grid(grid)) return rc;
   if (int rc = check_render(grid, render, jitter, noise)) return rc;
   if (num_rays < 0 || num_rays > 0x7fffffff) return fail(VOXE_ERR_INVALID_ARGUMENT, "num_rays out of range");
   if (num_rays == 0) return VOXE_OK;
-  if (!packed || !rays_o || !rays_d || !g_colour || !packed_grad)
-    return fail(VOXE_ERR_INVALID_ARGUMENT, "voxe_render_bwd: NULL buffer");
+  if (!packed || !rays_o || !rays_d || !g_colour || !packed_grad || !saved)
+    return fail(VOXE_ERR_INVALID_ARGUMENT, "voxe_render_bwd: NULL buffer (saved is the workspace filled by voxe_render_fwd)");
   voxe::KParams p;
-  int L = 0;
-  if (int rc = fill_params(grid, render, num_rays, p, L)) return rc;
+  int regcap = 0;
+  if (int rc = fill_params(grid, render, num_rays, p, regcap)) return rc;
+  p.saved = const_cast<float*>(saved);
   p.grid = reinterpret_cast<const float4*>(packed);
   p.grad = reinterpret_cast<float4*>(packed_grad);
   p.rays_o = rays_o;
@@ -199,7 +218,7 @@ int voxe_render_bwd(const VoxeGridDesc* grid, const VoxeRenderDesc* render, cons
   p.g_depth = g_depth;
   p.g_acc = g_acc;
   p.g_disp = g_disp;
-  cudaError_t e = voxe::launch_render(p, render->sh_degree, render->n_colour, L, true, (cudaStream_t)stream);
+  cudaError_t e = voxe::launch_render(p, render->sh_degree, render->n_colour, regcap, true, (cudaStream_t)stream);
   if (e != cudaSuccess) return cuda_fail(e, "voxe_render_bwd launch");
   g_launches.fetch_add(1);
   return VOXE_OK;

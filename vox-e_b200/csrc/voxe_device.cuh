@@ -37,10 +37,12 @@ struct KParams {
   const float* g_disp;
   int R, S;
   int X, Y, Z;
-  float lo[3], hi[3], nscale[3], nbias[3];
+  float lo[3], hi[3];
+  float ua[3], ub[3];   // voxel-space coordinate u = p*ua + ub  (= ((p*nscale + nbias + 1) * N - 1) / 2, folded on the host)
   float near, far, dscale, noise_std, lin_step;
   int flags, preact, postact;
-  int rpc, nseg;  // rays per CTA, sample segments per ray (threads = rpc * nseg rounded up to 32)
+  int rpc, nseg, L;  // rays per CTA, sample segments per ray, samples per segment (threads = rpc * nseg -> x32)
+  float* saved;      // [NCOL+3][nseg][R] segment summaries written by the forward / read by the backward (or null)
 };
 
 // ---------------------------------------------------------------------------------------------------------
@@ -140,10 +142,13 @@ __device__ __forceinline__ bool inside_aabb(const KParams& p, float px, float py
   return (px > p.lo[0]) & (px < p.hi[0]) & (py > p.lo[1]) & (py < p.hi[1]) & (pz > p.lo[2]) & (pz < p.hi[2]);
 }
 
-__device__ __forceinline__ void axis_setup(float pc, float scale, float bias, int N, int& i0, int& i1, float& w0,
-                                           float& w1) {
-  const float n = __fadd_rn(__fmul_rn(pc, scale), bias);   // voxels.py:225-234 (two rounded ops)
-  const float u = ((n + 1.0f) * (float)N - 1.0f) * 0.5f;   // grid_sampler unnormalize, align_corners=False
+// One axis of the trilinear footprint.  u = (p - lo)/voxel - 0.5 is evaluated with one FMA (coefficients folded on the
+// host in double); unlike the inside test this is a continuous function of p, so the different rounding relative to
+// the reference's normalise -> unnormalise chain (voxels.py:225-234 + grid_sampler) only moves results by ~1e-7 * N.
+// For a point strictly inside the box floor(u) lies in [-1, N-1]: only the low corner can fall below 0 and only the
+// high corner above N-1; those get weight 0 (zeros padding) and a clamped, harmless address.
+__device__ __forceinline__ void axis_setup(float pc, float ua, float ub, int N, int& i0, int& i1, float& w0, float& w1) {
+  const float u = fmaf(pc, ua, ub);
   const float fl = floorf(u);
   const float f = u - fl;
   const int i = (int)fl;
@@ -156,9 +161,9 @@ __device__ __forceinline__ void axis_setup(float pc, float scale, float bias, in
 __device__ __forceinline__ void make_corners(const KParams& p, float px, float py, float pz, Corners& c) {
   int x0, x1, y0, y1, z0, z1;
   float wx0, wx1, wy0, wy1, wz0, wz1;
-  axis_setup(px, p.nscale[0], p.nbias[0], p.X, x0, x1, wx0, wx1);
-  axis_setup(py, p.nscale[1], p.nbias[1], p.Y, y0, y1, wy0, wy1);
-  axis_setup(pz, p.nscale[2], p.nbias[2], p.Z, z0, z1, wz0, wz1);
+  axis_setup(px, p.ua[0], p.ub[0], p.X, x0, x1, wx0, wx1);
+  axis_setup(py, p.ua[1], p.ub[1], p.Y, y0, y1, wy0, wy1);
+  axis_setup(pz, p.ua[2], p.ub[2], p.Z, z0, z1, wz0, wz1);
   const int r00 = (x0 * p.Y + y0) * p.Z, r01 = (x0 * p.Y + y1) * p.Z;
   const int r10 = (x1 * p.Y + y0) * p.Z, r11 = (x1 * p.Y + y1) * p.Z;
   c.idx[0] = r00 + z0; c.w[0] = wx0 * wy0 * wz0;
@@ -178,6 +183,11 @@ __device__ __forceinline__ void f4_set(float4& v, int k, float x) {
   if (k == 0) v.x = x; else if (k == 1) v.y = x; else if (k == 2) v.z = x; else v.w = x;
 }
 
+// Fast transcendental forms (ex2.approx / rcp.approx based, ~2 ulp): three orders of magnitude below the 1e-4 pixel
+// tolerance, and they keep the per-sample instruction count (the kernels are issue/latency bound, not DRAM bound).
+__device__ __forceinline__ float exp_fast(float x) { return __expf(x); }
+__device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+
 // post-activation and its derivative w.r.t. the interpolated (pre-activated) density
 __device__ __forceinline__ float post_act(int kind, float x, float& dydx) {
   if (kind == kPostRelu) {
@@ -189,8 +199,8 @@ __device__ __forceinline__ float post_act(int kind, float x, float& dydx) {
       dydx = 1.f;
       return x;
     }
-    const float e = expf(x);
-    dydx = e / (1.f + e);
+    const float e = __expf(x);
+    dydx = __fdividef(e, 1.f + e);
     return log1pf(e);
   }
   dydx = 1.f;
@@ -227,35 +237,52 @@ __device__ __forceinline__ void load_ray(const KParams& p, int ray, RayCtx& rc) 
   rc.dnorm = sqrtf(rc.d[0] * rc.d[0] + rc.d[1] * rc.d[1] + rc.d[2] * rc.d[2]);
 }
 
-// Depths z'[0..L] of samples i0 .. i0+L (the extra one closes the last interval), with stratified jitter
-// when requested (sample.py:57-64).  Entries beyond S-1 are left at the last valid depth.
-template <int L>
-__device__ __forceinline__ void segment_depths(const KParams& p, const RayCtx& rc, int ray, int i0, float (&z)[L + 1]) {
-  const int S = p.S;
-  if (!(p.flags & kPerturb)) {
-#pragma unroll
-    for (int j = 0; j <= L; ++j) {
-      const int i = min(i0 + j, S - 1);
-      z[j] = depth_plain(p, rc.near, rc.far, rc.inv_near, rc.inv_far, rc.disparity, i);
+// Rolling evaluation of the (optionally jittered) sample depths along one ray: `cur` is the depth of sample i,
+// `next` the depth of sample i+1 (it closes the interval delta_i).  Stratified jitter follows sample.py:57-64:
+// z'_i = lower_i + (upper_i - lower_i) * u_i with lower/upper the mid-points to the neighbouring plain depths.
+struct DepthWalker {
+  float a, b, c, d;  // plain depths of samples i-1, i, i+1, i+2 (indices clamped into [0, S-1])
+  float cur, next;
+  float u_pre;       // jitter of sample i+2, fetched one iteration before it is needed
+
+  __device__ __forceinline__ float plain(const KParams& p, const RayCtx& rc, int k) const {
+    return depth_plain(p, rc.near, rc.far, rc.inv_near, rc.inv_far, rc.disparity, min(max(k, 0), p.S - 1));
+  }
+  __device__ __forceinline__ static float jittered(const KParams& p, float lo, float mid, float hi, int i, float u) {
+    const float lower = (i <= 0) ? mid : __fmul_rn(0.5f, __fadd_rn(mid, lo));
+    const float upper = (i >= p.S - 1) ? mid : __fmul_rn(0.5f, __fadd_rn(hi, mid));
+    return __fadd_rn(lower, __fmul_rn(__fsub_rn(upper, lower), u));
+  }
+  __device__ __forceinline__ void init(const KParams& p, const RayCtx& rc, const float* u_row, int i) {
+    b = plain(p, rc, i);
+    c = plain(p, rc, i + 1);
+    if (p.flags & kPerturb) {
+      const float u0 = __ldg(u_row + min(i, p.S - 1));
+      const float u1 = __ldg(u_row + min(i + 1, p.S - 1));
+      u_pre = __ldg(u_row + min(i + 2, p.S - 1));
+      a = plain(p, rc, i - 1);
+      d = plain(p, rc, i + 2);
+      cur = jittered(p, a, b, c, i, u0);
+      next = jittered(p, b, c, d, i + 1, u1);
+    } else {
+      cur = b;
+      next = c;
     }
-    return;
   }
-  // plain depths i0-1 .. i0+L+1
-  float zp[L + 3];
-#pragma unroll
-  for (int j = 0; j < L + 3; ++j) {
-    const int i = min(max(i0 - 1 + j, 0), S - 1);
-    zp[j] = depth_plain(p, rc.near, rc.far, rc.inv_near, rc.inv_far, rc.disparity, i);
+  // step from sample i to sample i+1
+  __device__ __forceinline__ void advance(const KParams& p, const RayCtx& rc, const float* u_row, int i) {
+    cur = next;
+    if (p.flags & kPerturb) {
+      a = b;
+      b = c;
+      c = d;
+      d = plain(p, rc, i + 3);
+      next = jittered(p, b, c, d, i + 2, u_pre);
+      u_pre = __ldg(u_row + min(i + 3, p.S - 1));
+    } else {
+      next = plain(p, rc, i + 2);
+    }
   }
-  const float* u = p.jitter + (size_t)ray * S;
-#pragma unroll
-  for (int j = 0; j <= L; ++j) {
-    const int i = i0 + j;  // samples past S-1 get a finite but unused value
-    const float zi = zp[j + 1];
-    const float lower = (i == 0) ? zi : __fmul_rn(0.5f, __fadd_rn(zi, zp[j]));
-    const float upper = (i >= S - 1) ? zi : __fmul_rn(0.5f, __fadd_rn(zp[j + 2], zi));
-    z[j] = __fadd_rn(lower, __fmul_rn(__fsub_rn(upper, lower), __ldg(u + min(i, S - 1))));
-  }
-}
+};
 
 }  // namespace voxe

@@ -8,9 +8,9 @@ namespace voxe {
 struct KParams;
 
 // fused ray-marcher (voxe_render.cu)
-cudaError_t launch_render(const KParams& p, int sh_degree, int n_colour, int samples_per_thread, bool backward,
-                          cudaStream_t stream);
-int max_threads_per_cta();
+cudaError_t launch_render(const KParams& p, int sh_degree, int n_colour, int regcap, bool backward, cudaStream_t stream);
+int max_threads_per_cta(int regcap);
+int saved_floats_per_segment(int n_colour);
 
 // full-grid passes (voxe_grid_ops.cu)
 cudaError_t launch_pack_grid(const float* densities, const float* features, float* packed, int64_t n_voxels,

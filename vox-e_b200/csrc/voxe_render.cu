@@ -11,18 +11,27 @@
 //   product scan of T over `seg` (warp shuffles on a shared-memory transpose), which is the only cross-thread
 //   communication.  Nothing of size O(R*S) is ever written to memory.
 //
-// Backward (closed form of SURVEY.md 8.A): phase 1 re-gathers and keeps the L samples' (alpha, local T, delta, z,
-//   sigmoid(rgb), post') in registers; the scan additionally yields, per segment, the suffix sum of w*q over all
-//   later segments; phase 2 walks the L samples back to front, forms dL/dsigma and dL/draw and scatters them to
-//   the 8 corners with 16-byte vector REDs (red.global.add.v4.f32 -> REDG.E.ADD.F32x4).
+// Forward: streams over its L samples (gather 8 corners -> interpolate -> SH -> alpha), then the stitch.  When a
+//   `saved` workspace is given it also stores, per (ray, segment), the transmittance at the segment start and the
+//   segment's local sums -- (NCOL+3) floats per L samples -- which is all the backward needs from the forward.
+//
+// Backward (closed form of SURVEY.md 8.A): reads the saved segment summaries, turns them into "sum of w*q over
+//   everything behind this segment" with one suffix scan, and then streams over its samples ONCE: re-gather,
+//   recompute alpha / T / w, form dL/dsigma_i = delta_i (T_{i+1} q_i - sum_{j>i} w_j q_j) and dL/draw, and scatter
+//   to the 8 corners with 16-byte vector REDs (red.global.add.v4.f32 -> REDG.E.ADD.F32x4).  No per-sample state
+//   is kept in registers, so the kernel fits a 64-register budget and the whole 4096-ray batch is resident at once.
 #include "voxe_device.cuh"
 #include "voxe_launch.h"
+
+#ifndef VOXE_UNROLL
+#define VOXE_UNROLL 1
+#endif
 
 namespace voxe {
 
 namespace {
 
-constexpr int kMaxThreads = 512;
+constexpr int kSampleUnroll = VOXE_UNROLL;  // unroll factor of the per-thread sample loop
 
 template <int DEG, int NCOL>
 struct Layout {
@@ -31,6 +40,8 @@ struct Layout {
   static constexpr int CV = (F + 1 + 3) / 4;    // float4 vectors per voxel
   static constexpr int DCH = F / 4;             // vector / component holding the density channel
   static constexpr int DCO = F % 4;
+  static constexpr int NV = NCOL + 2;           // per-segment sums: colour..., depth, acc
+  static constexpr int SV = NCOL + 3;           // saved floats per (ray, segment): T_start + NV sums
 };
 
 // One sample: gather the 8 corners, interpolate, SH-contract.  Returns the (pre-activated, interpolated) raw
@@ -78,8 +89,6 @@ __device__ __forceinline__ float gather_sample(const KParams& p, const Corners& 
   return sig;
 }
 
-__device__ __forceinline__ float sigmoidf(float x) { return 1.0f / (1.0f + expf(-x)); }
-
 __device__ __forceinline__ float warp_sum(float x) {
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) x += __shfl_xor_sync(0xffffffffu, x, d);
@@ -106,13 +115,18 @@ __device__ __forceinline__ float warp_scan_suffix_add(float x, int lane) {
   return x;
 }
 
+template <int REGCAP>
+struct Bounds {
+  static constexpr int kThreads = (REGCAP <= 64) ? 1024 : 512;
+};
+
 // ---------------------------------------------------------------------------------------------------------
 // forward
 // ---------------------------------------------------------------------------------------------------------
-template <int DEG, int NCOL, int L>
-__global__ void __launch_bounds__(kMaxThreads) render_fwd_kernel(const __grid_constant__ KParams p) {
+template <int DEG, int NCOL, int REGCAP>
+__global__ void __launch_bounds__(Bounds<REGCAP>::kThreads, 1) render_fwd_kernel(const __grid_constant__ KParams p) {
   using LT = Layout<DEG, NCOL>;
-  constexpr int NV = NCOL + 2;  // colour..., depth, acc
+  constexpr int NV = LT::NV;
   extern __shared__ float smem[];
   const int rpc = p.rpc, nseg = p.nseg, stride = rpc + 1;
   float* sT = smem;                   // [nseg][stride]
@@ -129,55 +143,44 @@ __global__ void __launch_bounds__(kMaxThreads) render_fwd_kernel(const __grid_co
   if (active) {
     RayCtx rc;
     load_ray(p, ray, rc);
-    const int i0 = seg * L;
-    float z[L + 1];
-    segment_depths<L>(p, rc, ray, i0, z);
+    const int L = p.L, i0 = seg * L, i1 = min(i0 + L, p.S);
+    const float* u_row = p.jitter ? p.jitter + (size_t)ray * p.S : nullptr;
+    DepthWalker zw;
+    zw.init(p, rc, u_row, i0);
     const bool use_noise = (p.noise_std != 0.f);
-
-    // cheap reject: is any sample of this segment inside the grid?
-    unsigned in_mask = 0u;
-    float px[L], py[L], pz[L];
+    float Y[LT::K];
+    const float inv = 1.0f / rc.dnorm;
+    sh_basis<DEG>(rc.d[0] * inv, rc.d[1] * inv, rc.d[2] * inv, (p.flags & kDiffuse) != 0, Y);
+#pragma unroll(kSampleUnroll)
+    for (int i = i0; i < i1; ++i, zw.advance(p, rc, u_row, i - 1)) {
+      const float zi = zw.cur;
+      const float px = __fadd_rn(rc.o[0], __fmul_rn(rc.d[0], zi));   // sample.py:67: o + d * z (mul, then add)
+      const float py = __fadd_rn(rc.o[1], __fmul_rn(rc.d[1], zi));
+      const float pz = __fadd_rn(rc.o[2], __fmul_rn(rc.d[2], zi));
+      const bool in = inside_aabb(p, px, py, pz);
+      if (!in && !use_noise) continue;  // alpha == 0 exactly (process.py:80-91)
+      float sigma = 0.f, col[NCOL];
 #pragma unroll
-    for (int j = 0; j < L; ++j) {
-      px[j] = __fadd_rn(rc.o[0], __fmul_rn(rc.d[0], z[j]));   // sample.py:67: o + d * z (mul, then add)
-      py[j] = __fadd_rn(rc.o[1], __fmul_rn(rc.d[1], z[j]));
-      pz[j] = __fadd_rn(rc.o[2], __fmul_rn(rc.d[2], z[j]));
-      if (i0 + j < p.S && inside_aabb(p, px[j], py[j], pz[j])) in_mask |= (1u << j);
-    }
-    if (in_mask != 0u || use_noise) {
-      float Y[LT::K];
-      const float inv = 1.0f / rc.dnorm;
-      sh_basis<DEG>(rc.d[0] * inv, rc.d[1] * inv, rc.d[2] * inv, (p.flags & kDiffuse) != 0, Y);
+      for (int k = 0; k < NCOL; ++k) col[k] = 0.f;   // sigmoid(-1e10) == 0 outside the grid
+      if (in) {
+        Corners c;
+        make_corners(p, px, py, pz, c);
+        float raw[NCOL], dpost;
+        unsigned signs;
+        const float sraw = gather_sample<DEG, NCOL>(p, c, Y, raw, signs);
+        sigma = post_act(p.postact, sraw, dpost);
 #pragma unroll
-      for (int j = 0; j < L; ++j) {
-        const int i = i0 + j;
-        if (i >= p.S) break;
-        const bool in = (in_mask >> j) & 1u;
-        float sigma = 0.f, col[NCOL];
-#pragma unroll
-        for (int k = 0; k < NCOL; ++k) col[k] = 0.f;   // sigmoid(-1e10) == 0 outside the grid (process.py:80-84)
-        if (in) {
-          Corners c;
-          make_corners(p, px[j], py[j], pz[j], c);
-          float raw[NCOL], dpost;
-          unsigned signs;
-          const float sraw = gather_sample<DEG, NCOL>(p, c, Y, raw, signs);
-          sigma = post_act(p.postact, sraw, dpost);
-#pragma unroll
-          for (int k = 0; k < NCOL; ++k) col[k] = sigmoidf(raw[k]);
-        } else if (!use_noise) {
-          continue;  // alpha == 0 exactly
-        }
-        if (use_noise) sigma = fmaf(__ldg(p.noise + (size_t)ray * p.S + i), p.noise_std, sigma);
-        const float delta = ((i == p.S - 1) ? kInfinity : __fsub_rn(z[j + 1], z[j])) * rc.dnorm;  // accumulate.py:49-55
-        const float alpha = 1.0f - expf(-(sigma * delta));
-        const float w = alpha * Tl;
-#pragma unroll
-        for (int k = 0; k < NCOL; ++k) V[k] = fmaf(w, col[k], V[k]);
-        V[NCOL] = fmaf(w, z[j], V[NCOL]);
-        V[NCOL + 1] += w;
-        Tl *= (1.0f - alpha);
+        for (int k = 0; k < NCOL; ++k) col[k] = sigmoid_fast(raw[k]);
       }
+      if (use_noise) sigma = fmaf(__ldg(p.noise + (size_t)ray * p.S + i), p.noise_std, sigma);
+      const float delta = ((i == p.S - 1) ? kInfinity : __fsub_rn(zw.next, zi)) * rc.dnorm;  // accumulate.py:49-55
+      const float alpha = 1.0f - exp_fast(-(sigma * delta));
+      const float w = alpha * Tl;
+#pragma unroll
+      for (int k = 0; k < NCOL; ++k) V[k] = fmaf(w, col[k], V[k]);
+      V[NCOL] = fmaf(w, zi, V[NCOL]);
+      V[NCOL + 1] += w;
+      Tl *= (1.0f - alpha);
     }
   }
   if (seg < nseg) {
@@ -205,6 +208,7 @@ __global__ void __launch_bounds__(kMaxThreads) render_fwd_kernel(const __grid_co
       excl *= carry;
       carry *= __shfl_sync(0xffffffffu, inc, 31);
       if (ok) {
+        if (p.saved) sT[s * stride + r] = excl;  // T at segment start, written out below
 #pragma unroll
         for (int k = 0; k < NV; ++k) tot[k] = fmaf(excl, sV[(k * nseg + s) * stride + r], tot[k]);
       }
@@ -225,122 +229,51 @@ __global__ void __launch_bounds__(kMaxThreads) render_fwd_kernel(const __grid_co
       }
     }
   }
+  if (p.saved) {  // segment summaries for the backward: saved[k][seg][ray], coalesced over rays
+    __syncthreads();
+    if (active) {
+      const size_t plane = (size_t)nseg * p.R;
+      float* dst = p.saved + (size_t)seg * p.R + ray;
+      dst[0] = sT[seg * stride + r_in];
+#pragma unroll
+      for (int k = 0; k < NV; ++k) dst[(k + 1) * plane] = V[k];
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------
 // backward
 // ---------------------------------------------------------------------------------------------------------
-template <int DEG, int NCOL, int L>
-__global__ void __launch_bounds__(kMaxThreads) render_bwd_kernel(const __grid_constant__ KParams p) {
+template <int DEG, int NCOL, int REGCAP>
+__global__ void __launch_bounds__(Bounds<REGCAP>::kThreads, 1) render_bwd_kernel(const __grid_constant__ KParams p) {
   using LT = Layout<DEG, NCOL>;
-  constexpr int NV = NCOL + 2;
+  constexpr int NV = LT::NV;
   extern __shared__ float smem[];
   const int rpc = p.rpc, nseg = p.nseg, stride = rpc + 1;
-  float* sT = smem;                          // [nseg][stride]   T of the segment, then T at segment start
-  float* sV = smem + nseg * stride;          // [NV][nseg][stride]; plane 0 is reused for the suffix sums
+  float* sT = smem;                          // [nseg][stride]   T at segment start (from the forward)
+  float* sV = smem + nseg * stride;          // [NV][nseg][stride] local sums; plane 0 becomes q_s, plane 1 the suffix
   float* sG = sV + NV * nseg * stride;       // [2][rpc]  effective dL/ddepth, dL/dacc per ray
 
   const int r_in = threadIdx.x % rpc, seg = threadIdx.x / rpc;
   const int ray = blockIdx.x * rpc + r_in;
   const bool active = (seg < nseg) && (ray < p.R);
-  const int i0 = seg * L;
+  const int L = p.L, i0 = seg * L, i1 = min(i0 + L, p.S);
 
-  // per-sample state kept in registers between the two phases
-  float s_alpha[L], s_T[L], s_delta[L], s_z[L], s_dpost[L], s_col[L][NCOL];
-  unsigned s_signs = 0u;  // 8 bits per sample (L <= 4) or split over two words
-  unsigned s_signs_hi = 0u;
-  unsigned in_mask = 0u;
-  RayCtx rc;
-  float Tl = 1.f, V[NV];
-#pragma unroll
-  for (int k = 0; k < NV; ++k) V[k] = 0.f;
-  float Y[LT::K];
-  const bool use_noise = (p.noise_std != 0.f);
-
-  if (active) {
-    load_ray(p, ray, rc);
-    float z[L + 1];
-    segment_depths<L>(p, rc, ray, i0, z);
-    float px[L], py[L], pz[L];
-#pragma unroll
-    for (int j = 0; j < L; ++j) {
-      px[j] = __fadd_rn(rc.o[0], __fmul_rn(rc.d[0], z[j]));
-      py[j] = __fadd_rn(rc.o[1], __fmul_rn(rc.d[1], z[j]));
-      pz[j] = __fadd_rn(rc.o[2], __fmul_rn(rc.d[2], z[j]));
-      if (i0 + j < p.S && inside_aabb(p, px[j], py[j], pz[j])) in_mask |= (1u << j);
-      s_z[j] = z[j];
-      s_delta[j] = ((i0 + j >= p.S - 1) ? kInfinity : __fsub_rn(z[j + 1], z[j])) * rc.dnorm;
-      s_alpha[j] = 0.f;
-      s_T[j] = 1.f;
-      s_dpost[j] = 0.f;
-#pragma unroll
-      for (int k = 0; k < NCOL; ++k) s_col[j][k] = 0.f;
-    }
-    if (in_mask != 0u || use_noise) {
-      const float inv = 1.0f / rc.dnorm;
-      sh_basis<DEG>(rc.d[0] * inv, rc.d[1] * inv, rc.d[2] * inv, (p.flags & kDiffuse) != 0, Y);
-#pragma unroll
-      for (int j = 0; j < L; ++j) {
-        const int i = i0 + j;
-        if (i >= p.S) break;
-        const bool in = (in_mask >> j) & 1u;
-        float sigma = 0.f;
-        if (in) {
-          Corners c;
-          make_corners(p, px[j], py[j], pz[j], c);
-          float raw[NCOL];
-          unsigned signs;
-          const float sraw = gather_sample<DEG, NCOL>(p, c, Y, raw, signs);
-          sigma = post_act(p.postact, sraw, s_dpost[j]);
-#pragma unroll
-          for (int k = 0; k < NCOL; ++k) s_col[j][k] = sigmoidf(raw[k]);
-          if (j < 4) s_signs |= signs << (8 * j); else s_signs_hi |= signs << (8 * (j - 4));
-        } else if (!use_noise) {
-          continue;
-        }
-        if (use_noise) sigma = fmaf(__ldg(p.noise + (size_t)ray * p.S + i), p.noise_std, sigma);
-        const float alpha = 1.0f - expf(-(sigma * s_delta[j]));
-        const float w = alpha * Tl;
-        s_alpha[j] = alpha;
-        s_T[j] = Tl;
-#pragma unroll
-        for (int k = 0; k < NCOL; ++k) V[k] = fmaf(w, s_col[j][k], V[k]);
-        V[NCOL] = fmaf(w, s_z[j], V[NCOL]);
-        V[NCOL + 1] += w;
-        Tl *= (1.0f - alpha);
-      }
-    }
-  }
+  // load the forward's segment summaries (coalesced over rays) and transpose through shared memory
   if (seg < nseg) {
-    sT[seg * stride + r_in] = Tl;
+    const size_t plane = (size_t)nseg * p.R;
+    const float* src = p.saved + (size_t)seg * p.R + ray;
+    sT[seg * stride + r_in] = active ? __ldg(src) : 1.f;
 #pragma unroll
-    for (int k = 0; k < NV; ++k) sV[(k * nseg + seg) * stride + r_in] = V[k];
+    for (int k = 0; k < NV; ++k) sV[(k * nseg + seg) * stride + r_in] = active ? __ldg(src + (k + 1) * plane) : 0.f;
   }
   __syncthreads();
 
-  // stitch: T at segment start, totals, effective output gradients, suffix sums of w*q over later segments
+  // per ray: totals, effective output gradients, q_s = T_start * <g, sums_s>, and its exclusive suffix sum
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   for (int r = warp; r < rpc; r += nwarps) {
     const int ray2 = blockIdx.x * rpc + r;
     if (ray2 >= p.R) break;
-    float carry = 1.f, totD = 0.f, totA = 0.f;
-    for (int s0 = 0; s0 < nseg; s0 += 32) {
-      const int s = s0 + lane;
-      const bool ok = s < nseg;
-      const float T = ok ? sT[s * stride + r] : 1.f;
-      const float inc = warp_scan_mul(T, lane);
-      float excl = __shfl_up_sync(0xffffffffu, inc, 1);
-      if (lane == 0) excl = 1.f;
-      excl *= carry;
-      carry *= __shfl_sync(0xffffffffu, inc, 31);
-      if (ok) {
-        sT[s * stride + r] = excl;
-        totD = fmaf(excl, sV[(NCOL * nseg + s) * stride + r], totD);
-        totA = fmaf(excl, sV[((NCOL + 1) * nseg + s) * stride + r], totA);
-      }
-    }
-    totD = warp_sum(totD);
-    totA = warp_sum(totA);
     float gc[NCOL], gsum = 0.f;
 #pragma unroll
     for (int k = 0; k < NCOL; ++k) {
@@ -352,10 +285,19 @@ __global__ void __launch_bounds__(kMaxThreads) render_bwd_kernel(const __grid_co
     if ((p.flags & kWhite) && !(p.flags & kAttn)) ga -= gsum;  // colour += 1 - acc
     if (p.g_disp) {
       const float gq = __ldg(p.g_disp + ray2);
-      const float q = totD / totA;
-      if (gq != 0.f && q > kZeroPlus) {  // disparity = acc / depth on this branch of the max()
-        ga += gq / totD;
-        gd -= gq * totA / (totD * totD);
+      if (gq != 0.f) {
+        float totD = 0.f, totA = 0.f;
+        for (int s = lane; s < nseg; s += 32) {
+          const float ts = sT[s * stride + r];
+          totD = fmaf(ts, sV[(NCOL * nseg + s) * stride + r], totD);
+          totA = fmaf(ts, sV[((NCOL + 1) * nseg + s) * stride + r], totA);
+        }
+        totD = warp_sum(totD);
+        totA = warp_sum(totA);
+        if (totD / totA > kZeroPlus) {  // disparity = acc / depth on this branch of the max()
+          ga += gq / totD;
+          gd -= gq * totA / (totD * totD);
+        }
       }
     }
     float carry_q = 0.f;
@@ -375,7 +317,10 @@ __global__ void __launch_bounds__(kMaxThreads) render_bwd_kernel(const __grid_co
       if (lane == 31) excl = 0.f;
       excl += carry_q;
       carry_q += __shfl_sync(0xffffffffu, inc, 0);
-      if (ok) sV[s * stride + r] = excl;  // plane 0 <- suffix (own q was read above by this same lane)
+      if (ok) {
+        sV[s * stride + r] = q;                    // plane 0 <- sum of w*q inside segment s
+        sV[(nseg + s) * stride + r] = excl;        // plane 1 <- sum of w*q behind segment s
+      }
     }
     if (lane == 0) {
       sG[r] = gd;
@@ -383,41 +328,74 @@ __global__ void __launch_bounds__(kMaxThreads) render_bwd_kernel(const __grid_co
     }
   }
   __syncthreads();
+  if (!active) return;
 
-  if (!active || in_mask == 0u) return;
-
-  // phase 2: back to front over this thread's samples
-  const float Tstart = sT[seg * stride + r_in];
-  float suffix = sV[seg * stride + r_in];
+  // stream over this thread's samples, front to back
+  float Tcur = sT[seg * stride + r_in];
+  const float q_seg = sV[seg * stride + r_in];
+  const float q_behind = sV[(nseg + seg) * stride + r_in];
+  if (Tcur == 0.f && q_seg == 0.f && q_behind == 0.f) return;  // fully occluded and nothing behind: all gradients are 0
   const float gd = sG[r_in], ga = sG[rpc + r_in];
   float gc[NCOL];
 #pragma unroll
   for (int k = 0; k < NCOL; ++k) gc[k] = __ldg(p.g_colour + (size_t)ray * NCOL + k);
 
+  RayCtx rc;
+  load_ray(p, ray, rc);
+  const float* u_row = p.jitter ? p.jitter + (size_t)ray * p.S : nullptr;
+  DepthWalker zw;
+  zw.init(p, rc, u_row, i0);
+  const bool use_noise = (p.noise_std != 0.f);
+  float Y[LT::K];
+  const float inv = 1.0f / rc.dnorm;
+  sh_basis<DEG>(rc.d[0] * inv, rc.d[1] * inv, rc.d[2] * inv, (p.flags & kDiffuse) != 0, Y);
+  float prefix = 0.f;  // sum of w*q over this segment's samples up to and including the current one
+
+#pragma unroll(kSampleUnroll)
+  for (int i = i0; i < i1; ++i, zw.advance(p, rc, u_row, i - 1)) {
+    const float zi = zw.cur;
+    const float px = __fadd_rn(rc.o[0], __fmul_rn(rc.d[0], zi));
+    const float py = __fadd_rn(rc.o[1], __fmul_rn(rc.d[1], zi));
+    const float pz = __fadd_rn(rc.o[2], __fmul_rn(rc.d[2], zi));
+    const bool in = inside_aabb(p, px, py, pz);
+    if (!in && !use_noise) continue;
+    float sigma = 0.f, dpost = 0.f, col[NCOL];
 #pragma unroll
-  for (int j = L - 1; j >= 0; --j) {
-    if (i0 + j >= p.S) continue;
-    const float alpha = s_alpha[j];
-    const float T = Tstart * s_T[j];
-    const float w = alpha * T;
-    float q = fmaf(gd, s_z[j], ga);
+    for (int k = 0; k < NCOL; ++k) col[k] = 0.f;
+    Corners c;
+    unsigned signs = 0u;
+    if (in) {
+      make_corners(p, px, py, pz, c);
+      float raw[NCOL];
+      const float sraw = gather_sample<DEG, NCOL>(p, c, Y, raw, signs);
+      sigma = post_act(p.postact, sraw, dpost);
 #pragma unroll
-    for (int k = 0; k < NCOL; ++k) q = fmaf(gc[k], s_col[j][k], q);
-    // dL/dsigma_i = delta_i * (T_{i+1} * q_i - sum_{j>i} w_j q_j)
-    const float dsigma = s_delta[j] * (T * (1.0f - alpha) * q - suffix);
-    suffix = fmaf(w, q, suffix);
-    if (!((in_mask >> j) & 1u)) continue;  // masked samples pass no gradient (process.py:80-91)
-    const float dsraw = dsigma * s_dpost[j] * p.dscale;
+      for (int k = 0; k < NCOL; ++k) col[k] = sigmoid_fast(raw[k]);
+    }
+    if (use_noise) sigma = fmaf(__ldg(p.noise + (size_t)ray * p.S + i), p.noise_std, sigma);
+    const bool last = (i == p.S - 1);
+    const float delta = (last ? kInfinity : __fsub_rn(zw.next, zi)) * rc.dnorm;
+    const float alpha = 1.0f - exp_fast(-(sigma * delta));
+    const float w = alpha * Tcur;
+    float q = fmaf(gd, zi, ga);
+#pragma unroll
+    for (int k = 0; k < NCOL; ++k) q = fmaf(gc[k], col[k], q);
+    prefix = fmaf(w, q, prefix);
+    const float Tnext = Tcur * (1.0f - alpha);
+    // dL/dsigma_i = delta_i * (T_{i+1} q_i - sum_{j>i} w_j q_j); the sum behind the very last sample is exactly 0
+    const float behind = last ? 0.f : (q_behind + (q_seg - prefix));
+    const float dsigma = delta * (Tnext * q - behind);
+    Tcur = Tnext;
+    if (!in) continue;  // masked samples pass no gradient
+    const float dsraw = dsigma * dpost * p.dscale;
     float draw[NCOL];
     bool any = (dsraw != 0.f);
 #pragma unroll
     for (int k = 0; k < NCOL; ++k) {
-      const float sc = s_col[j][k];
-      draw[k] = gc[k] * w * sc * (1.0f - sc);
+      draw[k] = gc[k] * w * col[k] * (1.0f - col[k]);
       any |= (draw[k] != 0.f);
     }
     if (!any) continue;
-    // gradient w.r.t. the interpolated channel vector
     float gfe[LT::CV * 4];
 #pragma unroll
     for (int k = 0; k < LT::CV * 4; ++k) gfe[k] = 0.f;
@@ -425,14 +403,9 @@ __global__ void __launch_bounds__(kMaxThreads) render_bwd_kernel(const __grid_co
     for (int ch = 0; ch < NCOL; ++ch)
 #pragma unroll
       for (int k = 0; k < LT::K; ++k) gfe[ch * LT::K + k] = draw[ch] * Y[k];
-    const unsigned signs = (j < 4) ? (s_signs >> (8 * j)) : (s_signs_hi >> (8 * (j - 4)));
-    Corners c;
-    make_corners(p, __fadd_rn(rc.o[0], __fmul_rn(rc.d[0], s_z[j])), __fadd_rn(rc.o[1], __fmul_rn(rc.d[1], s_z[j])),
-                 __fadd_rn(rc.o[2], __fmul_rn(rc.d[2], s_z[j])), c);
 #pragma unroll
     for (int qn = 0; qn < 8; ++qn) {
-      const float wq = c.w[qn];
-      if (wq == 0.f) continue;
+      const float wq = c.w[qn];  // zero only for the padded corners of border cells: those add 0 to a clamped address
       float4* dst = p.grad + (size_t)c.idx[qn] * LT::CV;
       const float gdens = ((signs >> qn) & 1u) ? -dsraw : dsraw;
 #pragma unroll
@@ -447,48 +420,49 @@ __global__ void __launch_bounds__(kMaxThreads) render_bwd_kernel(const __grid_co
   }
 }
 
-template <int DEG, int NCOL, int L>
+template <int DEG, int NCOL, int REGCAP>
 cudaError_t launch_pair(const KParams& p, bool backward, cudaStream_t stream) {
+  using LT = Layout<DEG, NCOL>;
   const int threads = ((p.rpc * p.nseg + 31) / 32) * 32;
+  if (threads > Bounds<REGCAP>::kThreads) return cudaErrorInvalidConfiguration;
   const int blocks = (p.R + p.rpc - 1) / p.rpc;
-  const int nv = NCOL + 2;
-  size_t smem = sizeof(float) * ((size_t)(1 + nv) * p.nseg * (p.rpc + 1) + (backward ? 2 * p.rpc : 0));
+  size_t smem = sizeof(float) * ((size_t)(1 + LT::NV) * p.nseg * (p.rpc + 1) + (backward ? 2 * p.rpc : 0));
   if (backward) {
-    auto k = render_bwd_kernel<DEG, NCOL, L>;
+    auto k = render_bwd_kernel<DEG, NCOL, REGCAP>;
     if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     k<<<blocks, threads, smem, stream>>>(p);
   } else {
-    auto k = render_fwd_kernel<DEG, NCOL, L>;
+    auto k = render_fwd_kernel<DEG, NCOL, REGCAP>;
     if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     k<<<blocks, threads, smem, stream>>>(p);
   }
   return cudaGetLastError();
 }
 
-template <int L>
+template <int REGCAP>
 cudaError_t dispatch_deg(const KParams& p, int deg, int ncol, bool backward, cudaStream_t stream) {
   if (ncol == 1) {
-    if (deg == 0) return launch_pair<0, 1, L>(p, backward, stream);
+    if (deg == 0) return launch_pair<0, 1, REGCAP>(p, backward, stream);
     return cudaErrorInvalidValue;
   }
   switch (deg) {
-    case 0: return launch_pair<0, 3, L>(p, backward, stream);
-    case 1: return launch_pair<1, 3, L>(p, backward, stream);
-    case 2: return launch_pair<2, 3, L>(p, backward, stream);
-    case 3: return launch_pair<3, 3, L>(p, backward, stream);
+    case 0: return launch_pair<0, 3, REGCAP>(p, backward, stream);
+    case 1: return launch_pair<1, 3, REGCAP>(p, backward, stream);
+    case 2: return launch_pair<2, 3, REGCAP>(p, backward, stream);
+    case 3: return launch_pair<3, 3, REGCAP>(p, backward, stream);
   }
   return cudaErrorInvalidValue;
 }
 
 }  // namespace
 
-cudaError_t launch_render(const KParams& p, int deg, int ncol, int samples_per_thread, bool backward,
-                          cudaStream_t stream) {
-  if (samples_per_thread == 4) return dispatch_deg<4>(p, deg, ncol, backward, stream);
-  if (samples_per_thread == 8) return dispatch_deg<8>(p, deg, ncol, backward, stream);
-  return cudaErrorInvalidValue;
+cudaError_t launch_render(const KParams& p, int deg, int ncol, int regcap, bool backward, cudaStream_t stream) {
+  if (regcap <= 64) return dispatch_deg<64>(p, deg, ncol, backward, stream);
+  return dispatch_deg<128>(p, deg, ncol, backward, stream);
 }
 
-int max_threads_per_cta() { return kMaxThreads; }
+int max_threads_per_cta(int regcap) { return regcap <= 64 ? Bounds<64>::kThreads : Bounds<128>::kThreads; }
+
+int saved_floats_per_segment(int ncol) { return ncol + 3; }
 
 }  // namespace voxe

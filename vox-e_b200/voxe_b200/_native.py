@@ -16,7 +16,7 @@ _lock = threading.Lock()
 _lib: Optional[ctypes.CDLL] = None
 
 # ---- enums of include/voxe.h -------------------------------------------------------------------------------
-ABI_VERSION = 1
+ABI_VERSION = 2
 PREACT_IDENTITY, PREACT_ABS = 0, 1
 POSTACT_IDENTITY, POSTACT_RELU, POSTACT_SOFTPLUS = 0, 1, 2
 FLAG_PERTURB, FLAG_AABB_SAMPLING, FLAG_DISPARITY_SAMPLING = 1, 2, 4
@@ -63,9 +63,10 @@ EXPORTS = {
     "voxe_packed_channels": (ctypes.c_int, [ctypes.c_int]),
     "voxe_pack_grid": (ctypes.c_int, [_GD, _P, _P, _P, _P]),
     "voxe_unpack_grad": (ctypes.c_int, [_GD, _P, _P, _P, ctypes.c_int, _P]),
-    "voxe_render_fwd": (ctypes.c_int, [_GD, _RD, _P, _P, _P, _P, _P, _P, _P, _P, _P, ctypes.c_int64, _P]),
-    "voxe_render_bwd": (ctypes.c_int, [_GD, _RD, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, ctypes.c_int64, _P]),
-    "voxe_set_tuning": (ctypes.c_int, [ctypes.c_int, ctypes.c_int]),
+    "voxe_saved_floats": (ctypes.c_int64, [_RD, ctypes.c_int64]),
+    "voxe_render_fwd": (ctypes.c_int, [_GD, _RD, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, ctypes.c_int64, _P]),
+    "voxe_render_bwd": (ctypes.c_int, [_GD, _RD, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, ctypes.c_int64, _P]),
+    "voxe_set_tuning": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int]),
     "voxe_launch_count": (ctypes.c_int64, []),
 }
 
@@ -118,5 +119,7 @@ def launch_count() -> int:
     return int(load_library().voxe_launch_count())
 
 
-def set_tuning(samples_per_thread: int = 0, rays_per_cta: int = 0) -> None:
-    check(load_library().voxe_set_tuning(samples_per_thread, rays_per_cta), "voxe_set_tuning")
+def set_tuning(samples_per_thread: int = 0, rays_per_cta: int = 0, register_cap: int = 0) -> None:
+    """Launch-shape override for tuning runs (0 = built-in choice).  Do not change it between a forward call and its
+    backward: the ``saved`` workspace layout depends on it."""
+    check(load_library().voxe_set_tuning(samples_per_thread, rays_per_cta, register_cap), "voxe_set_tuning")

@@ -148,20 +148,24 @@ class _FusedRender(torch.autograd.Function):
         acc = torch.empty((R, 1), dtype=torch.float32, device=dev)
         disp = torch.empty((R, 1), dtype=torch.float32, device=dev)
         gd, rd = gspec.to_native(), rspec.to_native()
+        # segment summaries linking this call to its backward: < 1 float per sample instead of autograd's ~35
+        need_grad = bool(ctx.needs_input_grad[0] or ctx.needs_input_grad[1])
+        saved = torch.empty(int(lib.voxe_saved_floats(rd, R)), dtype=torch.float32, device=dev) if need_grad else None
         with torch.cuda.device(dev):
             nat.check(
                 lib.voxe_render_fwd(gd, rd, packed.data_ptr(), rays_o.data_ptr(), rays_d.data_ptr(), _ptr(jitter), _ptr(noise),
-                                    colour.data_ptr(), depth.data_ptr(), acc.data_ptr(), disp.data_ptr(), R, _stream_ptr(dev)),
+                                    colour.data_ptr(), depth.data_ptr(), acc.data_ptr(), disp.data_ptr(), _ptr(saved), R,
+                                    _stream_ptr(dev)),
                 "voxe_render_fwd",
             )
         ctx.set_materialize_grads(False)
         ctx.gspec, ctx.rspec = gspec, rspec
-        ctx.save_for_backward(densities, features, packed, rays_o, rays_d, jitter, noise)
+        ctx.save_for_backward(densities, features, packed, rays_o, rays_d, jitter, noise, saved)
         return colour, depth, acc, disp
 
     @staticmethod
     def backward(ctx, g_colour, g_depth, g_acc, g_disp):
-        densities, features, packed, rays_o, rays_d, jitter, noise = ctx.saved_tensors
+        densities, features, packed, rays_o, rays_d, jitter, noise, saved = ctx.saved_tensors
         need_d, need_f = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
         none9 = (None,) * 9
         if not (need_d or need_f):
@@ -183,7 +187,7 @@ class _FusedRender(torch.autograd.Function):
             s = _stream_ptr(dev)
             nat.check(
                 lib.voxe_render_bwd(gd, rd, packed.data_ptr(), rays_o.data_ptr(), rays_d.data_ptr(), _ptr(jitter), _ptr(noise),
-                                    _ptr(gs[0]), _ptr(gs[1]), _ptr(gs[2]), _ptr(gs[3]), packed_grad.data_ptr(), R, s),
+                                    saved.data_ptr(), _ptr(gs[0]), _ptr(gs[1]), _ptr(gs[2]), _ptr(gs[3]), packed_grad.data_ptr(), R, s),
                 "voxe_render_bwd",
             )
             nat.check(lib.voxe_unpack_grad(gd, packed_grad.data_ptr(), _ptr(d_dens), _ptr(d_feat), 0, s), "voxe_unpack_grad")
