@@ -317,6 +317,29 @@ def build_volmodel(ref, seed):
                 meta=np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8))
 
 
+def build_checkpoint(ref, seed):
+    """A model file written by the reference itself (torch.save of VolumetricModel.get_save_info, trainers.py:460-469):
+    pickles the reference's import paths for render_sh_voxel_grid, SHVoxGridRenderConfig, VoxelSize, CameraBounds, ..."""
+    rng = np.random.default_rng(seed)
+    dims = (6, 7, 8)
+    dens, feat = blob_grid(dims, 3, rng)
+    grid = ref["VoxelGrid"](
+        densities=torch.from_numpy(dens.copy()), features=torch.from_numpy(feat.copy()),
+        voxel_size=ref["VoxelSize"](0.5, 0.4, 0.3), grid_location=ref["VoxelGridLocation"](0.1, 0.0, -0.1),
+        density_preactivation=torch.nn.Identity(), density_postactivation=torch.nn.Softplus(), expected_density_scale=33.333,
+        tunable=True,
+    )
+    vm = ref["VolumetricModel"](
+        thre3d_repr=grid, render_procedure=ref["render_sh_voxel_grid"],
+        render_config=ref["SHVoxGridRenderConfig"](num_samples_per_ray=64, camera_bounds=ref["CameraBounds"](1.8, 6.6), white_bkgd=True),
+        device=torch.device("cpu"),
+    )
+    info = vm.get_save_info(extra_info={"camera_bounds": ref["CameraBounds"](1.8, 6.6),
+                                        "camera_intrinsics": ref["CameraIntrinsics"](100, 100, 140.0), "hemispherical_radius": 4.0311})
+    torch.save(info, OUT_DIR / "reference_checkpoint.pth")
+    np.savez_compressed(OUT_DIR / "reference_checkpoint_values.npz", densities=dens, features=feat)
+
+
 def main():
     ref = _import_reference()
     torch.set_num_threads(1)  # deterministic reduction order for the goldens
@@ -328,6 +351,7 @@ def main():
     np.savez_compressed(OUT_DIR / "attn.npz", **build_attn_case(ref, 142))
     np.savez_compressed(OUT_DIR / "cameras.npz", **build_cameras(ref))
     np.savez_compressed(OUT_DIR / "volmodel.npz", **build_volmodel(ref, 242))
+    build_checkpoint(ref, 342)
     print("done")
 
 
