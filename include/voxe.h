@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define VOXE_ABI_VERSION 2
+#define VOXE_ABI_VERSION 3
 
 #if defined(__GNUC__)
 #define VOXE_API __attribute__((visibility("default")))
@@ -103,7 +103,12 @@ VOXE_API const char* voxe_last_error(void);
 /* roundup4(n_features + 1): channel count of the packed volume. */
 VOXE_API int voxe_packed_channels(int n_features);
 
-/* packed[X,Y,Z,C] <- concat(features[X,Y,Z,F], densities[X,Y,Z,1], zero padding).  Values are copied verbatim;
+/* Number of floats of the packed volume of `grid`: channels * 8 * ceil(X/2) * ceil(Y/2) * ceil(Z/2).  The volume is
+ * stored as 2x2x2 bricks of voxels (one brick of SH-0 voxels = one 128-byte line) -- an internal layout: only
+ * voxe_pack_grid / voxe_unpack_grad convert to and from the reference's [X,Y,Z,.] tensors. */
+VOXE_API int64_t voxe_packed_floats(const VoxeGridDesc* grid);
+
+/* packed <- bricked concat(features[X,Y,Z,F], densities[X,Y,Z,1], zero padding).  Values are copied verbatim;
  * density scale and pre-activation are applied inside the render kernels at gather time. */
 VOXE_API int voxe_pack_grid(const VoxeGridDesc* grid, const float* densities, const float* features, float* packed,
                    voxe_stream_t stream);
@@ -120,7 +125,7 @@ VOXE_API int voxe_unpack_grad(const VoxeGridDesc* grid, const float* packed_grad
 VOXE_API int64_t voxe_saved_floats(const VoxeRenderDesc* render, int64_t num_rays);
 
 /* Forward render of R rays.
- *   packed   [X,Y,Z,C]   from voxe_pack_grid
+ *   packed   voxe_packed_floats() floats from voxe_pack_grid
  *   rays_o/d [R,3]       origins / (un-normalised) directions
  *   jitter   [R,S] or NULL   the U[0,1) draws of sample.py:63 (required with VOXE_FLAG_PERTURB)
  *   noise    [R,S] or NULL   the N(0,1) draws of accumulate.py:59-62 (required when noise_std != 0)
@@ -132,7 +137,7 @@ VOXE_API int voxe_render_fwd(const VoxeGridDesc* grid, const VoxeRenderDesc* ren
                     voxe_stream_t stream);
 
 /* Backward: re-gathers per sample (no O(R*S) activations are stored), and scatter-ADDS dL/d(packed) into
- * `packed_grad` [X,Y,Z,C] (caller-zeroed; accumulate-into, so several ray batches or both renders of a training step
+ * `packed_grad` (same layout and size as `packed`; caller-zeroed; accumulate-into, so several ray batches or both renders of a training step
  * can share one buffer).  `saved` is the workspace the matching forward call filled (same grid, rays, jitter, noise).
  * g_depth / g_acc / g_disp may be NULL (treated as zero).  The disparity gradient is applied only on rays whose
  * disparity is finite (depth/acc > 1e-10). */

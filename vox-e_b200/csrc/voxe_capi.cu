@@ -36,7 +36,7 @@ int check_grid(const VoxeGridDesc* g) {
   if (g->channels != voxe_packed_channels(g->n_features))
     return fail(VOXE_ERR_INVALID_ARGUMENT, "channels must be roundup4(n_features+1) = %d (got %d)",
                 voxe_packed_channels(g->n_features), g->channels);
-  const int64_t nvec = (int64_t)g->dims[0] * g->dims[1] * g->dims[2] * (g->channels / 4);
+  const int64_t nvec = voxe::packed_voxel_slots(g->dims) * (g->channels / 4);
   if (nvec >= (int64_t)1 << 31) return fail(VOXE_ERR_UNSUPPORTED, "packed grid has %lld 16-byte vectors; limit is 2^31", (long long)nvec);
   if (g->preact != VOXE_PREACT_IDENTITY && g->preact != VOXE_PREACT_ABS)
     return fail(VOXE_ERR_UNSUPPORTED, "density pre-activation %d is not in the fused set {identity, abs}", g->preact);
@@ -90,6 +90,8 @@ int fill_params(const VoxeGridDesc* g, const VoxeRenderDesc* r, int64_t R, voxe:
   p.X = g->dims[0];
   p.Y = g->dims[1];
   p.Z = g->dims[2];
+  p.sby = ((g->dims[2] + 1) / 2) * 8;
+  p.sbx = ((g->dims[1] + 1) / 2) * p.sby;
   for (int a = 0; a < 3; ++a) {
     p.lo[a] = g->aabb_lo[a];
     p.hi[a] = g->aabb_hi[a];
@@ -118,6 +120,11 @@ const char* voxe_last_error(void) { return g_error; }
 
 int voxe_packed_channels(int n_features) { return ((n_features + 1 + 3) / 4) * 4; }
 
+int64_t voxe_packed_floats(const VoxeGridDesc* grid) {
+  if (!grid || grid->dims[0] < 1 || grid->dims[1] < 1 || grid->dims[2] < 1 || grid->channels < 4) return 0;
+  return voxe::packed_voxel_slots(grid->dims) * grid->channels;
+}
+
 int64_t voxe_launch_count(void) { return g_launches.load(); }
 
 int voxe_set_tuning(int samples_per_thread, int rays_per_cta, int register_cap) {
@@ -144,8 +151,7 @@ int voxe_pack_grid(const VoxeGridDesc* grid, const float* densities, const float
                    voxe_stream_t stream) {
   if (int rc = check_grid(grid)) return rc;
   if (!densities || !features || !packed) return fail(VOXE_ERR_INVALID_ARGUMENT, "voxe_pack_grid: NULL buffer");
-  const int64_t nvox = (int64_t)grid->dims[0] * grid->dims[1] * grid->dims[2];
-  cudaError_t e = voxe::launch_pack_grid(densities, features, packed, nvox, grid->n_features, grid->channels,
+  cudaError_t e = voxe::launch_pack_grid(densities, features, packed, grid->dims, grid->n_features, grid->channels,
                                          (cudaStream_t)stream);
   if (e != cudaSuccess) return cuda_fail(e, "voxe_pack_grid launch");
   g_launches.fetch_add(1);
@@ -157,8 +163,7 @@ int voxe_unpack_grad(const VoxeGridDesc* grid, const float* packed_grad, float* 
   if (int rc = check_grid(grid)) return rc;
   if (!packed_grad) return fail(VOXE_ERR_INVALID_ARGUMENT, "voxe_unpack_grad: NULL packed_grad");
   if (!d_densities && !d_features) return VOXE_OK;
-  const int64_t nvox = (int64_t)grid->dims[0] * grid->dims[1] * grid->dims[2];
-  cudaError_t e = voxe::launch_unpack_grad(packed_grad, d_densities, d_features, nvox, grid->n_features,
+  cudaError_t e = voxe::launch_unpack_grad(packed_grad, d_densities, d_features, grid->dims, grid->n_features,
                                            grid->channels, accumulate != 0, (cudaStream_t)stream);
   if (e != cudaSuccess) return cuda_fail(e, "voxe_unpack_grad launch");
   g_launches.fetch_add(1);

@@ -37,6 +37,7 @@ struct KParams {
   const float* g_disp;
   int R, S;
   int X, Y, Z;
+  int sbx, sby;   // brick strides in voxels: voxel (x,y,z) lives at (x>>1)*sbx + (y>>1)*sby + (z>>1)*8 + (x&1)*4 + (y&1)*2 + (z&1)
   float lo[3], hi[3];
   float ua[3], ub[3];   // voxel-space coordinate u = p*ua + ub  (= ((p*nscale + nbias + 1) * N - 1) / 2, folded on the host)
   float near, far, dscale, noise_std, lin_step;
@@ -133,7 +134,7 @@ __device__ __forceinline__ void sh_basis(float x, float y, float z, bool diffuse
 // trilinear corner set (grid_sample: bilinear, zeros padding, align_corners=False)
 // ---------------------------------------------------------------------------------------------------------
 struct Corners {
-  int idx[8];   // linear voxel index (clamped into range; weight is zero when the true corner is outside)
+  int idx[8];   // voxel slot in the bricked volume (clamped into range; weight is zero when the true corner is outside)
   float w[8];
 };
 
@@ -164,16 +165,19 @@ __device__ __forceinline__ void make_corners(const KParams& p, float px, float p
   axis_setup(px, p.ua[0], p.ub[0], p.X, x0, x1, wx0, wx1);
   axis_setup(py, p.ua[1], p.ub[1], p.Y, y0, y1, wy0, wy1);
   axis_setup(pz, p.ua[2], p.ub[2], p.Z, z0, z1, wz0, wz1);
-  const int r00 = (x0 * p.Y + y0) * p.Z, r01 = (x0 * p.Y + y1) * p.Z;
-  const int r10 = (x1 * p.Y + y0) * p.Z, r11 = (x1 * p.Y + y1) * p.Z;
-  c.idx[0] = r00 + z0; c.w[0] = wx0 * wy0 * wz0;
-  c.idx[1] = r00 + z1; c.w[1] = wx0 * wy0 * wz1;
-  c.idx[2] = r01 + z0; c.w[2] = wx0 * wy1 * wz0;
-  c.idx[3] = r01 + z1; c.w[3] = wx0 * wy1 * wz1;
-  c.idx[4] = r10 + z0; c.w[4] = wx1 * wy0 * wz0;
-  c.idx[5] = r10 + z1; c.w[5] = wx1 * wy0 * wz1;
-  c.idx[6] = r11 + z0; c.w[6] = wx1 * wy1 * wz0;
-  c.idx[7] = r11 + z1; c.w[7] = wx1 * wy1 * wz1;
+  // 2x2x2-brick addressing (one brick of SH-0 voxels = one 128-byte line): per-axis partial offsets, then 8 sums
+  const int xa0 = (x0 >> 1) * p.sbx + ((x0 & 1) << 2), xa1 = (x1 >> 1) * p.sbx + ((x1 & 1) << 2);
+  const int ya0 = (y0 >> 1) * p.sby + ((y0 & 1) << 1), ya1 = (y1 >> 1) * p.sby + ((y1 & 1) << 1);
+  const int za0 = ((z0 >> 1) << 3) + (z0 & 1), za1 = ((z1 >> 1) << 3) + (z1 & 1);
+  const int r00 = xa0 + ya0, r01 = xa0 + ya1, r10 = xa1 + ya0, r11 = xa1 + ya1;
+  c.idx[0] = r00 + za0; c.w[0] = wx0 * wy0 * wz0;
+  c.idx[1] = r00 + za1; c.w[1] = wx0 * wy0 * wz1;
+  c.idx[2] = r01 + za0; c.w[2] = wx0 * wy1 * wz0;
+  c.idx[3] = r01 + za1; c.w[3] = wx0 * wy1 * wz1;
+  c.idx[4] = r10 + za0; c.w[4] = wx1 * wy0 * wz0;
+  c.idx[5] = r10 + za1; c.w[5] = wx1 * wy0 * wz1;
+  c.idx[6] = r11 + za0; c.w[6] = wx1 * wy1 * wz0;
+  c.idx[7] = r11 + za1; c.w[7] = wx1 * wy1 * wz1;
 }
 
 __device__ __forceinline__ float f4_get(const float4& v, int k) {

@@ -9,29 +9,55 @@
 namespace voxe {
 namespace {
 
-// one thread per packed float4: packed[v][4j..4j+3]
+// Packed volume layout: 2x2x2 bricks of voxels, bricks in (x, y, z) row-major order, 8 voxel slots per brick ordered
+// (x&1, y&1, z&1), CV float4 per slot.  At SH-0 (CV = 1) a brick is exactly one 128-byte line, so the 8 corners of a
+// trilinear cell touch 1..8 lines (3.4 on average) instead of 4..8, and neighbouring rays share lines in x and y as
+// well as in z.  Slots of partial bricks at odd grid dimensions are zero and never addressed by the kernels.
+struct BrickDims {
+  int X, Y, Z, BY, BZ;
+};
+
+__device__ __forceinline__ bool slot_to_voxel(const BrickDims& d, int64_t slot, int64_t& v) {
+  const int64_t brick = slot >> 3;
+  const int within = (int)(slot & 7);
+  const int bz = (int)(brick % d.BZ);
+  const int64_t t = brick / d.BZ;
+  const int by = (int)(t % d.BY);
+  const int bx = (int)(t / d.BY);
+  const int x = 2 * bx + (within >> 2), y = 2 * by + ((within >> 1) & 1), z = 2 * bz + (within & 1);
+  v = ((int64_t)x * d.Y + y) * d.Z + z;
+  return x < d.X && y < d.Y && z < d.Z;
+}
+
+// one thread per packed float4: slot = t / CV, channels 4j..4j+3
 __global__ void __launch_bounds__(256) pack_grid_kernel(const float* __restrict__ dens, const float* __restrict__ feat,
-                                                        float4* __restrict__ packed, int64_t n_vec, int F, int CV) {
+                                                        float4* __restrict__ packed, int64_t n_vec, int F, int CV,
+                                                        BrickDims d) {
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n_vec) return;
-  const int64_t v = t / CV;
-  const int c0 = (int)(t - v * CV) * 4;
-  float out[4];
+  const int64_t slot = t / CV;
+  const int c0 = (int)(t - slot * CV) * 4;
+  int64_t v;
+  float out[4] = {0.f, 0.f, 0.f, 0.f};
+  if (slot_to_voxel(d, slot, v)) {
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const int c = c0 + k;
-    out[k] = (c < F) ? __ldg(feat + v * F + c) : (c == F ? __ldg(dens + v) : 0.f);
+    for (int k = 0; k < 4; ++k) {
+      const int c = c0 + k;
+      out[k] = (c < F) ? __ldg(feat + v * F + c) : (c == F ? __ldg(dens + v) : 0.f);
+    }
   }
   packed[t] = make_float4(out[0], out[1], out[2], out[3]);
 }
 
 __global__ void __launch_bounds__(256) unpack_grad_kernel(const float4* __restrict__ pg, float* __restrict__ d_dens,
                                                           float* __restrict__ d_feat, int64_t n_vec, int F, int CV,
-                                                          int accumulate) {
+                                                          int accumulate, BrickDims d) {
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n_vec) return;
-  const int64_t v = t / CV;
-  const int c0 = (int)(t - v * CV) * 4;
+  const int64_t slot = t / CV;
+  const int c0 = (int)(t - slot * CV) * 4;
+  int64_t v;
+  if (!slot_to_voxel(d, slot, v)) return;
   const float4 g = __ldg(pg + t);
   const float in[4] = {g.x, g.y, g.z, g.w};
 #pragma unroll
@@ -51,28 +77,34 @@ __global__ void __launch_bounds__(256) unpack_grad_kernel(const float4* __restri
   }
 }
 
+BrickDims brick_dims(const int dims[3]) { return BrickDims{dims[0], dims[1], dims[2], (dims[1] + 1) / 2, (dims[2] + 1) / 2}; }
+
 }  // namespace
 
-cudaError_t launch_pack_grid(const float* densities, const float* features, float* packed, int64_t n_voxels,
+int64_t packed_voxel_slots(const int dims[3]) {
+  return (int64_t)((dims[0] + 1) / 2) * ((dims[1] + 1) / 2) * ((dims[2] + 1) / 2) * 8;
+}
+
+cudaError_t launch_pack_grid(const float* densities, const float* features, float* packed, const int dims[3],
                              int n_features, int channels, cudaStream_t stream) {
   const int CV = channels / 4;
-  const int64_t n_vec = n_voxels * CV;
+  const int64_t n_vec = packed_voxel_slots(dims) * CV;
   const int threads = 256;
   const int64_t blocks = (n_vec + threads - 1) / threads;
   pack_grid_kernel<<<(unsigned)blocks, threads, 0, stream>>>(densities, features, reinterpret_cast<float4*>(packed),
-                                                             n_vec, n_features, CV);
+                                                             n_vec, n_features, CV, brick_dims(dims));
   return cudaGetLastError();
 }
 
-cudaError_t launch_unpack_grad(const float* packed_grad, float* d_densities, float* d_features, int64_t n_voxels,
+cudaError_t launch_unpack_grad(const float* packed_grad, float* d_densities, float* d_features, const int dims[3],
                                int n_features, int channels, bool accumulate, cudaStream_t stream) {
   const int CV = channels / 4;
-  const int64_t n_vec = n_voxels * CV;
+  const int64_t n_vec = packed_voxel_slots(dims) * CV;
   const int threads = 256;
   const int64_t blocks = (n_vec + threads - 1) / threads;
   unpack_grad_kernel<<<(unsigned)blocks, threads, 0, stream>>>(reinterpret_cast<const float4*>(packed_grad),
                                                                d_densities, d_features, n_vec, n_features, CV,
-                                                               accumulate ? 1 : 0);
+                                                               accumulate ? 1 : 0, brick_dims(dims));
   return cudaGetLastError();
 }
 

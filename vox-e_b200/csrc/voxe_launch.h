@@ -13,9 +13,10 @@ int max_threads_per_cta(int regcap);
 int saved_floats_per_segment(int n_colour);
 
 // full-grid passes (voxe_grid_ops.cu)
-cudaError_t launch_pack_grid(const float* densities, const float* features, float* packed, int64_t n_voxels,
+int64_t packed_voxel_slots(const int dims[3]);  // voxel slots of the 2x2x2-bricked volume (>= X*Y*Z)
+cudaError_t launch_pack_grid(const float* densities, const float* features, float* packed, const int dims[3],
                              int n_features, int channels, cudaStream_t stream);
-cudaError_t launch_unpack_grad(const float* packed_grad, float* d_densities, float* d_features, int64_t n_voxels,
+cudaError_t launch_unpack_grad(const float* packed_grad, float* d_densities, float* d_features, const int dims[3],
                                int n_features, int channels, bool accumulate, cudaStream_t stream);
 
 }  // namespace voxe

@@ -16,7 +16,7 @@ _lock = threading.Lock()
 _lib: Optional[ctypes.CDLL] = None
 
 # ---- enums of include/voxe.h -------------------------------------------------------------------------------
-ABI_VERSION = 2
+ABI_VERSION = 3
 PREACT_IDENTITY, PREACT_ABS = 0, 1
 POSTACT_IDENTITY, POSTACT_RELU, POSTACT_SOFTPLUS = 0, 1, 2
 FLAG_PERTURB, FLAG_AABB_SAMPLING, FLAG_DISPARITY_SAMPLING = 1, 2, 4
@@ -61,6 +61,7 @@ EXPORTS = {
     "voxe_abi_version": (ctypes.c_int, []),
     "voxe_last_error": (ctypes.c_char_p, []),
     "voxe_packed_channels": (ctypes.c_int, [ctypes.c_int]),
+    "voxe_packed_floats": (ctypes.c_int64, [_GD]),
     "voxe_pack_grid": (ctypes.c_int, [_GD, _P, _P, _P, _P]),
     "voxe_unpack_grad": (ctypes.c_int, [_GD, _P, _P, _P, ctypes.c_int, _P]),
     "voxe_saved_floats": (ctypes.c_int64, [_RD, ctypes.c_int64]),

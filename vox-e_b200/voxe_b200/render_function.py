@@ -96,13 +96,15 @@ def _stream_ptr(dev: torch.device) -> int:
 
 
 def pack_volume(spec: FusedGridSpec, densities: Tensor, features: Tensor, out: Optional[Tensor] = None) -> Tensor:
-    """packed[X,Y,Z,C] = concat(features, densities, 0-padding) via ``voxe_pack_grid``."""
+    """Packed volume (2x2x2 bricks of concat(features, densities, 0-padding) voxels) via ``voxe_pack_grid``: a flat
+    fp32 tensor whose layout is private to the library."""
     dev = _require_cuda(densities, features)
     lib = nat.load_library()
     dens, feat = densities.detach().contiguous(), features.detach().contiguous()
-    if out is None:
-        out = torch.empty((*spec.dims, spec.channels), dtype=torch.float32, device=dev)
     gd = spec.to_native()
+    n = int(lib.voxe_packed_floats(gd))
+    if out is None or out.numel() != n or out.device != dev:
+        out = torch.empty(n, dtype=torch.float32, device=dev)
     with torch.cuda.device(dev):
         nat.check(lib.voxe_pack_grid(gd, dens.data_ptr(), feat.data_ptr(), out.data_ptr(), _stream_ptr(dev)), "voxe_pack_grid")
     return out
@@ -127,10 +129,7 @@ class PackedVolumeCache:
     def get(self, spec: FusedGridSpec, densities: Tensor, features: Tensor) -> Tensor:
         key = (densities.data_ptr(), densities._version, features.data_ptr(), features._version, densities.device, spec)
         if key != self._key or self._packed is None:
-            reuse = self._packed
-            if reuse is not None and (reuse.device != densities.device or reuse.shape != (*spec.dims, spec.channels)):
-                reuse = None
-            self._packed = pack_volume(spec, densities, features, out=reuse)
+            self._packed = pack_volume(spec, densities, features, out=self._packed)
             self._key = key
         return self._packed
 
