@@ -227,13 +227,24 @@ class VoxelGrid(Module):
     # ------------------------------------------------------------------------------------------------------
     def fused_spec(self, n_features: Optional[int] = None) -> FusedGridSpec:
         """Describe this grid to the CUDA kernels; rejects activations the kernels do not fuse."""
+        nf = int(self._features.shape[-1]) if n_features is None else int(n_features)
+        key = (nf, id(self._density_preactivation), id(self._density_postactivation), id(self._feature_preactivation),
+               id(self._feature_postactivation), self._aabb, self._expected_density_scale, self.grid_dims)
+        cached = getattr(self, "_fused_spec_cache", None)
+        if cached is not None and cached[0] == key:
+            return cached[1]
+        spec = self._build_fused_spec(nf)
+        self._fused_spec_cache = (key, spec)
+        return spec
+
+    def _build_fused_spec(self, n_features: int) -> FusedGridSpec:
         for name in ("_feature_preactivation", "_feature_postactivation"):
             if not isinstance(getattr(self, name), torch.nn.Identity):
                 raise NotImplementedError(f"{name[1:]} must be torch.nn.Identity() on the fused render path")
         return FusedGridSpec(
             dims=self.grid_dims,
-            n_features=int(self._features.shape[-1]) if n_features is None else int(n_features),
-            aabb=tuple((float(lo), float(hi)) for lo, hi in self._aabb),
+            n_features=int(n_features),
+            aabb=tuple((float(lo), float(hi)) for lo, hi in self._aabb),  # fixed at construction, as upstream
             density_scale=float(self._expected_density_scale),
             preact=_classify_preactivation(self._density_preactivation),
             postact=_classify_postactivation(self._density_postactivation),

@@ -12,6 +12,7 @@ parameters, as autograd would have produced.  Rays never receive gradients (they
 from __future__ import annotations
 
 import dataclasses
+import functools
 from typing import Optional, Tuple
 
 import numpy as np
@@ -36,6 +37,7 @@ class FusedGridSpec:
     def channels(self) -> int:
         return ((self.n_features + 1 + 3) // 4) * 4
 
+    @functools.lru_cache(maxsize=64)  # frozen + hashable: the ctypes struct is built once per distinct grid description
     def to_native(self) -> nat.VoxeGridDesc:
         d = nat.VoxeGridDesc()
         for a in range(3):
@@ -65,6 +67,7 @@ class FusedRenderSpec:
     n_colour: int
     noise_std: float = 0.0
 
+    @functools.lru_cache(maxsize=256)
     def to_native(self) -> nat.VoxeRenderDesc:
         r = nat.VoxeRenderDesc()
         r.num_samples, r.near, r.far = int(self.num_samples), float(self.near), float(self.far)
@@ -173,10 +176,12 @@ class _FusedRender(torch.autograd.Function):
         dev = packed.device
         lib = nat.load_library()
         R = rays_o.shape[0]
-        d_dens = torch.zeros_like(densities, memory_format=torch.contiguous_format) if need_d else None
-        d_feat = torch.zeros_like(features, memory_format=torch.contiguous_format) if need_f else None
         if all(g is None for g in (g_colour, g_depth, g_acc, g_disp)):
-            return (d_dens, d_feat) + (None,) * 7
+            zeros = lambda t, need: torch.zeros_like(t, memory_format=torch.contiguous_format) if need else None  # noqa: E731
+            return (zeros(densities, need_d), zeros(features, need_f)) + (None,) * 7
+        # fully overwritten by voxe_unpack_grad(accumulate=0): no zero-fill needed
+        d_dens = torch.empty_like(densities, memory_format=torch.contiguous_format) if need_d else None
+        d_feat = torch.empty_like(features, memory_format=torch.contiguous_format) if need_f else None
         if g_colour is None:
             g_colour = torch.zeros((R, rspec.n_colour), dtype=torch.float32, device=dev)
         gs = [None if g is None else g.contiguous().float() for g in (g_colour, g_depth, g_acc, g_disp)]
