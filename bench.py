@@ -536,7 +536,7 @@ def run_ours(args):
             "peak_source": peak_note, "kernel": "render_bwd_kernel<DEG=0,NCOL=3,L=8>", "us_per_launch": round(bwd_us, 2),
             "algorithmic_bytes_per_launch": round(bwd_bytes), "fwd_kernel": {"us_per_launch": round(fwd_us, 2),
             "achieved": round(fwd_bytes / (fwd_us * 1e-6) / 1e9, 1), "frac": round(fwd_bytes / (fwd_us * 1e-6) / 1e9 / peak, 4)},
-            "step": {"achieved": round(step_gbs / world, 1), "frac": round(step_gbs / world / peak, 4),
+            "step": {"achieved": round(step_gbs, 1), "frac": round(step_gbs / peak, 4),  # per GPU (each rank renders its own frame)
                      "bytes_per_ray": round(step_bytes / bench.R, 1), "s_in_per_ray": round(s_in_mean / bench.R, 2)},
         }
     if world > 1:

@@ -25,7 +25,10 @@ is pinned against outputs of the *executed* reference: ``tests/golden/make_golde
 ``/root/reference`` in the build container and writes ``tests/golden/*.npz``;
 ``tests/test_oracle_vs_golden.py`` checks this file against every one of them (forward outputs and voxel
 gradients).  Gradients come from torch autograd over this restatement (``dtype=torch.float64`` is the
-"truth" mode, ``torch.float32`` mimics the reference's rounding).
+"truth" mode, ``torch.float32`` mimics the reference's rounding).  It is written with whole-tensor torch ops like the
+reference itself and runs on whatever device its inputs live on: the CPU everywhere it is used as a baseline, and -- for
+the 15 GB grid of BASELINE.json's largest configuration only -- a CUDA device, where it is still plain ATen arithmetic
+independent of the kernels under test.
 """
 from __future__ import annotations
 
@@ -125,12 +128,13 @@ def ray_intervals(
 ) -> Tuple[Tensor, Tensor]:
     """Per-ray (near, far).  sample.py:38-44 for the plain case; sample.py:71-184 for the slab test."""
     R = rays_o.shape[0]
-    near = torch.full((R,), cfg.near, dtype=dtype)
-    far = torch.full((R,), cfg.far, dtype=dtype)
+    dev = rays_o.device
+    near = torch.full((R,), cfg.near, dtype=dtype, device=dev)
+    far = torch.full((R,), cfg.far, dtype=dtype, device=dev)
     if not cfg.optimized_sampling:
         return near, far
     lo = hi = None
-    hit = torch.ones(R, dtype=torch.bool)
+    hit = torch.ones(R, dtype=torch.bool, device=dev)
     for axis in range(3):
         denom = rays_d[:, axis] + ZERO_PLUS
         t0 = (aabb[axis][0] - rays_o[:, axis]) / denom
@@ -152,7 +156,7 @@ def sample_depths(near: Tensor, far: Tensor, cfg: OracleConfig, jitter: Optional
     """z_vals [R,S].  sample.py:46-64.  Disparity sampling is only reachable without optimized_sampling
     (renderers.py:66-78)."""
     S = cfg.num_samples
-    t = torch.linspace(0.0, 1.0, S, dtype=dtype)[None, :]
+    t = torch.linspace(0.0, 1.0, S, dtype=dtype, device=near.device)[None, :]
     n, f = near[:, None], far[:, None]
     if cfg.linear_disparity_sampling and not cfg.optimized_sampling:
         z = 1.0 / (1.0 / (n + ZERO_PLUS) * (1.0 - t) + 1.0 / f * t)
@@ -199,7 +203,7 @@ def trilinear_fetch(vol: Tensor, pts: Tensor, aabb, dtype) -> Tensor:
         i0 = torch.floor(u)
         idx0.append(i0.long())
         frac.append(u - i0)
-    out = torch.zeros(pts.shape[0], C, dtype=dtype)
+    out = torch.zeros(pts.shape[0], C, dtype=dtype, device=pts.device)
     flat = vol.reshape(-1, C)
     for dx in (0, 1):
         for dy in (0, 1):
@@ -247,7 +251,7 @@ def render_oracle(
     near, far = ray_intervals(ro32, rd32, cfg, aabb, torch.float32)
     z32 = sample_depths(near, far, cfg, jitter, torch.float32)  # [R,S]
     pts32 = (ro32[:, None, :] + rd32[:, None, :] * z32[:, :, None]).reshape(-1, 3)
-    inside = torch.ones(pts32.shape[0], dtype=torch.bool)
+    inside = torch.ones(pts32.shape[0], dtype=torch.bool, device=pts32.device)
     for a in range(3):
         inside &= (pts32[:, a] > aabb[a][0]) & (pts32[:, a] < aabb[a][1])  # python double vs fp32 tensor, as voxels.py:263-285
     inside = inside.reshape(R, S)
@@ -272,16 +276,16 @@ def render_oracle(
 
     # strict inside test on the world-space points (voxels.py:263-285; process.py:80-84): mask computed above
     raw = torch.where(inside[..., None], raw, torch.full_like(raw, -INFINITY))
-    sigma = torch.where(inside, sigma.reshape(R, S), torch.zeros(R, S, dtype=dtype))
+    sigma = torch.where(inside, sigma.reshape(R, S), torch.zeros(R, S, dtype=dtype, device=sigma.device))
 
     # compositing (accumulate.py:49-88)
-    delta = torch.cat([z[:, 1:] - z[:, :-1], torch.full((R, 1), INFINITY, dtype=dtype)], dim=-1)
+    delta = torch.cat([z[:, 1:] - z[:, :-1], torch.full((R, 1), INFINITY, dtype=dtype, device=z.device)], dim=-1)
     delta = delta * torch.linalg.norm(rays_d, dim=-1, keepdim=True)
     if cfg.noise_std != 0.0:
         assert noise is not None
         sigma = sigma + noise.to(dtype) * cfg.noise_std
     alpha = 1.0 - torch.exp(-(sigma * delta))
-    trans = torch.cumprod(torch.cat([torch.ones(R, 1, dtype=dtype), 1.0 - alpha], dim=-1), dim=-1)[:, :-1]
+    trans = torch.cumprod(torch.cat([torch.ones(R, 1, dtype=dtype, device=alpha.device), 1.0 - alpha], dim=-1), dim=-1)[:, :-1]
     w = alpha * trans
     colour = (torch.sigmoid(raw) * w[..., None]).sum(dim=1)
     acc = w.sum(dim=-1, keepdim=True)
