@@ -472,6 +472,63 @@ def e2e_leg(device, rank, world, steps, warmup, dist):
             "ms_per_step": 1e3 * elapsed / steps, "steps": steps, "api": "VolumetricModel.render_rays + backward, 4096-ray batches"}
 
 
+def fused_step_leg(device, peak):
+    """Row f2: the optimiser-step grid pass.  Fused kernel (consume packed grads + Adam + repack + zero) against the
+    unfused sequence the reference-style loop runs (zero-fill, unpack, torch.optim.Adam.step, repack), CUDA events."""
+    from thre3d_atom.thre3d_reprs.voxels import VoxelGrid, VoxelSize
+    from voxe_b200.optim import FusedVoxelAdam
+    from voxe_b200.render_function import pack_volume
+
+    def timed(fn, n=20, warm=3):
+        for _ in range(warm):
+            fn()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(device)
+        a.record()
+        for _ in range(n):
+            fn()
+        b.record()
+        torch.cuda.synchronize(device)
+        return 1e3 * a.elapsed_time(b) / n  # us
+
+    dens, feat = make_grid_tensors(device)
+    grid = VoxelGrid(dens, feat, VoxelSize(*(w / d for w, d in zip(WL["world"], WL["dims"]))), density_preactivation=torch.nn.Identity(),
+                     density_postactivation=torch.nn.ReLU(), expected_density_scale=WL["density_scale"], tunable=True)
+    spec = grid.fused_spec()
+    packed = grid.packed_cache().get(spec, grid.densities, grid.features)
+    opt = FusedVoxelAdam(grid, lr=0.03)
+    acc = grid.render_gradient_accumulator
+    buf = acc.get(packed)
+    buf.normal_()
+
+    def fused():
+        acc.dirty = True  # pretend a backward pass just scattered into the volume
+        opt.step()
+
+    fused_us = timed(fused)
+    channels = packed.numel()
+    fused_bytes = 36.0 * dens.numel() * (feat.shape[-1] + 1)  # r: g,p,m,v  w: p,m,v,packed,zeroed g  (4 B each)
+
+    ref_d, ref_f = torch.nn.Parameter(dens.clone()), torch.nn.Parameter(feat.clone())
+    ref = torch.optim.Adam([{"params": [ref_d, ref_f], "lr": 0.03}], betas=(0.9, 0.999))
+    pg = torch.randn_like(packed)
+    ref_d.grad, ref_f.grad = torch.zeros_like(ref_d), torch.zeros_like(ref_f)
+    lib, gd = grid_lib = (__import__("voxe_b200._native", fromlist=["x"]).load_library(), spec.to_native())
+    stream = torch.cuda.current_stream(device).cuda_stream
+
+    def unfused():
+        lib.voxe_unpack_grad(gd, pg.data_ptr(), ref_d.grad.data_ptr(), ref_f.grad.data_ptr(), 1, stream)  # .grad += render grads
+        pg.zero_()
+        ref.step()
+        pack_volume(spec, ref_d, ref_f, out=packed)
+        ref_d.grad.zero_(), ref_f.grad.zero_()
+
+    unfused_us = timed(unfused)
+    return {"kernel": "adam_step_kernel (voxe_adam_step)", "us": round(fused_us, 1), "bytes": int(fused_bytes),
+            "achieved": round(fused_bytes / (fused_us * 1e-6) / 1e9, 1), "unit": "GB/s", "frac": round(fused_bytes / (fused_us * 1e-6) / 1e9 / peak, 4),
+            "unfused_us": round(unfused_us, 1), "unfused": "unpack(+=) + zero-fill + torch.optim.Adam.step + repack + grad zero", "packed_floats": channels}
+
+
 def run_ours(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -582,6 +639,10 @@ def run_ours(args):
         r = cpu_leg(steps=6, warmup=1, budget_s=25.0)
         cpu = {"value": r["rays_per_s"], "unit": "rays/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]}
 
+    fused_step = None
+    if rank == 0 and world == 1 and args.workload == "cfg2":
+        fused_step = fused_step_leg(device, peak)
+
     if rank == 0:
         line = {
             "metric": "rays/s fwd+bwd, 160^3 SH-0 grid, 400x400 render", "value": rays_per_s, "unit": "rays/s", "n_gpus": world,
@@ -595,6 +656,8 @@ def run_ours(args):
         }
         if cpu:
             line["cpu_baseline"] = cpu
+        if fused_step:
+            line["fused_step"] = fused_step
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define VOXE_ABI_VERSION 3
+#define VOXE_ABI_VERSION 4
 
 #if defined(__GNUC__)
 #define VOXE_API __attribute__((visibility("default")))
@@ -145,6 +145,27 @@ VOXE_API int voxe_render_bwd(const VoxeGridDesc* grid, const VoxeRenderDesc* ren
                     const float* rays_o, const float* rays_d, const float* jitter, const float* noise,
                     const float* saved, const float* g_colour, const float* g_depth, const float* g_acc,
                     const float* g_disp, float* packed_grad, int64_t num_rays, voxe_stream_t stream);
+
+/* One Adam step on the two grids, fused with everything else the optimiser step does to them
+ * (replaces `optimizer.zero_grad(); ...; optimizer.step()` of thre3d_atom/modules/trainers.py:247-255,348-351 and
+ * thre3d_atom/modules/sds_trainer.py:198-203,332-334 for torch.optim.Adam(betas, eps), no weight decay / amsgrad):
+ *   gradient = packed_grad (what voxe_render_bwd accumulated; may be NULL) + dense_d_* (gradients of torch-side losses
+ *   such as the TV / density-correlation terms of sds_trainer.py:290-326; may be NULL);
+ *   densities / features and their moments m_*, v_* (reference layout, shaped like the parameters) are updated in place,
+ *   `packed` (may be NULL) is refreshed with the new values and `packed_grad` is zeroed -- all in one streaming pass.
+ * `step` is the 1-based step count AFTER this update (bias corrections 1 - beta^step). */
+typedef struct VoxeAdamDesc {
+  double lr;     /* doubles, like the Python scalars torch.optim.Adam derives 1 - beta and lr / (1 - beta1^step) from */
+  double beta1;
+  double beta2;
+  double eps;
+  int32_t step;
+} VoxeAdamDesc;
+
+VOXE_API int voxe_adam_step(const VoxeGridDesc* grid, const VoxeAdamDesc* adam, float* densities, float* features,
+                            float* packed, float* packed_grad, const float* dense_d_densities,
+                            const float* dense_d_features, float* m_densities, float* v_densities, float* m_features,
+                            float* v_features, voxe_stream_t stream);
 
 /* Launch-shape override for tuning runs: samples per thread (1..64), rays per CTA (power of two <= 32) and the
  * register budget of the kernel variant (64 or 128); 0 restores the built-in choice of that knob.  Does not change

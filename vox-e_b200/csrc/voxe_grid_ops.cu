@@ -4,6 +4,8 @@
 // VoxelGrid.forward touches the whole density grid on every call (voxels.py:303-305).  The render kernels instead
 // read ONE packed channel-last volume so that a trilinear corner is a 16-byte vector; these two kernels convert
 // between the layouts.  They are pure HBM streams: 2*(F+1)*4 bytes per voxel each.
+#include <cmath>
+
 #include "voxe_launch.h"
 
 namespace voxe {
@@ -77,6 +79,61 @@ __global__ void __launch_bounds__(256) unpack_grad_kernel(const float4* __restri
   }
 }
 
+// Fused per-step grid pass: consume the packed gradient volume (plus optional dense gradients from torch-side losses),
+// apply one Adam step to the reference-layout parameters and their moments, refresh the packed volume and zero the
+// packed gradients -- one launch instead of zero-fill + unpack + AccumulateGrad + ~10 optimiser kernels + repack.
+// Arithmetic follows torch.optim.Adam (single-tensor path, amsgrad=False, weight_decay=0, maximize=False):
+//   m <- m + (g - m) * (1 - beta1);  v <- v * beta2 + g * g * (1 - beta2)
+//   p <- p - (lr / bc1) * m / (sqrt(v) / sqrt(bc2) + eps)
+// One thread per packed float4 (4 channels of one voxel).  Pure HBM stream: 36 bytes per channel-slot.
+struct AdamScalars {
+  float one_minus_beta1, beta2, one_minus_beta2, step_size, sqrt_bc2, eps;
+};
+
+__global__ void __launch_bounds__(256) adam_step_kernel(float4* __restrict__ packed, float4* __restrict__ packed_grad,
+                                                        float* __restrict__ dens, float* __restrict__ feat,
+                                                        const float* __restrict__ dense_gd, const float* __restrict__ dense_gf,
+                                                        float* __restrict__ m_d, float* __restrict__ v_d,
+                                                        float* __restrict__ m_f, float* __restrict__ v_f, int64_t n_vec,
+                                                        int F, int CV, AdamScalars a, BrickDims d) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_vec) return;
+  const int64_t slot = t / CV;
+  const int c0 = (int)(t - slot * CV) * 4;
+  int64_t v;
+  if (!slot_to_voxel(d, slot, v)) return;  // padding slots of partial bricks stay zero
+  float g[4] = {0.f, 0.f, 0.f, 0.f};
+  if (packed_grad) {
+    const float4 pg = packed_grad[t];
+    g[0] = pg.x; g[1] = pg.y; g[2] = pg.z; g[3] = pg.w;
+    packed_grad[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  float out[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int c = c0 + k;
+    float *pp, *pm, *pv;
+    const float* pg2;
+    if (c < F) {
+      const int64_t i = v * F + c;
+      pp = feat + i; pm = m_f + i; pv = v_f + i; pg2 = dense_gf ? dense_gf + i : nullptr;
+    } else if (c == F) {
+      pp = dens + v; pm = m_d + v; pv = v_d + v; pg2 = dense_gd ? dense_gd + v : nullptr;
+    } else {
+      continue;
+    }
+    const float grad = g[k] + (pg2 ? __ldg(pg2) : 0.f);
+    float m = *pm, vv = *pv, p = *pp;
+    m = m + (grad - m) * a.one_minus_beta1;
+    vv = vv * a.beta2 + grad * grad * a.one_minus_beta2;
+    const float denom = sqrtf(vv) / a.sqrt_bc2 + a.eps;
+    p = p - a.step_size * (m / denom);
+    *pm = m; *pv = vv; *pp = p;
+    out[k] = p;
+  }
+  if (packed) packed[t] = make_float4(out[0], out[1], out[2], out[3]);
+}
+
 BrickDims brick_dims(const int dims[3]) { return BrickDims{dims[0], dims[1], dims[2], (dims[1] + 1) / 2, (dims[2] + 1) / 2}; }
 
 }  // namespace
@@ -105,6 +162,30 @@ cudaError_t launch_unpack_grad(const float* packed_grad, float* d_densities, flo
   unpack_grad_kernel<<<(unsigned)blocks, threads, 0, stream>>>(reinterpret_cast<const float4*>(packed_grad),
                                                                d_densities, d_features, n_vec, n_features, CV,
                                                                accumulate ? 1 : 0, brick_dims(dims));
+  return cudaGetLastError();
+}
+
+cudaError_t launch_adam_step(float* packed, float* packed_grad, float* densities, float* features,
+                             const float* dense_gd, const float* dense_gf, float* m_d, float* v_d, float* m_f, float* v_f,
+                             const int dims[3], int n_features, int channels, double lr, double beta1, double beta2, double eps,
+                             int step, cudaStream_t stream) {
+  const int CV = channels / 4;
+  const int64_t n_vec = packed_voxel_slots(dims) * CV;
+  // bias corrections in double, like the Python scalars of torch.optim.Adam
+  const double bc1 = 1.0 - pow(beta1, (double)step);
+  const double bc2 = 1.0 - pow(beta2, (double)step);
+  AdamScalars a;
+  a.one_minus_beta1 = (float)(1.0 - beta1);
+  a.beta2 = (float)beta2;
+  a.one_minus_beta2 = (float)(1.0 - beta2);
+  a.step_size = (float)(lr / bc1);
+  a.sqrt_bc2 = (float)sqrt(bc2);
+  a.eps = (float)eps;
+  const int threads = 256;
+  const int64_t blocks = (n_vec + threads - 1) / threads;
+  adam_step_kernel<<<(unsigned)blocks, threads, 0, stream>>>(
+      reinterpret_cast<float4*>(packed), reinterpret_cast<float4*>(packed_grad), densities, features, dense_gd, dense_gf,
+      m_d, v_d, m_f, v_f, n_vec, n_features, CV, a, brick_dims(dims));
   return cudaGetLastError();
 }
 

@@ -116,7 +116,8 @@ def render_sh_voxel_grid(
     features, densities = voxel_grid.features, voxel_grid.densities
     spec = _render_spec(render_config, features.shape[-1], attn=False, per_call_sampling_flags=True)
     colour, depth, acc, disparity = fused_render(
-        voxel_grid.fused_spec(), spec, densities, features, rays.origins, rays.directions, cache=voxel_grid.packed_cache()
+        voxel_grid.fused_spec(), spec, densities, features, rays.origins, rays.directions, cache=voxel_grid.packed_cache(),
+        grad_sink=voxel_grid.render_gradient_accumulator,
     )
     return RenderOut(colour=colour, depth=depth, extra={EXTRA_DISPARITY: disparity, EXTRA_ACCUMULATED_WEIGHTS: acc})
 

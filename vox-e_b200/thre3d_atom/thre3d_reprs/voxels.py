@@ -20,7 +20,7 @@ from torch.nn.functional import interpolate
 
 from thre3d_atom.thre3d_reprs.constants import CONFIG_DICT, STATE_DICT, THRE3D_REPR, u_ATTN, u_DENSITIES, u_FEATURES
 from voxe_b200 import _native as nat
-from voxe_b200.render_function import FusedGridSpec, PackedVolumeCache
+from voxe_b200.render_function import FusedGridSpec, PackedGradAccumulator, PackedVolumeCache
 
 
 class VoxelSize(NamedTuple):
@@ -124,6 +124,7 @@ class VoxelGrid(Module):
         # packed-volume caches for the render kernels (colour render / attention render)
         self._packed = PackedVolumeCache()
         self._packed_attn = PackedVolumeCache()
+        self._grad_accumulator: Optional[PackedGradAccumulator] = None  # deferred render gradients (opt-in)
 
     # ------------------------------------------------------------------------------------------------------
     # parameters
@@ -257,6 +258,27 @@ class VoxelGrid(Module):
         """Call after writing grid values through ``.data`` (which autograd's version counter does not see)."""
         self._packed.invalidate()
         self._packed_attn.invalidate()
+
+    def accumulate_render_gradients(self, enabled: bool = True) -> None:
+        """Opt into deferred gradients: render backward passes scatter into one persistent packed volume instead of
+        producing dense ``.grad`` tensors per call; ``materialize_render_gradients()`` (called automatically before any
+        ``torch.optim`` step once ``voxe_b200.optim`` is imported, or replaced by ``FusedVoxelAdam``) makes them visible."""
+        if enabled and self._grad_accumulator is None:
+            from voxe_b200 import optim  # registers the optimiser pre-step hook
+
+            self._grad_accumulator = PackedGradAccumulator()
+            optim.track_grid(self)
+        elif not enabled and self._grad_accumulator is not None:
+            self.materialize_render_gradients()
+            self._grad_accumulator = None
+
+    @property
+    def render_gradient_accumulator(self) -> Optional[PackedGradAccumulator]:
+        return self._grad_accumulator
+
+    def materialize_render_gradients(self) -> None:
+        if self._grad_accumulator is not None:
+            self._grad_accumulator.materialize(self.fused_spec(), self._densities, self._features)
 
     def forward(self, points: Tensor, viewdirs: Optional[Tensor] = None) -> Tensor:
         """Point queries are not a separate operation here: sampling, interpolation and compositing are one kernel,

@@ -129,6 +129,14 @@ class PackedVolumeCache:
     def invalidate(self) -> None:
         self._key = None
 
+    def mark_fresh(self, spec: FusedGridSpec, densities: Tensor, features: Tensor) -> None:
+        """The packed volume was brought up to date out of band (the fused optimiser step rewrites it)."""
+        if self._packed is not None:
+            self._key = (densities.data_ptr(), densities._version, features.data_ptr(), features._version, densities.device, spec)
+
+    def peek(self) -> Optional[Tensor]:
+        return self._packed
+
     def get(self, spec: FusedGridSpec, densities: Tensor, features: Tensor) -> Tensor:
         key = (densities.data_ptr(), densities._version, features.data_ptr(), features._version, densities.device, spec)
         if key != self._key or self._packed is None:
@@ -137,11 +145,64 @@ class PackedVolumeCache:
         return self._packed
 
 
+class PackedGradAccumulator:
+    """Persistent packed gradient volume of one grid ("deferred gradients").
+
+    With an accumulator attached, the backward kernel scatter-adds straight into this buffer and autograd receives no
+    gradient for ``_densities`` / ``_features``: the per-call zero-fill, unpack and ``.grad +=`` passes (3 x 65 MB at
+    160^3) disappear from every render call.  The gradients become visible to torch when :meth:`materialize` splits the
+    buffer into ``.grad`` (done automatically right before any ``torch.optim`` step, see ``voxe_b200.optim``), or are
+    consumed in place by ``FusedVoxelAdam``.  Opt-in, because code that reads ``.grad`` between ``backward()`` and the
+    optimiser step would not see the render's contribution."""
+
+    def __init__(self) -> None:
+        self.buffer: Optional[Tensor] = None
+        self.dirty = False
+
+    def get(self, like: Tensor) -> Tensor:
+        if self.buffer is None or self.buffer.numel() != like.numel() or self.buffer.device != like.device:
+            self.buffer = torch.zeros_like(like)
+            self.dirty = False
+        return self.buffer
+
+    def zero(self) -> None:
+        if self.buffer is not None and self.dirty:
+            self.buffer.zero_()
+        self.dirty = False
+
+    def materialize(self, spec: "FusedGridSpec", densities: Tensor, features: Tensor) -> None:
+        """``densities.grad`` / ``features.grad`` += what the render backward passes accumulated; then clear."""
+        if self.buffer is None or not self.dirty:
+            return
+        lib = nat.load_library()
+        dev = self.buffer.device
+        outs = []
+        for p in (densities, features):
+            if not p.requires_grad:
+                outs.append((None, 0))
+            elif p.grad is None:
+                p.grad = torch.empty_like(p, memory_format=torch.contiguous_format)
+                outs.append((p.grad, 0))
+            else:
+                outs.append((p.grad, 1))
+        gd = spec.to_native()
+        with torch.cuda.device(dev):
+            s = _stream_ptr(dev)
+            for (g, acc), which in zip(outs, (0, 1)):
+                if g is None:
+                    continue
+                args = (g.data_ptr(), None) if which == 0 else (None, g.data_ptr())
+                nat.check(lib.voxe_unpack_grad(gd, self.buffer.data_ptr(), args[0], args[1], acc, s), "voxe_unpack_grad")
+        self.buffer.zero_()
+        self.dirty = False
+
+
 class _FusedRender(torch.autograd.Function):
     """colour, depth, acc, disparity = render(densities, features | rays, jitter, noise)."""
 
     @staticmethod
-    def forward(ctx, densities, features, packed, rays_o, rays_d, jitter, noise, gspec: FusedGridSpec, rspec: FusedRenderSpec):
+    def forward(ctx, densities, features, packed, rays_o, rays_d, jitter, noise, gspec: FusedGridSpec, rspec: FusedRenderSpec,
+                sink: Optional[PackedGradAccumulator] = None):
         dev = _require_cuda(packed, rays_o, rays_d)
         lib = nat.load_library()
         R = rays_o.shape[0]
@@ -161,7 +222,7 @@ class _FusedRender(torch.autograd.Function):
                 "voxe_render_fwd",
             )
         ctx.set_materialize_grads(False)
-        ctx.gspec, ctx.rspec = gspec, rspec
+        ctx.gspec, ctx.rspec, ctx.sink = gspec, rspec, sink
         ctx.save_for_backward(densities, features, packed, rays_o, rays_d, jitter, noise, saved)
         return colour, depth, acc, disp
 
@@ -169,24 +230,36 @@ class _FusedRender(torch.autograd.Function):
     def backward(ctx, g_colour, g_depth, g_acc, g_disp):
         densities, features, packed, rays_o, rays_d, jitter, noise, saved = ctx.saved_tensors
         need_d, need_f = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
-        none9 = (None,) * 9
+        none10 = (None,) * 10
         if not (need_d or need_f):
-            return none9
+            return none10
         gspec, rspec = ctx.gspec, ctx.rspec
         dev = packed.device
         lib = nat.load_library()
         R = rays_o.shape[0]
         if all(g is None for g in (g_colour, g_depth, g_acc, g_disp)):
             zeros = lambda t, need: torch.zeros_like(t, memory_format=torch.contiguous_format) if need else None  # noqa: E731
-            return (zeros(densities, need_d), zeros(features, need_f)) + (None,) * 7
-        # fully overwritten by voxe_unpack_grad(accumulate=0): no zero-fill needed
-        d_dens = torch.empty_like(densities, memory_format=torch.contiguous_format) if need_d else None
-        d_feat = torch.empty_like(features, memory_format=torch.contiguous_format) if need_f else None
+            return (zeros(densities, need_d), zeros(features, need_f)) + (None,) * 8
         if g_colour is None:
             g_colour = torch.zeros((R, rspec.n_colour), dtype=torch.float32, device=dev)
         gs = [None if g is None else g.contiguous().float() for g in (g_colour, g_depth, g_acc, g_disp)]
-        packed_grad = torch.zeros_like(packed)
         gd, rd = gspec.to_native(), rspec.to_native()
+        sink = ctx.sink
+        if sink is not None:  # deferred gradients: scatter into the grid's persistent volume, hand autograd nothing
+            target = sink.get(packed)
+            with torch.cuda.device(dev):
+                nat.check(
+                    lib.voxe_render_bwd(gd, rd, packed.data_ptr(), rays_o.data_ptr(), rays_d.data_ptr(), _ptr(jitter), _ptr(noise),
+                                        saved.data_ptr(), _ptr(gs[0]), _ptr(gs[1]), _ptr(gs[2]), _ptr(gs[3]), target.data_ptr(), R,
+                                        _stream_ptr(dev)),
+                    "voxe_render_bwd",
+                )
+            sink.dirty = True
+            return none10
+        # fully overwritten by voxe_unpack_grad(accumulate=0): no zero-fill needed
+        d_dens = torch.empty_like(densities, memory_format=torch.contiguous_format) if need_d else None
+        d_feat = torch.empty_like(features, memory_format=torch.contiguous_format) if need_f else None
+        packed_grad = torch.zeros_like(packed)
         with torch.cuda.device(dev):
             s = _stream_ptr(dev)
             nat.check(
@@ -195,7 +268,7 @@ class _FusedRender(torch.autograd.Function):
                 "voxe_render_bwd",
             )
             nat.check(lib.voxe_unpack_grad(gd, packed_grad.data_ptr(), _ptr(d_dens), _ptr(d_feat), 0, s), "voxe_unpack_grad")
-        return (d_dens, d_feat) + (None,) * 7
+        return (d_dens, d_feat) + (None,) * 8
 
 
 def _prep_rays(rays_o: Tensor, rays_d: Tensor) -> Tuple[Tensor, Tensor]:
@@ -215,6 +288,7 @@ def fused_render(
     jitter: Optional[Tensor] = None,
     noise: Optional[Tensor] = None,
     generator: Optional[torch.Generator] = None,
+    grad_sink: Optional[PackedGradAccumulator] = None,
 ) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
     """Render flat rays through the fused kernels.  Returns (colour [R,C], depth [R,1], acc [R,1], disparity [R,1]).
 
@@ -242,7 +316,7 @@ def fused_render(
     if R == 0:
         z = torch.zeros((0, 1), dtype=torch.float32, device=dev)
         return torch.zeros((0, rspec.n_colour), dtype=torch.float32, device=dev), z, z.clone(), z.clone()
-    return _FusedRender.apply(densities, features, packed, rays_o, rays_d, jitter, noise, gspec, rspec)
+    return _FusedRender.apply(densities, features, packed, rays_o, rays_d, jitter, noise, gspec, rspec, grad_sink)
 
 
 def fused_render_attn(*args, **kwargs):
