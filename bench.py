@@ -479,17 +479,24 @@ def fused_step_leg(device, peak):
     from voxe_b200.optim import FusedVoxelAdam
     from voxe_b200.render_function import pack_volume
 
-    def timed(fn, n=20, warm=3):
+    def timed(fn, prepare, n=20, warm=3):
+        """Mean device time of fn(): [prepare(); fn()] x n back to back minus [prepare()] x n, CUDA events on the stream.
+        prepare() restores what a backward pass leaves behind (a non-trivial gradient volume)."""
+        def loop(with_fn):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize(device)
+            a.record()
+            for _ in range(n):
+                prepare()
+                if with_fn:
+                    fn()
+            b.record()
+            torch.cuda.synchronize(device)
+            return a.elapsed_time(b)
         for _ in range(warm):
+            prepare()
             fn()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        torch.cuda.synchronize(device)
-        a.record()
-        for _ in range(n):
-            fn()
-        b.record()
-        torch.cuda.synchronize(device)
-        return 1e3 * a.elapsed_time(b) / n  # us
+        return 1e3 * (loop(True) - loop(False)) / n  # us
 
     dens, feat = make_grid_tensors(device)
     grid = VoxelGrid(dens, feat, VoxelSize(*(w / d for w, d in zip(WL["world"], WL["dims"]))), density_preactivation=torch.nn.Identity(),
@@ -499,19 +506,19 @@ def fused_step_leg(device, peak):
     opt = FusedVoxelAdam(grid, lr=0.03)
     acc = grid.render_gradient_accumulator
     buf = acc.get(packed)
-    buf.normal_()
+    noise = torch.randn_like(packed)
 
-    def fused():
-        acc.dirty = True  # pretend a backward pass just scattered into the volume
-        opt.step()
+    def scattered():  # what a backward pass leaves behind: a non-trivial gradient volume
+        buf.copy_(noise)
+        acc.dirty = True
 
-    fused_us = timed(fused)
+    fused_us = timed(opt.step, scattered)
     channels = packed.numel()
     fused_bytes = 36.0 * dens.numel() * (feat.shape[-1] + 1)  # r: g,p,m,v  w: p,m,v,packed,zeroed g  (4 B each)
 
     ref_d, ref_f = torch.nn.Parameter(dens.clone()), torch.nn.Parameter(feat.clone())
     ref = torch.optim.Adam([{"params": [ref_d, ref_f], "lr": 0.03}], betas=(0.9, 0.999))
-    pg = torch.randn_like(packed)
+    pg = torch.empty_like(packed)
     ref_d.grad, ref_f.grad = torch.zeros_like(ref_d), torch.zeros_like(ref_f)
     lib, gd = grid_lib = (__import__("voxe_b200._native", fromlist=["x"]).load_library(), spec.to_native())
     stream = torch.cuda.current_stream(device).cuda_stream
@@ -523,7 +530,7 @@ def fused_step_leg(device, peak):
         pack_volume(spec, ref_d, ref_f, out=packed)
         ref_d.grad.zero_(), ref_f.grad.zero_()
 
-    unfused_us = timed(unfused)
+    unfused_us = timed(unfused, lambda: pg.copy_(noise))
     return {"kernel": "adam_step_kernel (voxe_adam_step)", "us": round(fused_us, 1), "bytes": int(fused_bytes),
             "achieved": round(fused_bytes / (fused_us * 1e-6) / 1e9, 1), "unit": "GB/s", "frac": round(fused_bytes / (fused_us * 1e-6) / 1e9 / peak, 4),
             "unfused_us": round(unfused_us, 1), "unfused": "unpack(+=) + zero-fill + torch.optim.Adam.step + repack + grad zero", "packed_floats": channels}

@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define VOXE_ABI_VERSION 4
+#define VOXE_ABI_VERSION 5
 
 #if defined(__GNUC__)
 #define VOXE_API __attribute__((visibility("default")))
@@ -149,10 +149,12 @@ VOXE_API int voxe_render_bwd(const VoxeGridDesc* grid, const VoxeRenderDesc* ren
 /* One Adam step on the two grids, fused with everything else the optimiser step does to them
  * (replaces `optimizer.zero_grad(); ...; optimizer.step()` of thre3d_atom/modules/trainers.py:247-255,348-351 and
  * thre3d_atom/modules/sds_trainer.py:198-203,332-334 for torch.optim.Adam(betas, eps), no weight decay / amsgrad):
- *   gradient = packed_grad (what voxe_render_bwd accumulated; may be NULL) + dense_d_* (gradients of torch-side losses
- *   such as the TV / density-correlation terms of sds_trainer.py:290-326; may be NULL);
- *   densities / features and their moments m_*, v_* (reference layout, shaped like the parameters) are updated in place,
- *   `packed` (may be NULL) is refreshed with the new values and `packed_grad` is zeroed -- all in one streaming pass.
+ *   gradient = packed_grad (what voxe_render_bwd accumulated; may be NULL) + dense_d_* (reference-layout gradients of
+ *   torch-side losses such as the TV / density-correlation terms of sds_trainer.py:290-326; may be NULL);
+ *   `packed` must mirror the parameters (voxe_pack_grid) and is updated in place, the new values are also written to
+ *   densities / features (reference layout), the moments packed_m / packed_v live in the packed layout
+ *   (voxe_packed_floats() floats each; convert with voxe_pack_grid / voxe_unpack_grad for checkpoints), and
+ *   `packed_grad` is zeroed -- one streaming pass, ten 16-byte-coalesced streams.
  * `step` is the 1-based step count AFTER this update (bias corrections 1 - beta^step). */
 typedef struct VoxeAdamDesc {
   double lr;     /* doubles, like the Python scalars torch.optim.Adam derives 1 - beta and lr / (1 - beta1^step) from */
@@ -164,8 +166,7 @@ typedef struct VoxeAdamDesc {
 
 VOXE_API int voxe_adam_step(const VoxeGridDesc* grid, const VoxeAdamDesc* adam, float* densities, float* features,
                             float* packed, float* packed_grad, const float* dense_d_densities,
-                            const float* dense_d_features, float* m_densities, float* v_densities, float* m_features,
-                            float* v_features, voxe_stream_t stream);
+                            const float* dense_d_features, float* packed_m, float* packed_v, voxe_stream_t stream);
 
 /* Launch-shape override for tuning runs: samples per thread (1..64), rays per CTA (power of two <= 32) and the
  * register budget of the kernel variant (64 or 128); 0 restores the built-in choice of that knob.  Does not change

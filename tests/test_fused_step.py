@@ -40,12 +40,26 @@ def test_adam_kernel_matches_torch_adam(dims, n_feat):
         grid.densities.grad, grid.features.grad = gd.clone(), gf.clone()
         ref.step()
         ours.step()
-        for a, b in ((grid.densities, ref_d), (grid.features, ref_f)):
+        moments = ours.moments()
+        for (a, b), (m, v) in zip(((grid.densities, ref_d), (grid.features, ref_f)), moments):
             assert torch.allclose(a, b, rtol=2e-6, atol=2e-7), float((a - b).abs().max())
-            assert torch.allclose(ours.state[a]["exp_avg"], ref.state[b]["exp_avg"], rtol=2e-6, atol=1e-9)
-            assert torch.allclose(ours.state[a]["exp_avg_sq"], ref.state[b]["exp_avg_sq"], rtol=2e-6, atol=1e-12)
-    assert set(ours.state_dict()["state"][0]) == {"step", "exp_avg", "exp_avg_sq"}
-    assert float(ours.state[grid.densities]["step"]) == 4.0
+            assert torch.allclose(m, ref.state[b]["exp_avg"], rtol=2e-6, atol=1e-9)
+            assert torch.allclose(v, ref.state[b]["exp_avg_sq"], rtol=2e-6, atol=1e-12)
+    # checkpoints keep torch.optim.Adam's layout and round-trip, also into a stock torch.optim.Adam
+    sd = ours.state_dict()
+    assert set(sd["state"][0]) == {"step", "exp_avg", "exp_avg_sq"} and float(sd["state"][0]["step"]) == 4.0
+    assert sd["state"][1]["exp_avg"].shape == ref_f.shape
+    stock = torch.optim.Adam([{"params": [ref_d, ref_f], "lr": 0.03}], betas=(0.9, 0.999))
+    stock.load_state_dict(sd)
+    again = FusedVoxelAdam(grid, lr=0.01)
+    again.load_state_dict(sd)
+    assert again.param_groups[0]["lr"] == 0.03
+    gd, gf = torch.randn_like(ref_d), torch.randn_like(ref_f)
+    ref_d.grad, ref_f.grad = gd.clone(), gf.clone()
+    grid.densities.grad, grid.features.grad = gd.clone(), gf.clone()
+    stock.step()
+    again.step()
+    assert torch.allclose(grid.features, ref_f, rtol=2e-6, atol=2e-7) and torch.allclose(grid.densities, ref_d, rtol=2e-6, atol=2e-7)
 
 
 def _render_loss(grid, meta, a, sel=slice(None)):

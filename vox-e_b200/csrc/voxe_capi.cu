@@ -171,19 +171,18 @@ int voxe_unpack_grad(const VoxeGridDesc* grid, const float* packed_grad, float* 
 }
 
 int voxe_adam_step(const VoxeGridDesc* grid, const VoxeAdamDesc* adam, float* densities, float* features, float* packed,
-                   float* packed_grad, const float* dense_d_densities, const float* dense_d_features, float* m_densities,
-                   float* v_densities, float* m_features, float* v_features, voxe_stream_t stream) {
+                   float* packed_grad, const float* dense_d_densities, const float* dense_d_features, float* packed_m,
+                   float* packed_v, voxe_stream_t stream) {
   if (int rc = check_grid(grid)) return rc;
   if (!adam) return fail(VOXE_ERR_INVALID_ARGUMENT, "voxe_adam_step: NULL descriptor");
-  if (!densities || !features || !m_densities || !v_densities || !m_features || !v_features)
-    return fail(VOXE_ERR_INVALID_ARGUMENT, "voxe_adam_step: NULL parameter / moment buffer");
+  if (!densities || !features || !packed || !packed_m || !packed_v)
+    return fail(VOXE_ERR_INVALID_ARGUMENT, "voxe_adam_step: NULL parameter / packed volume / moment buffer");
   if (adam->step < 1) return fail(VOXE_ERR_INVALID_ARGUMENT, "voxe_adam_step: step must be >= 1 (got %d)", adam->step);
   if (!(adam->beta1 >= 0.0 && adam->beta1 < 1.0 && adam->beta2 >= 0.0 && adam->beta2 < 1.0 && adam->eps >= 0.0))
     return fail(VOXE_ERR_INVALID_ARGUMENT, "voxe_adam_step: betas must be in [0,1) and eps >= 0");
-  cudaError_t e = voxe::launch_adam_step(packed, packed_grad, densities, features, dense_d_densities, dense_d_features,
-                                         m_densities, v_densities, m_features, v_features, grid->dims, grid->n_features,
-                                         grid->channels, adam->lr, adam->beta1, adam->beta2, adam->eps, adam->step,
-                                         (cudaStream_t)stream);
+  cudaError_t e = voxe::launch_adam_step(packed, packed_grad, packed_m, packed_v, densities, features, dense_d_densities,
+                                         dense_d_features, grid->dims, grid->n_features, grid->channels, adam->lr,
+                                         adam->beta1, adam->beta2, adam->eps, adam->step, (cudaStream_t)stream);
   if (e != cudaSuccess) return cuda_fail(e, "voxe_adam_step launch");
   g_launches.fetch_add(1);
   return VOXE_OK;

@@ -19,9 +19,8 @@ cudaError_t launch_pack_grid(const float* densities, const float* features, floa
 cudaError_t launch_unpack_grad(const float* packed_grad, float* d_densities, float* d_features, const int dims[3],
                                int n_features, int channels, bool accumulate, cudaStream_t stream);
 
-cudaError_t launch_adam_step(float* packed, float* packed_grad, float* densities, float* features,
-                             const float* dense_gd, const float* dense_gf, float* m_d, float* v_d, float* m_f, float* v_f,
-                             const int dims[3], int n_features, int channels, double lr, double beta1, double beta2, double eps,
-                             int step, cudaStream_t stream);
+cudaError_t launch_adam_step(float* packed, float* packed_grad, float* packed_m, float* packed_v, float* densities,
+                             float* features, const float* dense_gd, const float* dense_gf, const int dims[3], int n_features,
+                             int channels, double lr, double beta1, double beta2, double eps, int step, cudaStream_t stream);
 
 }  // namespace voxe

@@ -61,7 +61,11 @@ class FusedVoxelAdam(Optimizer):
         params = [voxel_grid.densities, voxel_grid.features]
         if not all(isinstance(p, torch.nn.Parameter) for p in params):
             raise ValueError("FusedVoxelAdam needs a tunable VoxelGrid (densities / features must be Parameters)")
-        super().__init__([{"params": params}], dict(lr=lr, betas=betas, eps=eps))
+        # the extra keys are torch.optim.Adam's remaining hyper-parameters at the only values this kernel implements, so
+        # that state dicts move freely between the two optimisers
+        defaults = dict(lr=lr, betas=betas, eps=eps, weight_decay=0, amsgrad=False, maximize=False, foreach=None, capturable=False,
+                        differentiable=False, fused=None, decoupled_weight_decay=False)
+        super().__init__([{"params": params}], defaults)
         self._grid = weakref.ref(voxel_grid)
         voxel_grid.accumulate_render_gradients(True)
 
@@ -86,22 +90,19 @@ class FusedVoxelAdam(Optimizer):
             raise RuntimeError("the grid's parameters were replaced after the optimiser was built; build a new optimiser")
         if dens.device.type != "cuda":
             raise RuntimeError("FusedVoxelAdam runs on CUDA only (no CPU fallback)")
-        moments = []
-        for p in (dens, feat):
-            st = self.state[p]
-            if len(st) == 0:
-                st["step"] = torch.tensor(0.0, dtype=torch.float32)
-                st["exp_avg"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
-                st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
-            st["step"] += 1
-            moments.append(st)
-        step = int(moments[0]["step"].item())
         spec = grid.fused_spec()
         gd = spec.to_native()
+        cache = grid.packed_cache()
+        packed = cache.get(spec, dens, feat)  # no-op when the volume already mirrors the parameters
+        st = self.state[dens]  # one shared record: the moments live in the packed layout, next to the packed volume
+        if len(st) == 0:
+            st["step"] = torch.tensor(0.0, dtype=torch.float32)
+            st["packed_exp_avg"] = torch.zeros_like(packed)
+            st["packed_exp_avg_sq"] = torch.zeros_like(packed)
+        st["step"] += 1
+        step = int(st["step"].item())
         acc = grid.render_gradient_accumulator
         packed_grad = acc.buffer if (acc is not None and acc.dirty) else None
-        cache = grid.packed_cache()
-        packed = cache.peek()
         adam = nat.VoxeAdamDesc(lr=float(group["lr"]), beta1=float(group["betas"][0]), beta2=float(group["betas"][1]),
                                 eps=float(group["eps"]), step=step)
         dense = [None if p.grad is None else p.grad.contiguous() for p in (dens, feat)]
@@ -109,9 +110,9 @@ class FusedVoxelAdam(Optimizer):
         lib = nat.load_library()
         with torch.cuda.device(dens.device):
             nat.check(
-                lib.voxe_adam_step(gd, adam, dens.data_ptr(), feat.data_ptr(), ptr(packed), ptr(packed_grad), ptr(dense[0]), ptr(dense[1]),
-                                   moments[0]["exp_avg"].data_ptr(), moments[0]["exp_avg_sq"].data_ptr(),
-                                   moments[1]["exp_avg"].data_ptr(), moments[1]["exp_avg_sq"].data_ptr(), _stream_ptr(dens.device)),
+                lib.voxe_adam_step(gd, adam, dens.data_ptr(), feat.data_ptr(), packed.data_ptr(), ptr(packed_grad), ptr(dense[0]),
+                                   ptr(dense[1]), st["packed_exp_avg"].data_ptr(), st["packed_exp_avg_sq"].data_ptr(),
+                                   _stream_ptr(dens.device)),
                 "voxe_adam_step",
             )
         if acc is not None:
@@ -120,3 +121,47 @@ class FusedVoxelAdam(Optimizer):
         torch.autograd.graph.increment_version([dens, feat])
         cache.mark_fresh(spec, dens, feat)
         return loss
+
+    # -- checkpoints keep torch.optim.Adam's per-parameter layout (exp_avg / exp_avg_sq shaped like the parameters) -------
+    def moments(self):
+        """(exp_avg, exp_avg_sq) for densities and features in the reference layout: ((m_d, v_d), (m_f, v_f))."""
+        grid = self._grid()
+        dens, feat = self.param_groups[0]["params"]
+        st = self.state[dens]
+        if len(st) == 0:
+            z = lambda p: torch.zeros_like(p, memory_format=torch.contiguous_format)  # noqa: E731
+            return (z(dens), z(dens)), (z(feat), z(feat))
+        gd = grid.fused_spec().to_native()
+        lib = nat.load_library()
+        out = []
+        with torch.cuda.device(dens.device):
+            for key in ("packed_exp_avg", "packed_exp_avg_sq"):
+                d, f = torch.empty_like(dens, memory_format=torch.contiguous_format), torch.empty_like(feat, memory_format=torch.contiguous_format)
+                nat.check(lib.voxe_unpack_grad(gd, st[key].data_ptr(), d.data_ptr(), f.data_ptr(), 0, _stream_ptr(dens.device)), "voxe_unpack_grad")
+                out.append((d, f))
+        return (out[0][0], out[1][0]), (out[0][1], out[1][1])
+
+    def state_dict(self):
+        sd = super().state_dict()
+        dens, feat = self.param_groups[0]["params"]
+        if len(self.state[dens]):
+            (m_d, v_d), (m_f, v_f) = self.moments()
+            step = self.state[dens]["step"].clone()
+            sd["state"] = {0: {"step": step, "exp_avg": m_d, "exp_avg_sq": v_d}, 1: {"step": step.clone(), "exp_avg": m_f, "exp_avg_sq": v_f}}
+        return sd
+
+    def load_state_dict(self, state_dict):
+        from voxe_b200.render_function import pack_volume
+
+        state = state_dict.get("state", {})
+        super().load_state_dict({"state": {}, "param_groups": state_dict["param_groups"]})
+        if 0 in state and 1 in state:
+            grid = self._grid()
+            dens, feat = self.param_groups[0]["params"]
+            spec = grid.fused_spec()
+            to = lambda t, like: t.to(device=like.device, dtype=torch.float32).reshape(like.shape).contiguous()  # noqa: E731
+            self.state[dens] = {
+                "step": torch.as_tensor(float(state[0]["step"]), dtype=torch.float32),
+                "packed_exp_avg": pack_volume(spec, to(state[0]["exp_avg"], dens), to(state[1]["exp_avg"], feat)),
+                "packed_exp_avg_sq": pack_volume(spec, to(state[0]["exp_avg_sq"], dens), to(state[1]["exp_avg_sq"], feat)),
+            }
