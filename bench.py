@@ -11,7 +11,9 @@ A *step* is one frame = 160 000 rays = 40 x (jitter draw, forward kernel, backwa
 gradient volume) + one gradient zero-fill + one unpack of the packed gradient into d_densities / d_features (+ one NCCL
 all-reduce of the packed gradient when N > 1: each rank renders its own pose -- weak scaling).
 
-  value     device-resident throughput: the step above replayed as a CUDA graph over C-ABI launches, inputs in HBM
+  value     device-resident throughput: the step above replayed as a CUDA graph over C-ABI launches, inputs in HBM;
+            two batches are in flight on two streams (--lanes 2; the strictly serialised number is reported as
+            ``serialized``) and the jitter draws run ahead on a side stream
   e2e       the same frame through the public API (``VolumetricModel.render_rays`` + ``.backward()``) with rays and
             upstream gradients starting in pinned HOST memory and loss + colour read back every step
   roofline  the backward kernel (dominant) timed alone with CUDA events: algorithmic bytes / duration vs measured HBM peak
@@ -277,7 +279,7 @@ class DeviceBench:
 
     N_GRID_COPIES = 3  # rotating copies: 3 x 65.5 MB of grid + 65.5 MB of gradients >> 126 MB L2
 
-    def __init__(self, device, rank, world, count_s_in=True):
+    def __init__(self, device, rank, world, count_s_in=True, n_lanes=1):
         from voxe_b200 import _native as nat
         from voxe_b200.render_function import FusedGridSpec, FusedRenderSpec, pack_volume
 
@@ -310,10 +312,13 @@ class DeviceBench:
         self.depth = torch.empty(self.R, device=device)
         self.acc = torch.empty(self.R, device=device)
         self.disp = torch.empty(self.R, device=device)
-        self.jitter2 = [torch.rand(WL["batch"], WL["S"], device=device) for _ in range(2)]
-        self.jitter = self.jitter2[0]
+        self.n_lanes = max(1, n_lanes)
+        self.jitter_ring = [torch.rand(WL["batch"], WL["S"], device=device) for _ in range(self.n_lanes + 1)]
+        self.jitter = self.jitter_ring[0]
         self.side = torch.cuda.Stream(device)
+        self.lane_streams = [torch.cuda.Stream(device) for _ in range(self.n_lanes - 1)]
         self.saved = torch.empty(int(self.lib.voxe_saved_floats(self.rd, WL["batch"])), device=device)
+        self.saved_lane = [self.saved] + [torch.empty_like(self.saved) for _ in range(self.n_lanes - 1)]
         self.batches = [(s, min(s + WL["batch"], self.R)) for s in range(0, self.R, WL["batch"])]
         self.s_in = [count_inside_samples(o, d) for (o, d) in self.rays] if count_s_in else None
         self.kernels_per_step = 2 * len(self.batches) + 1
@@ -341,33 +346,53 @@ class DeviceBench:
 
     def frame_body(self, pose, copy, what="both", saved_set=None, refresh_jitter=True):
         """One frame.  ``saved_set``: per-batch workspaces (needed when fwd and bwd of a batch are not adjacent).
-        The jitter draw of batch k+1 (torch.rand, sample.py:63) runs on a side stream while batch k renders; two jitter
-        buffers alternate."""
+
+        Stream structure of the whole-frame step: the jitter draw of a later batch (torch.rand, sample.py:63) runs on a side
+        stream while earlier batches render, and ``self.n_lanes`` batches are in flight at once, each lane running
+        fwd(k) -> bwd(k) in order on its own stream with its own workspace.  Within a frame gradients are accumulated (one
+        optimiser step per frame), so batch k+1's forward does not depend on batch k's backward; the scatter-adds of
+        concurrent backward kernels into the shared gradient volume are atomic."""
         main = torch.cuda.current_stream(self.device)
-        draw = what == "both" and WL["perturb"] and refresh_jitter
-        if what == "both":
-            self.packed_grad.zero_()
+        if what != "both":
+            for k, (b0, b1) in enumerate(self.batches):
+                saved = self.saved if saved_set is None else saved_set[k]
+                if what == "fwd":
+                    self._fwd(pose, copy, b0, b1, saved)
+                else:
+                    self._bwd(pose, copy, b0, b1, saved)
+            return
+        draw = WL["perturb"] and refresh_jitter
+        self.packed_grad.zero_()
+        n = self.n_lanes
+        lanes = [main] + self.lane_streams[: n - 1]
+        for lane in lanes[1:]:
+            lane.wait_stream(main)
         if draw:
             self.side.wait_stream(main)
+        ring = len(self.jitter_ring)
         done = {}
         for k, (b0, b1) in enumerate(self.batches):
-            saved = self.saved if saved_set is None else saved_set[k]
+            lane = lanes[k % n]
+            ready = None
             if draw:
-                self.jitter = self.jitter2[k % 2]
+                jit = self.jitter_ring[k % ring]
                 with torch.cuda.stream(self.side):
-                    if k >= 2:
-                        self.side.wait_event(done[k - 2])
-                    self.jitter.uniform_()
+                    if k >= ring:
+                        self.side.wait_event(done[k - ring])
+                    jit.uniform_()
                     ready = torch.cuda.Event()
                     ready.record(self.side)
-                main.wait_event(ready)
-            if what in ("both", "fwd"):
+                self.jitter = jit
+            with torch.cuda.stream(lane):
+                if ready is not None:
+                    lane.wait_event(ready)
+                saved = self.saved_lane[k % n] if saved_set is None else saved_set[k]
                 self._fwd(pose, copy, b0, b1, saved)
-            if what in ("both", "bwd"):
                 self._bwd(pose, copy, b0, b1, saved)
-            if draw:
                 done[k] = torch.cuda.Event()
-                done[k].record(main)
+                done[k].record(lane)
+        for lane in lanes[1:]:
+            main.wait_stream(lane)
         if draw:
             main.wait_stream(self.side)
 
@@ -410,8 +435,9 @@ class DeviceBench:
         return start.elapsed_time(stop)  # ms
 
 
-def e2e_leg(device, rank, world, steps, warmup, dist):
-    """The frame through the public API, inputs starting in pinned host memory."""
+def e2e_leg(device, rank, world, steps, warmup, dist, deferred=False):
+    """The frame through the public API, inputs starting in pinned host memory.  ``deferred``: the opt-in gradient
+    accumulation mode (VoxelGrid.accumulate_render_gradients) with one materialisation per frame."""
     from thre3d_atom.modules.volumetric_model import VolumetricModel
     from thre3d_atom.rendering.volumetric.render_interface import Rays
     from thre3d_atom.thre3d_reprs.renderers import SHVoxGridRenderConfig, render_sh_voxel_grid
@@ -424,6 +450,8 @@ def e2e_leg(device, rank, world, steps, warmup, dist):
     vm = VolumetricModel(grid, render_sh_voxel_grid,
                          SHVoxGridRenderConfig(num_samples_per_ray=WL["S"], camera_bounds=CameraBounds(WL["near"], WL["far"]),
                                                white_bkgd=True, perturb_sampled_points=WL["perturb"]), device=device)
+    if deferred:
+        grid.accumulate_render_gradients()
     poses = make_poses()
     host = []
     g = torch.Generator().manual_seed(7)
@@ -449,7 +477,11 @@ def e2e_leg(device, rank, world, steps, warmup, dist):
             loss.backward()
             loss_total += loss.detach()
             colour_host[s : s + B].copy_(out.colour.detach(), non_blocking=True)
-        if world > 1:
+        if deferred:
+            if world > 1:
+                dist.all_reduce(grid.render_gradient_accumulator.buffer)  # ONE collective on the packed volume
+            grid.materialize_render_gradients()
+        elif world > 1:
             dist.all_reduce(grid.densities.grad)
             dist.all_reduce(grid.features.grad)
         return float(loss_total.item())  # D2H of the step's result; also orders the colour copy
@@ -551,7 +583,7 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=device)
     torch.manual_seed(WL["seed"] + rank)
 
-    bench = DeviceBench(device, rank, world, count_s_in=not (args.ncu or args.sweep))
+    bench = DeviceBench(device, rank, world, count_s_in=not (args.ncu or args.sweep), n_lanes=args.lanes)
     barrier = (lambda: dist.barrier()) if world > 1 else None
 
     if args.ncu:  # profiler mode: eager launches of whole frames, nothing else (numbers printed here are NOT bench values)
@@ -579,6 +611,7 @@ def run_ours(args):
             try:
                 nat.set_tuning(l, rpc, cap)
                 bench.saved = torch.empty(int(bench.lib.voxe_saved_floats(bench.rd, WL["batch"])), device=device)
+                bench.saved_lane = [bench.saved] + [torch.empty_like(bench.saved) for _ in range(bench.n_lanes - 1)]
                 res = {}
                 for what in ("fwd", "bwd", "both"):
                     gs = bench.capture(what, poses=[0, 3, 5])
@@ -590,6 +623,22 @@ def run_ours(args):
             except Exception as exc:  # noqa: BLE001
                 print(json.dumps({"sweep": cfg, "error": str(exc)[:200]}), flush=True)
         return
+
+    # strictly serialised variant first (one batch in flight), reported beside the headline
+    serialized = None
+    if bench.n_lanes > 1:
+        lanes = bench.n_lanes
+        bench.n_lanes = 1
+        g1 = bench.capture("both")
+        ms1 = bench.time_graphs(g1, args.steps, args.warmup, after_replay=after_replay, barrier=barrier)
+        if world > 1:
+            t = torch.tensor([ms1], device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms1 = float(t.item())
+        serialized = {"value": world * bench.R / (ms1 / args.steps * 1e-3), "ms_per_step": ms1 / args.steps,
+                      "note": "one batch in flight: fwd(k) -> bwd(k) -> fwd(k+1) ... on a single stream"}
+        del g1
+        bench.n_lanes = lanes
 
     graphs = bench.capture("both")
     sampler = ClockSampler(local)
@@ -640,6 +689,9 @@ def run_ours(args):
     e2e = None
     if args.workload == "cfg2":
         e2e = e2e_leg(device, rank, world, max(2, min(args.steps, args.e2e_steps)), min(args.warmup, 3), dist)
+        e2e_deferred = e2e_leg(device, rank, world, max(2, min(args.steps, args.e2e_steps)), min(args.warmup, 3), dist, deferred=True)
+        e2e["deferred_grads"] = {"value": e2e_deferred["value"], "ms_per_step": e2e_deferred["ms_per_step"],
+                                 "note": "same loop with VoxelGrid.accumulate_render_gradients(): gradients materialised once per frame"}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu and args.workload == "cfg2":
@@ -657,6 +709,8 @@ def run_ours(args):
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WL["name"], "step": f"one {WL['height']}x{WL['width']} frame = {len(bench.batches)} batches x (jitter, fwd, bwd) + grad zero-fill + unpack"
                        + (" + 1 NCCL all-reduce of packed voxel grads" if world > 1 else ""),
+                       "batches_in_flight": f"{bench.n_lanes} (each launch is one <=4096-ray batch with its own workspace; gradients accumulate "
+                                            "over the frame, so batch k+1's forward does not wait for batch k's backward)",
                        "l2": "3 rotating grid copies (197 MB) + 65.5 MB gradient volume > 126 MB L2; 8 poses rotate",
                        "parallelism": f"ray/view data parallel x{world}", "timing": "CUDA events around K graph replays, max over ranks"},
             "e2e": e2e, "gpu_launches": args.steps * bench.kernels_per_step, "roofline": roof, "clocks": clocks,
@@ -665,6 +719,8 @@ def run_ours(args):
             line["cpu_baseline"] = cpu
         if fused_step:
             line["fused_step"] = fused_step
+        if serialized:
+            line["serialized"] = serialized
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
@@ -682,6 +738,7 @@ def main():
     ap.add_argument("--ncu", action="store_true", help="profiler mode: run --steps eager frames and exit")
     ap.add_argument("--workload", choices=["cfg2", "cfg3", "cfg4", "cfg5"], default="cfg2",
                     help="cfg2 is the headline (the line the driver reads); the others are recorded in DESIGN.md")
+    ap.add_argument("--lanes", type=int, default=2, help="ray batches in flight within a frame (streams)")
     ap.add_argument("--sweep", type=str, default="", help="tuning sweep: 'L,rpc,cap;L,rpc,cap;...'")
     ap.add_argument("--tune", type=str, default="", help="L,rpc,regcap launch-shape override for tuning runs")
     args = ap.parse_args()
