@@ -292,3 +292,35 @@ def test_no_grad_and_partial_inputs():
         grid.densities.mul_(0.0)
     out0 = render_sh_voxel_grid(grid, rays, make_config(meta))
     assert float(out0.extra["accumulated_weight"].abs().max()) == 0.0
+
+
+def test_generator_consumption_matches_the_reference_in_strict_mode():
+    """Two consecutive seeded renders with perturb=True: in strict mode the global CUDA generator is consumed exactly as
+    the reference consumes it (rand for the jitter, then the always-drawn randn of accumulate.py:59-62)."""
+    import voxe_b200.render_function as rf
+    from _product import make_config, make_grid
+    from thre3d_atom.rendering.volumetric.render_interface import Rays
+    from thre3d_atom.thre3d_reprs.renderers import _render_spec, render_sh_voxel_grid
+
+    meta, a = load_case("perturb_jitter")
+    grid = make_grid(meta, a["densities"], a["features"], "cuda")
+    cfg = make_config(meta)
+    rays = Rays(a["rays_o"].cuda(), a["rays_d"].cuda())
+    R, S = len(rays), meta["num_samples"]
+    torch.manual_seed(123)
+    u1 = torch.rand(R, S, device="cuda")
+    torch.randn(R, S, device="cuda")
+    u2 = torch.rand(R, S, device="cuda")
+    spec = _render_spec(cfg, 3, attn=False, per_call_sampling_flags=True)
+    want = [rf.fused_render(grid.fused_spec(), spec, grid.densities, grid.features, rays.origins, rays.directions, jitter=u)[0].detach()
+            for u in (u1, u2)]
+    try:
+        rf.STRICT_REFERENCE_RNG = True
+        torch.manual_seed(123)
+        got = [render_sh_voxel_grid(grid, rays, cfg).colour.detach() for _ in range(2)]
+    finally:
+        rf.STRICT_REFERENCE_RNG = False
+    assert torch.equal(got[0], want[0]) and torch.equal(got[1], want[1])
+    torch.manual_seed(123)
+    loose = [render_sh_voxel_grid(grid, rays, cfg).colour.detach() for _ in range(2)]
+    assert torch.equal(loose[0], want[0]) and not torch.equal(loose[1], want[1])  # default mode: first call identical only

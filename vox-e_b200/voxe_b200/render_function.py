@@ -75,6 +75,13 @@ class FusedRenderSpec:
         return r
 
 
+# The reference draws ``torch.randn(R, S)`` for the density noise on EVERY call, even when
+# stochastic_density_noise_std == 0 and the draw is multiplied away (accumulate.py:59-62).  Skipping that draw changes
+# nothing in one call's result but leaves the global generator in a different state for the next call.  Set this to True
+# to consume the generator exactly like the reference (one extra RNG kernel per call) when replaying its seeded runs.
+STRICT_REFERENCE_RNG = False
+
+
 def _ptr(t: Optional[Tensor]) -> Optional[int]:
     return None if t is None else t.data_ptr()
 
@@ -312,6 +319,8 @@ def fused_render(
         noise = noise.detach().float().contiguous()
     else:
         noise = None
+        if STRICT_REFERENCE_RNG:
+            torch.randn(R, S, dtype=torch.float32, device=dev, generator=generator)  # drawn and discarded, as upstream
     packed = (cache or PackedVolumeCache()).get(gspec, densities, features)
     if R == 0:
         z = torch.zeros((0, 1), dtype=torch.float32, device=dev)
