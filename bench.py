@@ -738,7 +738,7 @@ def main():
     ap.add_argument("--ncu", action="store_true", help="profiler mode: run --steps eager frames and exit")
     ap.add_argument("--workload", choices=["cfg2", "cfg3", "cfg4", "cfg5"], default="cfg2",
                     help="cfg2 is the headline (the line the driver reads); the others are recorded in DESIGN.md")
-    ap.add_argument("--lanes", type=int, default=2, help="ray batches in flight within a frame (streams)")
+    ap.add_argument("--lanes", type=int, default=3, help="ray batches in flight within a frame (streams)")
     ap.add_argument("--sweep", type=str, default="", help="tuning sweep: 'L,rpc,cap;L,rpc,cap;...'")
     ap.add_argument("--tune", type=str, default="", help="L,rpc,regcap launch-shape override for tuning runs")
     args = ap.parse_args()

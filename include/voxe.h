@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define VOXE_ABI_VERSION 5
+#define VOXE_ABI_VERSION 6
 
 #if defined(__GNUC__)
 #define VOXE_API __attribute__((visibility("default")))
@@ -103,9 +103,10 @@ VOXE_API const char* voxe_last_error(void);
 /* roundup4(n_features + 1): channel count of the packed volume. */
 VOXE_API int voxe_packed_channels(int n_features);
 
-/* Number of floats of the packed volume of `grid`: channels * 8 * ceil(X/2) * ceil(Y/2) * ceil(Z/2).  The volume is
- * stored as 2x2x2 bricks of voxels (one brick of SH-0 voxels = one 128-byte line) -- an internal layout: only
- * voxe_pack_grid / voxe_unpack_grad convert to and from the reference's [X,Y,Z,.] tensors. */
+/* Number of floats of the packed volume of `grid`: channels * 8 * ceil((X+2)/2) * ceil((Y+2)/2) * ceil((Z+2)/2).  The
+ * volume is the grid plus a one-voxel apron of zeros (grid_sample's zeros padding, voxels.py:306-333, without range
+ * checks in the kernels), stored as 2x2x2 bricks of voxels (one brick of SH-0 voxels = one 128-byte line) -- an internal
+ * layout: only voxe_pack_grid / voxe_unpack_grad convert to and from the reference's [X,Y,Z,.] tensors. */
 VOXE_API int64_t voxe_packed_floats(const VoxeGridDesc* grid);
 
 /* packed <- bricked concat(features[X,Y,Z,F], densities[X,Y,Z,1], zero padding).  Values are copied verbatim;
@@ -118,10 +119,12 @@ VOXE_API int voxe_pack_grid(const VoxeGridDesc* grid, const float* densities, co
 VOXE_API int voxe_unpack_grad(const VoxeGridDesc* grid, const float* packed_grad, float* d_densities, float* d_features,
                      int accumulate, voxe_stream_t stream);
 
-/* Number of floats of the `saved` workspace that links a forward call to its backward call:
- * (n_colour + 3) per ray and per depth segment (the transmittance at the segment start and the segment's local sums
- * of w*colour, w*z, w).  It replaces the O(R*S) activations autograd keeps for the reference (~35 floats per sample)
- * with < 1 float per sample.  Depends on the current voxe_set_tuning() state: do not retune between the two calls. */
+/* Number of floats of the `saved` workspace that links a forward call to its backward call: one 16-byte vector per
+ * sample slot (tone-mapped colour(s) + interpolated raw density, so the backward does not re-gather the 8 corner
+ * vectors of every sample) plus (n_colour + 3) floats per ray and depth segment (the transmittance at the segment
+ * start and the segment's local sums of w*colour, w*z, w).  About 4.4 floats per sample, against the ~35 floats per
+ * sample autograd keeps for the reference.  The buffer must be 16-byte aligned.  Depends on the current
+ * voxe_set_tuning() state: do not retune between the two calls. */
 VOXE_API int64_t voxe_saved_floats(const VoxeRenderDesc* render, int64_t num_rays);
 
 /* Forward render of R rays.
@@ -145,6 +148,15 @@ VOXE_API int voxe_render_bwd(const VoxeGridDesc* grid, const VoxeRenderDesc* ren
                     const float* rays_o, const float* rays_d, const float* jitter, const float* noise,
                     const float* saved, const float* g_colour, const float* g_depth, const float* g_acc,
                     const float* g_disp, float* packed_grad, int64_t num_rays, voxe_stream_t stream);
+
+/* Sparse hand-over of a packed gradient volume: every non-zero 16-byte vector of `packed_grad` is ADDED into
+ * d_densities[X,Y,Z,1] / d_features[X,Y,Z,F] (either may be NULL) and then cleared, so that `packed_grad` is all-zero
+ * again when the call returns.  A ray batch touches a few percent of the voxels; this pass reads the volume once and
+ * writes only what the batch touched, replacing zero-fill + voxe_unpack_grad + a dense `.grad +=` per backward call
+ * (the autograd accumulation of trainers.py:350 / sds_trainer.py:332).  Requires d_* to hold valid values (zeros for
+ * a fresh gradient). */
+VOXE_API int voxe_consume_grad(const VoxeGridDesc* grid, float* packed_grad, float* d_densities, float* d_features,
+                      voxe_stream_t stream);
 
 /* One Adam step on the two grids, fused with everything else the optimiser step does to them
  * (replaces `optimizer.zero_grad(); ...; optimizer.step()` of thre3d_atom/modules/trainers.py:247-255,348-351 and

@@ -74,7 +74,8 @@ def test_argument_validation_without_a_gpu():
     assert lib.voxe_render_fwd(gd, rd, None, None, None, None, None, None, None, None, None, None, 16, None) == 1
     assert b"jitter" in lib.voxe_last_error()
     rd.flags = 0
-    assert lib.voxe_saved_floats(rd, 4096) == 6 * 8 * 4096  # (n_colour+3) floats x 8 segments of 8 samples x rays
+    # per segment (8 segments of 8 samples at S=64): (n_colour+3) summary floats + one float4 per sample slot
+    assert lib.voxe_saved_floats(rd, 4096) == (6 + 4 * 8) * 8 * 4096
     assert lib.voxe_set_tuning(3, 5, 0) == 1 and lib.voxe_set_tuning(0, 0, 0) == 0
     with pytest.raises(NotImplementedError):
         nat.check(2, "x")

@@ -62,16 +62,19 @@ int check_render(const VoxeGridDesc* g, const VoxeRenderDesc* r, const float* ji
   return VOXE_OK;
 }
 
-// Launch shape: samples per thread L, sample segments per ray, rays per CTA, register budget of the kernel variant.
-// Measured on B200 at S=256 (profiles/): small CTAs (about four warps: 4 rays x 32 segments) balance best over the 148
-// SMs because rays through the middle of the grid cost several times more than rays that miss it; the 64-register
-// variant keeps a whole 4096-ray batch resident at SH-0, higher SH degrees need the 128-register one (no spills).
+// Launch shape: depth segments per ray nseg = ceil(S / L) (each thread streams 1/nseg of the ray's in-grid samples, see
+// thread_samples in voxe_render.cu), rays per CTA, register budget of the kernel variant.
+// Measured on B200 at S=256 (profiles/r1_sweep*.txt): small CTAs (four warps: 8 rays x 16 segments) balance best over
+// the 148 SMs; the 128-register variant has no spills and, with fewer and longer threads, leaves room for a second
+// batch's kernels to run beside it (a frame keeps 2-3 batches in flight): 30 us per 4096-ray batch fwd+bwd against
+// 38 us for 4 rays x 32 segments at 64 registers, although the kernels timed alone are equal.
 int pick_shape(int S, int sh_degree, int& L, int& nseg, int& rpc, int& regcap) {
   regcap = g_tune_reg.load();
-  if (regcap != 64 && regcap != 128) regcap = (sh_degree == 0) ? 64 : 128;
+  if (regcap != 64 && regcap != 128) regcap = 128;
+  (void)sh_degree;
   const int max_threads = voxe::max_threads_per_cta(regcap);
   L = g_tune_l.load();
-  if (L < 1 || L > 64) L = (S <= 32) ? 4 : 8;
+  if (L < 1 || L > 64) L = (S <= 32) ? 4 : (S < 128 ? 8 : 16);
   while ((S + L - 1) / L > max_threads) L *= 2;  // very long rays: more samples per thread
   nseg = (S + L - 1) / L;
   rpc = g_tune_rpc.load();
@@ -90,14 +93,14 @@ int fill_params(const VoxeGridDesc* g, const VoxeRenderDesc* r, int64_t R, voxe:
   p.X = g->dims[0];
   p.Y = g->dims[1];
   p.Z = g->dims[2];
-  p.sby = ((g->dims[2] + 1) / 2) * 8;
-  p.sbx = ((g->dims[1] + 1) / 2) * p.sby;
+  p.sby = ((g->dims[2] + 3) / 2) * 8;  // bricks over the aproned extent (N + 2 voxels per axis)
+  p.sbx = ((g->dims[1] + 3) / 2) * p.sby;
   for (int a = 0; a < 3; ++a) {
     p.lo[a] = g->aabb_lo[a];
     p.hi[a] = g->aabb_hi[a];
     // u = ((p*scale + bias + 1) * N - 1) / 2 folded into one multiply-add
     p.ua[a] = (float)(0.5 * (double)g->norm_scale[a] * g->dims[a]);
-    p.ub[a] = (float)(0.5 * (((double)g->norm_bias[a] + 1.0) * g->dims[a] - 1.0));
+    p.ub[a] = (float)(0.5 * (((double)g->norm_bias[a] + 1.0) * g->dims[a] - 1.0) + 1.0);  // +1: zero apron
   }
   p.near = r->near;
   p.far = r->far;
@@ -144,7 +147,7 @@ int64_t voxe_saved_floats(const VoxeRenderDesc* render, int64_t num_rays) {
   if (!render || render->num_samples < 2 || num_rays < 0) return 0;
   int L, nseg, rpc, regcap;
   if (pick_shape(render->num_samples, render->sh_degree, L, nseg, rpc, regcap)) return 0;
-  return (int64_t)voxe::saved_floats_per_segment(render->n_colour) * nseg * num_rays;
+  return (int64_t)voxe::saved_floats_per_segment(render->n_colour, L) * nseg * num_rays;
 }
 
 int voxe_pack_grid(const VoxeGridDesc* grid, const float* densities, const float* features, float* packed,
@@ -166,6 +169,17 @@ int voxe_unpack_grad(const VoxeGridDesc* grid, const float* packed_grad, float* 
   cudaError_t e = voxe::launch_unpack_grad(packed_grad, d_densities, d_features, grid->dims, grid->n_features,
                                            grid->channels, accumulate != 0, (cudaStream_t)stream);
   if (e != cudaSuccess) return cuda_fail(e, "voxe_unpack_grad launch");
+  g_launches.fetch_add(1);
+  return VOXE_OK;
+}
+
+int voxe_consume_grad(const VoxeGridDesc* grid, float* packed_grad, float* d_densities, float* d_features,
+                      voxe_stream_t stream) {
+  if (int rc = check_grid(grid)) return rc;
+  if (!packed_grad) return fail(VOXE_ERR_INVALID_ARGUMENT, "voxe_consume_grad: NULL packed_grad");
+  cudaError_t e = voxe::launch_consume_grad(packed_grad, d_densities, d_features, grid->dims, grid->n_features,
+                                            grid->channels, (cudaStream_t)stream);
+  if (e != cudaSuccess) return cuda_fail(e, "voxe_consume_grad launch");
   g_launches.fetch_add(1);
   return VOXE_OK;
 }

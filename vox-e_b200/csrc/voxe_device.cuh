@@ -37,13 +37,15 @@ struct KParams {
   const float* g_disp;
   int R, S;
   int X, Y, Z;
-  int sbx, sby;   // brick strides in voxels: voxel (x,y,z) lives at (x>>1)*sbx + (y>>1)*sby + (z>>1)*8 + (x&1)*4 + (y&1)*2 + (z&1)
+  int sbx, sby;   // brick strides in voxel slots; with x' = x+1 etc. (one-voxel zero apron) voxel (x,y,z) lives at
+                  // (x'>>1)*sbx + (y'>>1)*sby + (z'>>1)*8 + (x'&1)*4 + (y'&1)*2 + (z'&1)
   float lo[3], hi[3];
-  float ua[3], ub[3];   // voxel-space coordinate u = p*ua + ub  (= ((p*nscale + nbias + 1) * N - 1) / 2, folded on the host)
+  float ua[3], ub[3];   // apron-shifted voxel coordinate u = p*ua + ub  (= ((p*nscale + nbias + 1) * N - 1) / 2 + 1, folded on the host)
   float near, far, dscale, noise_std, lin_step;
   int flags, preact, postact;
   int rpc, nseg, L;  // rays per CTA, sample segments per ray, samples per segment (threads = rpc * nseg -> x32)
-  float* saved;      // [NCOL+3][nseg][R] segment summaries written by the forward / read by the backward (or null)
+  float* saved;      // workspace written by the forward / read by the backward (or null): [nseg*L][R] float4 sample
+                     // vectors, then [NCOL+3][nseg][R] segment summaries (16-byte aligned)
 };
 
 // ---------------------------------------------------------------------------------------------------------
@@ -134,7 +136,7 @@ __device__ __forceinline__ void sh_basis(float x, float y, float z, bool diffuse
 // trilinear corner set (grid_sample: bilinear, zeros padding, align_corners=False)
 // ---------------------------------------------------------------------------------------------------------
 struct Corners {
-  int idx[8];   // voxel slot in the bricked volume (clamped into range; weight is zero when the true corner is outside)
+  int idx[8];   // voxel slot in the bricked, zero-aproned volume
   float w[8];
 };
 
@@ -143,41 +145,43 @@ __device__ __forceinline__ bool inside_aabb(const KParams& p, float px, float py
   return (px > p.lo[0]) & (px < p.hi[0]) & (py > p.lo[1]) & (py < p.hi[1]) & (pz > p.lo[2]) & (pz < p.hi[2]);
 }
 
-// One axis of the trilinear footprint.  u = (p - lo)/voxel - 0.5 is evaluated with one FMA (coefficients folded on the
-// host in double); unlike the inside test this is a continuous function of p, so the different rounding relative to
-// the reference's normalise -> unnormalise chain (voxels.py:225-234 + grid_sampler) only moves results by ~1e-7 * N.
-// For a point strictly inside the box floor(u) lies in [-1, N-1]: only the low corner can fall below 0 and only the
-// high corner above N-1; those get weight 0 (zeros padding) and a clamped, harmless address.
-__device__ __forceinline__ void axis_setup(float pc, float ua, float ub, int N, int& i0, int& i1, float& w0, float& w1) {
+// One axis of the trilinear footprint.  The packed volume carries a one-voxel apron of zeros on every face, and the
+// voxel coordinate is shifted by +1 accordingly: u = (p - lo)/voxel + 0.5, evaluated with one FMA (coefficients folded
+// on the host in double; unlike the inside test this is a continuous function of p, so the different rounding
+// relative to the reference's normalise -> unnormalise chain (voxels.py:225-234 + grid_sampler) only moves results by
+// ~1e-7 * N).  For a point strictly inside the box floor(u) lies in [0, N], so both corners i and i+1 are always
+// addressable: a corner beyond the grid reads an apron zero -- exactly grid_sample's zeros padding -- and no range
+// checks or weight masking are needed.  (The clamp only guards the address against rounding at extreme coordinates.)
+__device__ __forceinline__ void axis_setup(float pc, float ua, float ub, int N, int& i0, float& w0, float& w1) {
   const float u = fmaf(pc, ua, ub);
   const float fl = floorf(u);
-  const float f = u - fl;
-  const int i = (int)fl;
-  w0 = (i >= 0 && i < N) ? (1.0f - f) : 0.f;
-  w1 = (i + 1 >= 0 && i + 1 < N) ? f : 0.f;
-  i0 = min(max(i, 0), N - 1);
-  i1 = min(max(i + 1, 0), N - 1);
+  w1 = u - fl;
+  w0 = 1.0f - w1;
+  i0 = min(max((int)fl, 0), N);
 }
 
 __device__ __forceinline__ void make_corners(const KParams& p, float px, float py, float pz, Corners& c) {
-  int x0, x1, y0, y1, z0, z1;
+  int x0, y0, z0;
   float wx0, wx1, wy0, wy1, wz0, wz1;
-  axis_setup(px, p.ua[0], p.ub[0], p.X, x0, x1, wx0, wx1);
-  axis_setup(py, p.ua[1], p.ub[1], p.Y, y0, y1, wy0, wy1);
-  axis_setup(pz, p.ua[2], p.ub[2], p.Z, z0, z1, wz0, wz1);
-  // 2x2x2-brick addressing (one brick of SH-0 voxels = one 128-byte line): per-axis partial offsets, then 8 sums
-  const int xa0 = (x0 >> 1) * p.sbx + ((x0 & 1) << 2), xa1 = (x1 >> 1) * p.sbx + ((x1 & 1) << 2);
-  const int ya0 = (y0 >> 1) * p.sby + ((y0 & 1) << 1), ya1 = (y1 >> 1) * p.sby + ((y1 & 1) << 1);
-  const int za0 = ((z0 >> 1) << 3) + (z0 & 1), za1 = ((z1 >> 1) << 3) + (z1 & 1);
+  axis_setup(px, p.ua[0], p.ub[0], p.X, x0, wx0, wx1);
+  axis_setup(py, p.ua[1], p.ub[1], p.Y, y0, wy0, wy1);
+  axis_setup(pz, p.ua[2], p.ub[2], p.Z, z0, wz0, wz1);
+  // 2x2x2-brick addressing (one brick of SH-0 voxels = one 128-byte line): per-axis partial offsets, then 8 sums.
+  // Index i+1 stays in the brick of i when i is even and moves to the next brick (low slot) when i is odd.
+  const int xo = x0 & 1, yo = y0 & 1, zo = z0 & 1;
+  const int xa0 = (x0 >> 1) * p.sbx + (xo << 2), xa1 = xa0 + (xo ? p.sbx - 4 : 4);
+  const int ya0 = (y0 >> 1) * p.sby + (yo << 1), ya1 = ya0 + (yo ? p.sby - 2 : 2);
+  const int za0 = ((z0 >> 1) << 3) + zo, za1 = za0 + (zo ? 7 : 1);
   const int r00 = xa0 + ya0, r01 = xa0 + ya1, r10 = xa1 + ya0, r11 = xa1 + ya1;
-  c.idx[0] = r00 + za0; c.w[0] = wx0 * wy0 * wz0;
-  c.idx[1] = r00 + za1; c.w[1] = wx0 * wy0 * wz1;
-  c.idx[2] = r01 + za0; c.w[2] = wx0 * wy1 * wz0;
-  c.idx[3] = r01 + za1; c.w[3] = wx0 * wy1 * wz1;
-  c.idx[4] = r10 + za0; c.w[4] = wx1 * wy0 * wz0;
-  c.idx[5] = r10 + za1; c.w[5] = wx1 * wy0 * wz1;
-  c.idx[6] = r11 + za0; c.w[6] = wx1 * wy1 * wz0;
-  c.idx[7] = r11 + za1; c.w[7] = wx1 * wy1 * wz1;
+  const float w00 = wx0 * wy0, w01 = wx0 * wy1, w10 = wx1 * wy0, w11 = wx1 * wy1;
+  c.idx[0] = r00 + za0; c.w[0] = w00 * wz0;
+  c.idx[1] = r00 + za1; c.w[1] = w00 * wz1;
+  c.idx[2] = r01 + za0; c.w[2] = w01 * wz0;
+  c.idx[3] = r01 + za1; c.w[3] = w01 * wz1;
+  c.idx[4] = r10 + za0; c.w[4] = w10 * wz0;
+  c.idx[5] = r10 + za1; c.w[5] = w10 * wz1;
+  c.idx[6] = r11 + za0; c.w[6] = w11 * wz0;
+  c.idx[7] = r11 + za1; c.w[7] = w11 * wz1;
 }
 
 __device__ __forceinline__ float f4_get(const float4& v, int k) {
@@ -239,6 +243,46 @@ __device__ __forceinline__ void load_ray(const KParams& p, int ray, RayCtx& rc) 
     rc.inv_far = __fdiv_rn(1.0f, rc.far);
   }
   rc.dnorm = sqrtf(rc.d[0] * rc.d[0] + rc.d[1] * rc.d[1] + rc.d[2] * rc.d[2]);
+}
+
+// Conservative index range [a, b) of the samples of one ray that can lie inside the grid AABB.  Samples outside the
+// box contribute exactly nothing (sigma = 0 -> alpha = 0, process.py:80-91), so the kernels only distribute [a, b)
+// over a ray's threads; the exact per-sample inside test (inside_aabb) still decides, this range only has to be a
+// superset.  Plain depths are z_i = near + (far-near) * i/(S-1); stratified jitter keeps z'_i between the mid-points to
+// its neighbours, i.e. within half a step of z_i.  The range is widened by one further sample on each side against
+// fp32 rounding of the slab arithmetic (a sample step is ~1e4 ulp of z).  Disparity sampling (non-linear in i), density
+// noise (every sample contributes) and degenerate intervals use the full range.
+__device__ __forceinline__ void sample_range(const KParams& p, const RayCtx& rc, int& a, int& b) {
+  a = 0;
+  b = p.S;
+  if (rc.disparity || p.noise_std != 0.f) return;
+  const float span = rc.far - rc.near;
+  if (!(span > 0.f)) return;
+  float zin = -kInfinity, zout = kInfinity;
+  bool empty = false;
+#pragma unroll
+  for (int ax = 0; ax < 3; ++ax) {
+    const float o = rc.o[ax], d = rc.d[ax];
+    if (d == 0.f) {
+      empty |= !(o > p.lo[ax] && o < p.hi[ax]);
+    } else {
+      const float inv = 1.0f / d;
+      const float t0 = (p.lo[ax] - o) * inv, t1 = (p.hi[ax] - o) * inv;
+      zin = fmaxf(zin, fminf(t0, t1));
+      zout = fminf(zout, fmaxf(t0, t1));
+    }
+  }
+  if (empty || !(zin <= zout)) {  // also catches NaN
+    b = 0;
+    return;
+  }
+  const float per_z = (float)(p.S - 1) / span;  // samples per unit depth
+  const float fs = (float)p.S;
+  const float xa = fminf(fmaxf((zin - rc.near) * per_z, -2.f), fs + 2.f);
+  const float xb = fminf(fmaxf((zout - rc.near) * per_z, -2.f), fs + 2.f);
+  a = max((int)floorf(xa) - 1, 0);
+  b = min((int)ceilf(xb) + 2, p.S);
+  if (b < a) b = a;
 }
 
 // Rolling evaluation of the (optionally jittered) sample depths along one ray: `cur` is the depth of sample i,

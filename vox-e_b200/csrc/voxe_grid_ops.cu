@@ -11,10 +11,13 @@
 namespace voxe {
 namespace {
 
-// Packed volume layout: 2x2x2 bricks of voxels, bricks in (x, y, z) row-major order, 8 voxel slots per brick ordered
+// Packed volume layout: the grid plus a one-voxel apron of zeros on every face ((X+2) x (Y+2) x (Z+2) voxels, index
+// shifted by +1), cut into 2x2x2 bricks, bricks in (x, y, z) row-major order, 8 voxel slots per brick ordered
 // (x&1, y&1, z&1), CV float4 per slot.  At SH-0 (CV = 1) a brick is exactly one 128-byte line, so the 8 corners of a
 // trilinear cell touch 1..8 lines (3.4 on average) instead of 4..8, and neighbouring rays share lines in x and y as
-// well as in z.  Slots of partial bricks at odd grid dimensions are zero and never addressed by the kernels.
+// well as in z.  The apron implements grid_sample's zeros padding without range checks in the render kernels: apron
+// slots (and the padding slots of partial bricks) hold zeros in the volume, and whatever the backward scatters into
+// them in the gradient volume is dropped here.
 struct BrickDims {
   int X, Y, Z, BY, BZ;
 };
@@ -26,9 +29,9 @@ __device__ __forceinline__ bool slot_to_voxel(const BrickDims& d, int64_t slot, 
   const int64_t t = brick / d.BZ;
   const int by = (int)(t % d.BY);
   const int bx = (int)(t / d.BY);
-  const int x = 2 * bx + (within >> 2), y = 2 * by + ((within >> 1) & 1), z = 2 * bz + (within & 1);
+  const int x = 2 * bx + (within >> 2) - 1, y = 2 * by + ((within >> 1) & 1) - 1, z = 2 * bz + (within & 1) - 1;
   v = ((int64_t)x * d.Y + y) * d.Z + z;
-  return x < d.X && y < d.Y && z < d.Z;
+  return x >= 0 && y >= 0 && z >= 0 && x < d.X && y < d.Y && z < d.Z;  // false: apron / brick padding slot
 }
 
 // one thread per packed float4: slot = t / CV, channels 4j..4j+3
@@ -75,6 +78,33 @@ __global__ void __launch_bounds__(256) unpack_grad_kernel(const float4* __restri
         float* dst = d_dens + v;
         *dst = accumulate ? (*dst + in[k]) : in[k];
       }
+    }
+  }
+}
+
+// Sparse hand-over: add the non-zero vectors of the packed gradient volume into the reference-layout gradients and
+// clear them.  One thread per packed float4; a warp reads 512 contiguous bytes and writes only where a ray batch
+// scattered something (a few percent of the volume), so the pass costs one read of the volume.
+__global__ void __launch_bounds__(256) consume_grad_kernel(float4* __restrict__ pg, float* __restrict__ d_dens,
+                                                           float* __restrict__ d_feat, int64_t n_vec, int F, int CV,
+                                                           BrickDims d) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_vec) return;
+  const float4 g = pg[t];
+  if (g.x == 0.f && g.y == 0.f && g.z == 0.f && g.w == 0.f) return;
+  pg[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+  const int64_t slot = t / CV;
+  const int c0 = (int)(t - slot * CV) * 4;
+  int64_t v;
+  if (!slot_to_voxel(d, slot, v)) return;  // apron / padding slot: whatever was scattered there is dropped
+  const float in[4] = {g.x, g.y, g.z, g.w};
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int c = c0 + k;
+    if (c < F) {
+      if (d_feat) d_feat[v * F + c] += in[k];
+    } else if (c == F) {
+      if (d_dens) d_dens[v] += in[k];
     }
   }
 }
@@ -134,12 +164,12 @@ __global__ void __launch_bounds__(256) adam_step_kernel(float4* __restrict__ pac
   packed_v[t] = make_float4(vv[0], vv[1], vv[2], vv[3]);
 }
 
-BrickDims brick_dims(const int dims[3]) { return BrickDims{dims[0], dims[1], dims[2], (dims[1] + 1) / 2, (dims[2] + 1) / 2}; }
+BrickDims brick_dims(const int dims[3]) { return BrickDims{dims[0], dims[1], dims[2], (dims[1] + 3) / 2, (dims[2] + 3) / 2}; }
 
 }  // namespace
 
 int64_t packed_voxel_slots(const int dims[3]) {
-  return (int64_t)((dims[0] + 1) / 2) * ((dims[1] + 1) / 2) * ((dims[2] + 1) / 2) * 8;
+  return (int64_t)((dims[0] + 3) / 2) * ((dims[1] + 3) / 2) * ((dims[2] + 3) / 2) * 8;  // N + 2 voxels per axis (apron)
 }
 
 cudaError_t launch_pack_grid(const float* densities, const float* features, float* packed, const int dims[3],
@@ -162,6 +192,17 @@ cudaError_t launch_unpack_grad(const float* packed_grad, float* d_densities, flo
   unpack_grad_kernel<<<(unsigned)blocks, threads, 0, stream>>>(reinterpret_cast<const float4*>(packed_grad),
                                                                d_densities, d_features, n_vec, n_features, CV,
                                                                accumulate ? 1 : 0, brick_dims(dims));
+  return cudaGetLastError();
+}
+
+cudaError_t launch_consume_grad(float* packed_grad, float* d_densities, float* d_features, const int dims[3],
+                                int n_features, int channels, cudaStream_t stream) {
+  const int CV = channels / 4;
+  const int64_t n_vec = packed_voxel_slots(dims) * CV;
+  const int threads = 256;
+  const int64_t blocks = (n_vec + threads - 1) / threads;
+  consume_grad_kernel<<<(unsigned)blocks, threads, 0, stream>>>(reinterpret_cast<float4*>(packed_grad), d_densities,
+                                                                d_features, n_vec, n_features, CV, brick_dims(dims));
   return cudaGetLastError();
 }
 

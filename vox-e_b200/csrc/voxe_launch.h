@@ -10,7 +10,7 @@ struct KParams;
 // fused ray-marcher (voxe_render.cu)
 cudaError_t launch_render(const KParams& p, int sh_degree, int n_colour, int regcap, bool backward, cudaStream_t stream);
 int max_threads_per_cta(int regcap);
-int saved_floats_per_segment(int n_colour);
+int saved_floats_per_segment(int n_colour, int samples_per_segment);  // segment summary + one float4 per sample
 
 // full-grid passes (voxe_grid_ops.cu)
 int64_t packed_voxel_slots(const int dims[3]);  // voxel slots of the 2x2x2-bricked volume (>= X*Y*Z)
@@ -18,6 +18,9 @@ cudaError_t launch_pack_grid(const float* densities, const float* features, floa
                              int n_features, int channels, cudaStream_t stream);
 cudaError_t launch_unpack_grad(const float* packed_grad, float* d_densities, float* d_features, const int dims[3],
                                int n_features, int channels, bool accumulate, cudaStream_t stream);
+
+cudaError_t launch_consume_grad(float* packed_grad, float* d_densities, float* d_features, const int dims[3],
+                                int n_features, int channels, cudaStream_t stream);
 
 cudaError_t launch_adam_step(float* packed, float* packed_grad, float* packed_m, float* packed_v, float* densities,
                              float* features, const float* dense_gd, const float* dense_gf, const int dims[3], int n_features,

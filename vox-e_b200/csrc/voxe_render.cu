@@ -11,15 +11,18 @@
 //   product scan of T over `seg` (warp shuffles on a shared-memory transpose), which is the only cross-thread
 //   communication.  Nothing of size O(R*S) is ever written to memory.
 //
-// Forward: streams over its L samples (gather 8 corners -> interpolate -> SH -> alpha), then the stitch.  When a
-//   `saved` workspace is given it also stores, per (ray, segment), the transmittance at the segment start and the
-//   segment's local sums -- (NCOL+3) floats per L samples -- which is all the backward needs from the forward.
+// Forward: streams over its samples (gather 8 corners -> interpolate -> SH -> alpha), then the stitch.  When a
+//   `saved` workspace is given (a backward will follow) it also stores
+//     * per in-grid sample the tone-mapped colour and the interpolated raw density -- one 16-byte vector, laid out
+//       [slot][ray] so that the rays of a warp write one 128-byte line per depth segment -- and
+//     * per (ray, segment) the transmittance at the segment start and the segment's local sums ((NCOL+3) floats).
 //
-// Backward (closed form of SURVEY.md 8.A): reads the saved segment summaries, turns them into "sum of w*q over
-//   everything behind this segment" with one suffix scan, and then streams over its samples ONCE: re-gather,
-//   recompute alpha / T / w, form dL/dsigma_i = delta_i (T_{i+1} q_i - sum_{j>i} w_j q_j) and dL/draw, and scatter
-//   to the 8 corners with 16-byte vector REDs (red.global.add.v4.f32 -> REDG.E.ADD.F32x4).  No per-sample state
-//   is kept in registers, so the kernel fits a 64-register budget and the whole 4096-ray batch is resident at once.
+// Backward (closed form of SURVEY.md 8.A): reads the segment summaries, turns them into "sum of w*q over everything
+//   behind this segment" with one suffix scan, and then streams over its samples ONCE: reload the sample vector (one
+//   LDG.128 instead of re-gathering 8 x CV corner vectors), recompute alpha / T / w, form
+//   dL/dsigma_i = delta_i (T_{i+1} q_i - sum_{j>i} w_j q_j) and dL/draw, and scatter to the 8 corners with 16-byte
+//   vector REDs (red.global.add.v4.f32 -> REDG.E.ADD.F32x4).  The workspace is 16 bytes per sample, against the ~140
+//   bytes per sample autograd keeps for the reference.
 #include "voxe_device.cuh"
 #include "voxe_launch.h"
 
@@ -72,12 +75,18 @@ __device__ __forceinline__ float gather_sample(const KParams& p, const Corners& 
       fe[4 * j + 2] = fmaf(w, v[q][j].z, fe[4 * j + 2]);
       fe[4 * j + 3] = fmaf(w, v[q][j].w, fe[4 * j + 3]);
     }
-    float dv = f4_get(v[q][LT::DCH], LT::DCO) * p.dscale;  // voxels.py:303-305: pre(density * scale) at the voxel
-    if (p.preact == kPreAbs) {
-      if (dv < 0.f) signs |= (1u << q);
-      dv = fabsf(dv);
+  }
+  // voxels.py:303-305: pre(density * scale) is applied at the voxels, then interpolated
+  if (p.preact == kPreAbs) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const float dv = f4_get(v[q][LT::DCH], LT::DCO);
+      if (dv * p.dscale < 0.f) signs |= (1u << q);
+      sig = fmaf(c.w[q], fabsf(dv), sig);
     }
-    sig = fmaf(w, dv, sig);
+    sig *= fabsf(p.dscale);
+  } else {
+    sig = fe[LT::F] * p.dscale;  // identity: the blend of the density channel, scaled once
   }
 #pragma unroll
   for (int ch = 0; ch < NCOL; ++ch) {
@@ -115,6 +124,37 @@ __device__ __forceinline__ float warp_scan_suffix_add(float x, int lane) {
   return x;
 }
 
+// Layout of the `saved` workspace: [nseg * L][R] sample vectors (float4), then [(NCOL+3)][nseg][R] segment summaries.
+__device__ __forceinline__ float4* sample_slots(const KParams& p, int seg, int ray) {
+  return reinterpret_cast<float4*>(p.saved) + (size_t)seg * p.L * p.R + ray;  // + j * R for the thread's j-th sample
+}
+__device__ __forceinline__ float* summaries(const KParams& p) { return p.saved + (size_t)4 * p.nseg * p.L * p.R; }
+
+// Sign bits of the 8 corner densities (abs pre-activation only): d|x|/dx < 0.
+template <int DEG, int NCOL>
+__device__ __forceinline__ unsigned corner_signs(const KParams& p, const Corners& c) {
+  using LT = Layout<DEG, NCOL>;
+  unsigned signs = 0u;
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const float dv = f4_get(__ldg(p.grid + (size_t)c.idx[q] * LT::CV + LT::DCH), LT::DCO);
+    if (dv * p.dscale < 0.f) signs |= (1u << q);
+  }
+  return signs;
+}
+
+// Samples [i0, i1) of depth segment `seg` of one ray: the ray's in-grid index range (sample_range) split evenly over
+// the nseg threads of the ray, so every thread of a ray streams the same number of (almost always in-grid) samples
+// whatever part of [near, far] the grid occupies; at most L = ceil(S / nseg) of them.  Forward and backward evaluate
+// this identically.
+__device__ __forceinline__ void thread_samples(const KParams& p, const RayCtx& rc, int seg, int& i0, int& i1) {
+  int a, b;
+  sample_range(p, rc, a, b);
+  const int per = (b - a + p.nseg - 1) / p.nseg;
+  i0 = a + seg * per;
+  i1 = min(i0 + per, b);
+}
+
 template <int REGCAP>
 struct Bounds {
   static constexpr int kThreads = (REGCAP <= 64) ? 1024 : 512;
@@ -143,10 +183,12 @@ __global__ void __launch_bounds__(Bounds<REGCAP>::kThreads, 1) render_fwd_kernel
   if (active) {
     RayCtx rc;
     load_ray(p, ray, rc);
-    const int L = p.L, i0 = seg * L, i1 = min(i0 + L, p.S);
+    int i0, i1;
+    thread_samples(p, rc, seg, i0, i1);
     const float* u_row = p.jitter ? p.jitter + (size_t)ray * p.S : nullptr;
+    float4* samples = p.saved ? sample_slots(p, seg, ray) : nullptr;
     DepthWalker zw;
-    zw.init(p, rc, u_row, i0);
+    if (i0 < i1) zw.init(p, rc, u_row, i0);
     const bool use_noise = (p.noise_std != 0.f);
     float Y[LT::K];
     const float inv = 1.0f / rc.dnorm;
@@ -171,6 +213,12 @@ __global__ void __launch_bounds__(Bounds<REGCAP>::kThreads, 1) render_fwd_kernel
         sigma = post_act(p.postact, sraw, dpost);
 #pragma unroll
         for (int k = 0; k < NCOL; ++k) col[k] = sigmoid_fast(raw[k]);
+        if (samples != nullptr) {  // what the backward needs of this sample: colour(s) and the raw density
+          float4 sv = make_float4(col[0], 0.f, 0.f, sraw);
+          if (NCOL > 1) sv.y = col[1];
+          if (NCOL > 2) sv.z = col[2];
+          samples[(size_t)(i - i0) * p.R] = sv;
+        }
       }
       if (use_noise) sigma = fmaf(__ldg(p.noise + (size_t)ray * p.S + i), p.noise_std, sigma);
       const float delta = ((i == p.S - 1) ? kInfinity : __fsub_rn(zw.next, zi)) * rc.dnorm;  // accumulate.py:49-55
@@ -233,7 +281,7 @@ __global__ void __launch_bounds__(Bounds<REGCAP>::kThreads, 1) render_fwd_kernel
     __syncthreads();
     if (active) {
       const size_t plane = (size_t)nseg * p.R;
-      float* dst = p.saved + (size_t)seg * p.R + ray;
+      float* dst = summaries(p) + (size_t)seg * p.R + ray;
       dst[0] = sT[seg * stride + r_in];
 #pragma unroll
       for (int k = 0; k < NV; ++k) dst[(k + 1) * plane] = V[k];
@@ -257,12 +305,11 @@ __global__ void __launch_bounds__(Bounds<REGCAP>::kThreads, 1) render_bwd_kernel
   const int r_in = threadIdx.x % rpc, seg = threadIdx.x / rpc;
   const int ray = blockIdx.x * rpc + r_in;
   const bool active = (seg < nseg) && (ray < p.R);
-  const int L = p.L, i0 = seg * L, i1 = min(i0 + L, p.S);
 
   // load the forward's segment summaries (coalesced over rays) and transpose through shared memory
   if (seg < nseg) {
     const size_t plane = (size_t)nseg * p.R;
-    const float* src = p.saved + (size_t)seg * p.R + ray;
+    const float* src = summaries(p) + (size_t)seg * p.R + ray;
     sT[seg * stride + r_in] = active ? __ldg(src) : 1.f;
 #pragma unroll
     for (int k = 0; k < NV; ++k) sV[(k * nseg + seg) * stride + r_in] = active ? __ldg(src + (k + 1) * plane) : 0.f;
@@ -342,7 +389,11 @@ __global__ void __launch_bounds__(Bounds<REGCAP>::kThreads, 1) render_bwd_kernel
 
   RayCtx rc;
   load_ray(p, ray, rc);
+  int i0, i1;
+  thread_samples(p, rc, seg, i0, i1);
+  if (i0 >= i1) return;
   const float* u_row = p.jitter ? p.jitter + (size_t)ray * p.S : nullptr;
+  const float4* samples = sample_slots(p, seg, ray);
   DepthWalker zw;
   zw.init(p, rc, u_row, i0);
   const bool use_noise = (p.noise_std != 0.f);
@@ -362,15 +413,12 @@ __global__ void __launch_bounds__(Bounds<REGCAP>::kThreads, 1) render_bwd_kernel
     float sigma = 0.f, dpost = 0.f, col[NCOL];
 #pragma unroll
     for (int k = 0; k < NCOL; ++k) col[k] = 0.f;
-    Corners c;
-    unsigned signs = 0u;
     if (in) {
-      make_corners(p, px, py, pz, c);
-      float raw[NCOL];
-      const float sraw = gather_sample<DEG, NCOL>(p, c, Y, raw, signs);
-      sigma = post_act(p.postact, sraw, dpost);
-#pragma unroll
-      for (int k = 0; k < NCOL; ++k) col[k] = sigmoid_fast(raw[k]);
+      const float4 sv = __ldg(samples + (size_t)(i - i0) * p.R);  // colour(s) + raw density stored by the forward
+      col[0] = sv.x;
+      if (NCOL > 1) col[1] = sv.y;
+      if (NCOL > 2) col[2] = sv.z;
+      sigma = post_act(p.postact, sv.w, dpost);
     }
     if (use_noise) sigma = fmaf(__ldg(p.noise + (size_t)ray * p.S + i), p.noise_std, sigma);
     const bool last = (i == p.S - 1);
@@ -396,6 +444,9 @@ __global__ void __launch_bounds__(Bounds<REGCAP>::kThreads, 1) render_bwd_kernel
       any |= (draw[k] != 0.f);
     }
     if (!any) continue;
+    Corners c;
+    make_corners(p, px, py, pz, c);
+    const unsigned signs = (p.preact == kPreAbs) ? corner_signs<DEG, NCOL>(p, c) : 0u;
     float gfe[LT::CV * 4];
 #pragma unroll
     for (int k = 0; k < LT::CV * 4; ++k) gfe[k] = 0.f;
@@ -405,7 +456,7 @@ __global__ void __launch_bounds__(Bounds<REGCAP>::kThreads, 1) render_bwd_kernel
       for (int k = 0; k < LT::K; ++k) gfe[ch * LT::K + k] = draw[ch] * Y[k];
 #pragma unroll
     for (int qn = 0; qn < 8; ++qn) {
-      const float wq = c.w[qn];  // zero only for the padded corners of border cells: those add 0 to a clamped address
+      const float wq = c.w[qn];  // corners beyond the grid land in the zero apron; unpack drops what they receive
       float4* dst = p.grad + (size_t)c.idx[qn] * LT::CV;
       const float gdens = ((signs >> qn) & 1u) ? -dsraw : dsraw;
 #pragma unroll
@@ -463,6 +514,6 @@ cudaError_t launch_render(const KParams& p, int deg, int ncol, int regcap, bool 
 
 int max_threads_per_cta(int regcap) { return regcap <= 64 ? Bounds<64>::kThreads : Bounds<128>::kThreads; }
 
-int saved_floats_per_segment(int ncol) { return ncol + 3; }
+int saved_floats_per_segment(int ncol, int samples_per_segment) { return ncol + 3 + 4 * samples_per_segment; }
 
 }  // namespace voxe

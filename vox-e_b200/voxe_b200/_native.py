@@ -16,7 +16,7 @@ _lock = threading.Lock()
 _lib: Optional[ctypes.CDLL] = None
 
 # ---- enums of include/voxe.h -------------------------------------------------------------------------------
-ABI_VERSION = 5
+ABI_VERSION = 6
 PREACT_IDENTITY, PREACT_ABS = 0, 1
 POSTACT_IDENTITY, POSTACT_RELU, POSTACT_SOFTPLUS = 0, 1, 2
 FLAG_PERTURB, FLAG_AABB_SAMPLING, FLAG_DISPARITY_SAMPLING = 1, 2, 4
@@ -69,6 +69,7 @@ EXPORTS = {
     "voxe_packed_floats": (ctypes.c_int64, [_GD]),
     "voxe_pack_grid": (ctypes.c_int, [_GD, _P, _P, _P, _P]),
     "voxe_unpack_grad": (ctypes.c_int, [_GD, _P, _P, _P, ctypes.c_int, _P]),
+    "voxe_consume_grad": (ctypes.c_int, [_GD, _P, _P, _P, _P]),
     "voxe_adam_step": (ctypes.c_int, [_GD, ctypes.POINTER(VoxeAdamDesc), _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "voxe_saved_floats": (ctypes.c_int64, [_RD, ctypes.c_int64]),
     "voxe_render_fwd": (ctypes.c_int, [_GD, _RD, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, ctypes.c_int64, _P]),
