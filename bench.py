@@ -467,16 +467,20 @@ def e2e_leg(device, rank, world, steps, warmup, dist, deferred=False):
         o_h, d_h, g_h = host[idx % len(host)]
         grid.densities.grad = None
         grid.features.grad = None
-        loss_total = torch.zeros((), device=device)
+        # the step's inputs: rays and upstream gradients of the whole frame, pinned host memory -> device
+        o = o_h.to(device, non_blocking=True)
+        d = d_h.to(device, non_blocking=True)
+        gc = g_h.to(device, non_blocking=True)
+        colours = []
         for s in range(0, R, B):
-            o = o_h[s : s + B].to(device, non_blocking=True)
-            d = d_h[s : s + B].to(device, non_blocking=True)
-            gc = g_h[s : s + B].to(device, non_blocking=True)
-            out = vm.render_rays(Rays(o, d))
-            loss = (out.colour * gc).sum()
-            loss.backward()
-            loss_total += loss.detach()
-            colour_host[s : s + B].copy_(out.colour.detach(), non_blocking=True)
+            out = vm.render_rays(Rays(o[s : s + B], d[s : s + B]))
+            # loss = <colour, G>: the upstream gradient is handed to autograd directly, as the SDS step does
+            # (thre3d_reprs/sd.py:20-34 SpecifyGradient)
+            out.colour.backward(gc[s : s + B])
+            colours.append(out.colour.detach())
+        colour = torch.cat(colours)
+        loss_total = (colour * gc).sum()
+        colour_host.copy_(colour, non_blocking=True)  # the step's result: the rendered frame and the loss
         if deferred:
             if world > 1:
                 dist.all_reduce(grid.render_gradient_accumulator.buffer)  # ONE collective on the packed volume
@@ -501,7 +505,8 @@ def e2e_leg(device, rank, world, steps, warmup, dist, deferred=False):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         elapsed = float(t.item())
     return {"value": world * R * steps / elapsed, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-            "ms_per_step": 1e3 * elapsed / steps, "steps": steps, "api": "VolumetricModel.render_rays + backward, 4096-ray batches"}
+            "ms_per_step": 1e3 * elapsed / steps, "steps": steps, "api": "per 4096-ray batch: VolumetricModel.render_rays(Rays) -> out.colour.backward(dL/dcolour); per frame: "
+            "one pinned H2D copy of rays + upstream gradients, one D2H copy of the rendered colours and the loss"}
 
 
 def fused_step_leg(device, peak):
@@ -677,7 +682,7 @@ def run_ours(args):
             # dram__bytes_read.sum + dram__bytes_write.sum per backward launch from the committed ncu --set full capture
             # (profiles/r1_bwd_kernel_metrics.txt); the grid is L2-resident at 160^3, hence far below the algorithmic bytes
             "traffic": 12.9e6 if args.workload == "cfg2" else None,
-            "peak_source": peak_note, "kernel": "render_bwd_kernel<DEG=0,NCOL=3,L=8>", "us_per_launch": round(bwd_us, 2),
+            "peak_source": peak_note, "kernel": "render_bwd_kernel<DEG=0,NCOL=3>", "us_per_launch": round(bwd_us, 2),
             "algorithmic_bytes_per_launch": round(bwd_bytes), "fwd_kernel": {"us_per_launch": round(fwd_us, 2),
             "achieved": round(fwd_bytes / (fwd_us * 1e-6) / 1e9, 1), "frac": round(fwd_bytes / (fwd_us * 1e-6) / 1e9 / peak, 4)},
             "step": {"achieved": round(step_gbs, 1), "frac": round(step_gbs / peak, 4),  # per GPU (each rank renders its own frame)

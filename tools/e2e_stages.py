@@ -53,25 +53,30 @@ def one_frame(idx):
     o_h, d_h, g_h = host[idx % len(host)]
     grid.densities.grad = None
     grid.features.grad = None
-    loss_total = torch.zeros((), device=dev)
+    t = time.perf_counter()
+    o = o_h.to(dev, non_blocking=True)
+    d = d_h.to(dev, non_blocking=True)
+    gc = g_h.to(dev, non_blocking=True)
+    t = mark("h2d(frame)", t)
+    colours = []
     for s in range(0, R, B):
         t = time.perf_counter()
-        o = o_h[s:s + B].to(dev, non_blocking=True)
-        d = d_h[s:s + B].to(dev, non_blocking=True)
-        gc = g_h[s:s + B].to(dev, non_blocking=True)
-        t = mark("h2d", t)
-        out = vm.render_rays(Rays(o, d))
+        rays = Rays(o[s:s + B], d[s:s + B])
+        gslice = gc[s:s + B]
+        t = mark("slice", t)
+        out = vm.render_rays(rays)
         t = mark("render_rays", t)
-        loss = (out.colour * gc).sum()
-        t = mark("loss", t)
-        loss.backward()
+        out.colour.backward(gslice)
         t = mark("backward", t)
-        loss_total += loss.detach()
-        colour_host[s:s + B].copy_(out.colour.detach(), non_blocking=True)
-        t = mark("d2h", t)
+        colours.append(out.colour.detach())
+        t = mark("collect", t)
+    t = time.perf_counter()
+    colour = torch.cat(colours)
+    loss_total = (colour * gc).sum()
+    colour_host.copy_(colour, non_blocking=True)
     if deferred:
         grid.materialize_render_gradients()
-    t = time.perf_counter()
+    t = mark("frame tail", t)
     v = float(loss_total.item())
     mark("item", t)
     return v

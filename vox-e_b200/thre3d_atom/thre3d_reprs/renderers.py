@@ -117,7 +117,7 @@ def render_sh_voxel_grid(
     spec = _render_spec(render_config, features.shape[-1], attn=False, per_call_sampling_flags=True)
     colour, depth, acc, disparity = fused_render(
         voxel_grid.fused_spec(), spec, densities, features, rays.origins, rays.directions, cache=voxel_grid.packed_cache(),
-        grad_sink=voxel_grid.render_gradient_accumulator,
+        grad_sink=voxel_grid.render_gradient_accumulator, grad_scratch=voxel_grid.render_gradient_scratch(),
     )
     return RenderOut(colour=colour, depth=depth, extra={EXTRA_DISPARITY: disparity, EXTRA_ACCUMULATED_WEIGHTS: acc})
 
@@ -139,5 +139,6 @@ def render_sh_voxel_grid_attn(
     attn, depth, acc, disparity = fused_render(
         voxel_grid.fused_spec(n_features=voxel_grid.attn.shape[-1]), spec, densities, voxel_grid.attn,
         rays.origins, rays.directions, cache=voxel_grid.packed_cache(attn=True),
+        grad_scratch=voxel_grid.render_gradient_scratch(attn=True),
     )
     return RenderOutAttn(attn=attn, depth=depth, extra={EXTRA_DISPARITY: disparity, EXTRA_ACCUMULATED_WEIGHTS: acc})

@@ -125,6 +125,9 @@ class VoxelGrid(Module):
         self._packed = PackedVolumeCache()
         self._packed_attn = PackedVolumeCache()
         self._grad_accumulator: Optional[PackedGradAccumulator] = None  # deferred render gradients (opt-in)
+        # packed gradient volumes the backward kernels scatter into; all-zero between calls (allocated on first use)
+        self._grad_scratch = PackedGradAccumulator()
+        self._grad_scratch_attn = PackedGradAccumulator()
 
     # ------------------------------------------------------------------------------------------------------
     # parameters
@@ -275,6 +278,9 @@ class VoxelGrid(Module):
     @property
     def render_gradient_accumulator(self) -> Optional[PackedGradAccumulator]:
         return self._grad_accumulator
+
+    def render_gradient_scratch(self, attn: bool = False) -> PackedGradAccumulator:
+        return self._grad_scratch_attn if attn else self._grad_scratch
 
     def materialize_render_gradients(self) -> None:
         if self._grad_accumulator is not None:

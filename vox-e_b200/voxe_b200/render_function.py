@@ -1,13 +1,14 @@
-"""Autograd bridge between torch tensors and the C ABI (``voxe_render_fwd`` / ``voxe_render_bwd``).
+"""Host side of one render call: descriptors, packed-volume cache, gradient volumes, and the hand-off to the C++
+autograd node (``voxe_b200._voxe_torch``, csrc/voxe_torch.cpp) that calls ``voxe_render_fwd`` / ``voxe_render_bwd``.
 
 ``fused_render`` is what ``thre3d_atom.thre3d_reprs.renderers.render_sh_voxel_grid`` calls: it replaces the reference's
 sampler -> point processor -> accumulator chain (render_interface.py:140-171) and its autograd graph with one
-forward kernel and one backward kernel.  The backward recomputes the forward per ray, so nothing of size
-O(rays x samples) is kept between the two (the reference retains ~35 such tensors).
+forward kernel and one backward kernel linked by a 16-byte-per-sample workspace (the reference retains ~35 floats per
+sample in autograd).
 
-Gradients w.r.t. ``densities`` [X,Y,Z,1] and ``features`` [X,Y,Z,F] are returned as dense tensors shaped like the
-parameters, as autograd would have produced.  Rays never receive gradients (they never require them upstream:
-``cast_rays`` builds them from poses, misc.py:30-50).
+Gradients w.r.t. ``densities`` [X,Y,Z,1] and ``features`` [X,Y,Z,F] reach ``.grad`` as dense tensors shaped like the
+parameters, as autograd would have produced (see ``DIRECT_GRAD_ACCUMULATION`` for how).  Rays never receive gradients
+(they never require them upstream: ``cast_rays`` builds them from poses, misc.py:30-50).
 """
 from __future__ import annotations
 
@@ -20,6 +21,26 @@ import torch
 from torch import Tensor
 
 from voxe_b200 import _native as nat
+
+_bridge_module = None
+
+
+def bridge():
+    """The C++ torch bridge (autograd node).  Like the C-ABI library it has no fallback: a missing build is an error."""
+    global _bridge_module
+    if _bridge_module is None:
+        nat.load_library()  # the bridge links against libvoxe_sm100a.so; surface a missing / stale library first
+        try:
+            from voxe_b200 import _voxe_torch
+        except ImportError as exc:
+            raise nat.NativeLibraryError(
+                f"cannot import voxe_b200._voxe_torch ({exc}): build it with `make -C vox-e_b200/csrc` "
+                "(or `python -c 'import __graft_entry__ as g; g.build()'`).  There is no Python fallback for the render path."
+            ) from exc
+        if _voxe_torch.abi_version() != nat.ABI_VERSION:
+            raise nat.NativeLibraryError("voxe_b200._voxe_torch was built against another ABI version; rebuild")
+        _bridge_module = _voxe_torch
+    return _bridge_module
 
 
 @dataclasses.dataclass(frozen=True)
@@ -54,6 +75,10 @@ class FusedGridSpec:
         d.preact, d.postact = int(self.preact), int(self.postact)
         return d
 
+    @functools.lru_cache(maxsize=64)
+    def native_bytes(self) -> bytes:
+        return bytes(self.to_native())
+
 
 @dataclasses.dataclass(frozen=True)
 class FusedRenderSpec:
@@ -74,12 +99,25 @@ class FusedRenderSpec:
         r.flags, r.sh_degree, r.n_colour, r.noise_std = int(self.flags), int(self.sh_degree), int(self.n_colour), float(self.noise_std)
         return r
 
+    @functools.lru_cache(maxsize=256)
+    def native_bytes(self) -> bytes:
+        return bytes(self.to_native())
+
 
 # The reference draws ``torch.randn(R, S)`` for the density noise on EVERY call, even when
 # stochastic_density_noise_std == 0 and the draw is multiplied away (accumulate.py:59-62).  Skipping that draw changes
 # nothing in one call's result but leaves the global generator in a different state for the next call.  Set this to True
 # to consume the generator exactly like the reference (one extra RNG kernel per call) when replaying its seeded runs.
 STRICT_REFERENCE_RNG = False
+
+# How the voxel gradients of a plain ``loss.backward()`` reach ``.grad``.  The backward kernel scatters into the grid's
+# packed gradient volume.  True (default): the autograd node then adds the touched voxels straight into
+# ``_densities.grad`` / ``_features.grad`` (creating zero gradients on first use) with one sparse pass
+# (``voxe_consume_grad``) -- AccumulateGrad's job without its three full-grid passes per call.  The node falls back to
+# returning dense gradients to autograd by itself whenever that would not be equivalent: ``torch.autograd.grad`` /
+# ``backward(inputs=...)``, parameters with tensor or post-accumulate hooks, non-leaf or oddly laid out ``.grad``.
+# False: always return dense gradients to autograd.
+DIRECT_GRAD_ACCUMULATION = True
 
 
 def _ptr(t: Optional[Tensor]) -> Optional[int]:
@@ -164,7 +202,15 @@ class PackedGradAccumulator:
 
     def __init__(self) -> None:
         self.buffer: Optional[Tensor] = None
-        self.dirty = False
+        self.flag = torch.zeros(1, dtype=torch.int64)  # set by the C++ backward node when it scatters into the buffer
+
+    @property
+    def dirty(self) -> bool:
+        return bool(self.flag[0] != 0)
+
+    @dirty.setter
+    def dirty(self, value: bool) -> None:
+        self.flag[0] = 1 if value else 0
 
     def get(self, like: Tensor) -> Tensor:
         if self.buffer is None or self.buffer.numel() != like.numel() or self.buffer.device != like.device:
@@ -204,84 +250,14 @@ class PackedGradAccumulator:
         self.dirty = False
 
 
-class _FusedRender(torch.autograd.Function):
-    """colour, depth, acc, disparity = render(densities, features | rays, jitter, noise)."""
-
-    @staticmethod
-    def forward(ctx, densities, features, packed, rays_o, rays_d, jitter, noise, gspec: FusedGridSpec, rspec: FusedRenderSpec,
-                sink: Optional[PackedGradAccumulator] = None):
-        dev = _require_cuda(packed, rays_o, rays_d)
-        lib = nat.load_library()
-        R = rays_o.shape[0]
-        colour = torch.empty((R, rspec.n_colour), dtype=torch.float32, device=dev)
-        depth = torch.empty((R, 1), dtype=torch.float32, device=dev)
-        acc = torch.empty((R, 1), dtype=torch.float32, device=dev)
-        disp = torch.empty((R, 1), dtype=torch.float32, device=dev)
-        gd, rd = gspec.to_native(), rspec.to_native()
-        # segment summaries linking this call to its backward: < 1 float per sample instead of autograd's ~35
-        need_grad = bool(ctx.needs_input_grad[0] or ctx.needs_input_grad[1])
-        saved = torch.empty(int(lib.voxe_saved_floats(rd, R)), dtype=torch.float32, device=dev) if need_grad else None
-        with torch.cuda.device(dev):
-            nat.check(
-                lib.voxe_render_fwd(gd, rd, packed.data_ptr(), rays_o.data_ptr(), rays_d.data_ptr(), _ptr(jitter), _ptr(noise),
-                                    colour.data_ptr(), depth.data_ptr(), acc.data_ptr(), disp.data_ptr(), _ptr(saved), R,
-                                    _stream_ptr(dev)),
-                "voxe_render_fwd",
-            )
-        ctx.set_materialize_grads(False)
-        ctx.gspec, ctx.rspec, ctx.sink = gspec, rspec, sink
-        ctx.save_for_backward(densities, features, packed, rays_o, rays_d, jitter, noise, saved)
-        return colour, depth, acc, disp
-
-    @staticmethod
-    def backward(ctx, g_colour, g_depth, g_acc, g_disp):
-        densities, features, packed, rays_o, rays_d, jitter, noise, saved = ctx.saved_tensors
-        need_d, need_f = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
-        none10 = (None,) * 10
-        if not (need_d or need_f):
-            return none10
-        gspec, rspec = ctx.gspec, ctx.rspec
-        dev = packed.device
-        lib = nat.load_library()
-        R = rays_o.shape[0]
-        if all(g is None for g in (g_colour, g_depth, g_acc, g_disp)):
-            zeros = lambda t, need: torch.zeros_like(t, memory_format=torch.contiguous_format) if need else None  # noqa: E731
-            return (zeros(densities, need_d), zeros(features, need_f)) + (None,) * 8
-        if g_colour is None:
-            g_colour = torch.zeros((R, rspec.n_colour), dtype=torch.float32, device=dev)
-        gs = [None if g is None else g.contiguous().float() for g in (g_colour, g_depth, g_acc, g_disp)]
-        gd, rd = gspec.to_native(), rspec.to_native()
-        sink = ctx.sink
-        if sink is not None:  # deferred gradients: scatter into the grid's persistent volume, hand autograd nothing
-            target = sink.get(packed)
-            with torch.cuda.device(dev):
-                nat.check(
-                    lib.voxe_render_bwd(gd, rd, packed.data_ptr(), rays_o.data_ptr(), rays_d.data_ptr(), _ptr(jitter), _ptr(noise),
-                                        saved.data_ptr(), _ptr(gs[0]), _ptr(gs[1]), _ptr(gs[2]), _ptr(gs[3]), target.data_ptr(), R,
-                                        _stream_ptr(dev)),
-                    "voxe_render_bwd",
-                )
-            sink.dirty = True
-            return none10
-        # fully overwritten by voxe_unpack_grad(accumulate=0): no zero-fill needed
-        d_dens = torch.empty_like(densities, memory_format=torch.contiguous_format) if need_d else None
-        d_feat = torch.empty_like(features, memory_format=torch.contiguous_format) if need_f else None
-        packed_grad = torch.zeros_like(packed)
-        with torch.cuda.device(dev):
-            s = _stream_ptr(dev)
-            nat.check(
-                lib.voxe_render_bwd(gd, rd, packed.data_ptr(), rays_o.data_ptr(), rays_d.data_ptr(), _ptr(jitter), _ptr(noise),
-                                    saved.data_ptr(), _ptr(gs[0]), _ptr(gs[1]), _ptr(gs[2]), _ptr(gs[3]), packed_grad.data_ptr(), R, s),
-                "voxe_render_bwd",
-            )
-            nat.check(lib.voxe_unpack_grad(gd, packed_grad.data_ptr(), _ptr(d_dens), _ptr(d_feat), 0, s), "voxe_unpack_grad")
-        return (d_dens, d_feat) + (None,) * 8
-
-
 def _prep_rays(rays_o: Tensor, rays_d: Tensor) -> Tuple[Tensor, Tensor]:
     assert rays_o.dim() == 2 and rays_d.dim() == 2, "Please note that the RENDER interface only works with FLAT RAYS!"
     assert rays_o.shape == rays_d.shape and rays_o.shape[-1] == 3
-    return rays_o.detach().float().contiguous(), rays_d.detach().float().contiguous()
+    if rays_o.dtype != torch.float32:
+        rays_o = rays_o.float()
+    if rays_d.dtype != torch.float32:
+        rays_d = rays_d.float()
+    return rays_o, rays_d
 
 
 def fused_render(
@@ -296,6 +272,7 @@ def fused_render(
     noise: Optional[Tensor] = None,
     generator: Optional[torch.Generator] = None,
     grad_sink: Optional[PackedGradAccumulator] = None,
+    grad_scratch: Optional[PackedGradAccumulator] = None,
 ) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
     """Render flat rays through the fused kernels.  Returns (colour [R,C], depth [R,1], acc [R,1], disparity [R,1]).
 
@@ -305,27 +282,26 @@ def fused_render(
     dev = _require_cuda(densities, features, rays_o, rays_d)
     rays_o, rays_d = _prep_rays(rays_o, rays_d)
     R, S = rays_o.shape[0], rspec.num_samples
-    if rspec.flags & nat.FLAG_PERTURB:
-        if jitter is None:
-            jitter = torch.rand(R, S, dtype=torch.float32, device=dev, generator=generator)
+    if jitter is not None and rspec.flags & nat.FLAG_PERTURB:
         assert jitter.shape == (R, S)
-        jitter = jitter.detach().float().contiguous()
-    else:
-        jitter = None
-    if rspec.noise_std != 0.0:
-        if noise is None:
-            noise = torch.randn(R, S, dtype=torch.float32, device=dev, generator=generator)
+    if noise is not None and rspec.noise_std != 0.0:
         assert noise.shape == (R, S)
-        noise = noise.detach().float().contiguous()
-    else:
-        noise = None
-        if STRICT_REFERENCE_RNG:
-            torch.randn(R, S, dtype=torch.float32, device=dev, generator=generator)  # drawn and discarded, as upstream
+    ext = bridge()
     packed = (cache or PackedVolumeCache()).get(gspec, densities, features)
     if R == 0:
         z = torch.zeros((0, 1), dtype=torch.float32, device=dev)
         return torch.zeros((0, rspec.n_colour), dtype=torch.float32, device=dev), z, z.clone(), z.clone()
-    return _FusedRender.apply(densities, features, packed, rays_o, rays_d, jitter, noise, gspec, rspec, grad_sink)
+    volume = flag = None
+    mode = ext.MODE_DENSE
+    if torch.is_grad_enabled() and (densities.requires_grad or features.requires_grad):
+        if grad_sink is not None:  # deferred gradients (opt-in): leave them in the grid's persistent volume
+            volume, flag, mode = grad_sink.get(packed), grad_sink.flag, ext.MODE_SINK
+        elif grad_scratch is not None:  # persistent all-zero-between-calls volume: no allocation / zero-fill per call
+            volume = grad_scratch.get(packed)
+            mode = ext.MODE_DIRECT if DIRECT_GRAD_ACCUMULATION else ext.MODE_DENSE
+    colour, depth, acc, disparity = ext.render(densities, features, packed, rays_o, rays_d, jitter, noise, volume, flag,
+                                               gspec.native_bytes(), rspec.native_bytes(), mode, STRICT_REFERENCE_RNG, generator)
+    return colour, depth, acc, disparity
 
 
 def fused_render_attn(*args, **kwargs):
