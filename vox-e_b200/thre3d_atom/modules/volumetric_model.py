@@ -75,7 +75,9 @@ class VolumetricModel:
     @staticmethod
     def _update_render_config(render_config: RenderConfig, update_dict: Dict[str, Any]) -> RenderConfig:
         """A private copy of the config with ``update_dict`` applied; the stored config is never touched."""
-        updated = copy.deepcopy(render_config) if update_dict else copy.copy(render_config)
+        if not update_dict:
+            return render_config  # render procedures never mutate the config they are handed
+        updated = copy.deepcopy(render_config)
         for field, value in update_dict.items():
             if not hasattr(updated, field):
                 raise ValueError(f"Unknown render configuration field {field} requested for overriding :(")

@@ -63,7 +63,25 @@ def _sh_degree_of(num_feature_channels: int, num_colour_channels: int) -> int:
     return degree
 
 
+_SPEC_CACHE = {}
+
+
 def _render_spec(config: SHVoxGridRenderConfig, num_feature_channels: int, attn: bool, per_call_sampling_flags: bool) -> FusedRenderSpec:
+    """The kernel-side description of ``config`` (configs are mutable and copied per call, so the translation is cached on
+    the field values, not on the object)."""
+    near, far = config.camera_bounds
+    key = (config.density2occupancy, config.radiance_hdr_tone_map, config.perturb_sampled_points, config.optimized_sampling,
+           config.linear_disparity_sampling, config.white_bkgd, config.render_diffuse, config.num_samples_per_ray, near, far,
+           config.stochastic_density_noise_std, num_feature_channels, attn, per_call_sampling_flags)
+    spec = _SPEC_CACHE.get(key)
+    if spec is None:
+        spec = _build_render_spec(config, num_feature_channels, attn, per_call_sampling_flags)
+        if len(_SPEC_CACHE) < 4096:
+            _SPEC_CACHE[key] = spec
+    return spec
+
+
+def _build_render_spec(config: SHVoxGridRenderConfig, num_feature_channels: int, attn: bool, per_call_sampling_flags: bool) -> FusedRenderSpec:
     if config.density2occupancy is not density2occupancy_pb:
         raise NotImplementedError(
             f"density2occupancy={config.density2occupancy!r}: the fused kernels implement density2occupancy_pb only"

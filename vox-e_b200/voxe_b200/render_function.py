@@ -58,8 +58,18 @@ class FusedGridSpec:
     def channels(self) -> int:
         return ((self.n_features + 1 + 3) // 4) * 4
 
-    @functools.lru_cache(maxsize=64)  # frozen + hashable: the ctypes struct is built once per distinct grid description
+    def __post_init__(self) -> None:  # the ctypes struct and its bytes are built once per description object
+        native = self._build_native()
+        object.__setattr__(self, "_native", native)
+        object.__setattr__(self, "_native_bytes", bytes(native))
+
     def to_native(self) -> nat.VoxeGridDesc:
+        return self._native
+
+    def native_bytes(self) -> bytes:
+        return self._native_bytes
+
+    def _build_native(self) -> nat.VoxeGridDesc:
         d = nat.VoxeGridDesc()
         for a in range(3):
             lo32, hi32 = np.float32(self.aabb[a][0]), np.float32(self.aabb[a][1])
@@ -75,10 +85,6 @@ class FusedGridSpec:
         d.preact, d.postact = int(self.preact), int(self.postact)
         return d
 
-    @functools.lru_cache(maxsize=64)
-    def native_bytes(self) -> bytes:
-        return bytes(self.to_native())
-
 
 @dataclasses.dataclass(frozen=True)
 class FusedRenderSpec:
@@ -92,16 +98,22 @@ class FusedRenderSpec:
     n_colour: int
     noise_std: float = 0.0
 
-    @functools.lru_cache(maxsize=256)
+    def __post_init__(self) -> None:
+        native = self._build_native()
+        object.__setattr__(self, "_native", native)
+        object.__setattr__(self, "_native_bytes", bytes(native))
+
     def to_native(self) -> nat.VoxeRenderDesc:
+        return self._native
+
+    def native_bytes(self) -> bytes:
+        return self._native_bytes
+
+    def _build_native(self) -> nat.VoxeRenderDesc:
         r = nat.VoxeRenderDesc()
         r.num_samples, r.near, r.far = int(self.num_samples), float(self.near), float(self.far)
         r.flags, r.sh_degree, r.n_colour, r.noise_std = int(self.flags), int(self.sh_degree), int(self.n_colour), float(self.noise_std)
         return r
-
-    @functools.lru_cache(maxsize=256)
-    def native_bytes(self) -> bytes:
-        return bytes(self.to_native())
 
 
 # The reference draws ``torch.randn(R, S)`` for the density noise on EVERY call, even when
@@ -184,7 +196,7 @@ class PackedVolumeCache:
 
     def get(self, spec: FusedGridSpec, densities: Tensor, features: Tensor) -> Tensor:
         key = (densities.data_ptr(), densities._version, features.data_ptr(), features._version, densities.device, spec)
-        if key != self._key or self._packed is None:
+        if self._packed is None or key != self._key:
             self._packed = pack_volume(spec, densities, features, out=self._packed)
             self._key = key
         return self._packed
@@ -279,7 +291,11 @@ def fused_render(
     ``jitter`` / ``noise`` default to fresh ``torch.rand`` / ``torch.randn`` draws on the rays' device -- the same
     generator, shapes and order as sample.py:63 and accumulate.py:59-62 -- when the render spec needs them.
     """
-    dev = _require_cuda(densities, features, rays_o, rays_d)
+    dev = densities.device
+    if dev.type != "cuda" or rays_o.device != dev:
+        _require_cuda(densities, features, rays_o, rays_d)  # raises the explanatory error
+    if densities.dtype != torch.float32 or features.dtype != torch.float32:
+        raise TypeError(f"the render path computes in fp32 (got {densities.dtype} / {features.dtype})")
     rays_o, rays_d = _prep_rays(rays_o, rays_d)
     R, S = rays_o.shape[0], rspec.num_samples
     if jitter is not None and rspec.flags & nat.FLAG_PERTURB:
