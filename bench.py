@@ -279,7 +279,7 @@ class DeviceBench:
 
     N_GRID_COPIES = 3  # rotating copies: 3 x 65.5 MB of grid + 65.5 MB of gradients >> 126 MB L2
 
-    def __init__(self, device, rank, world, count_s_in=True, n_lanes=1):
+    def __init__(self, device, rank, world, count_s_in=True, n_lanes=1, kernel_jitter=True):
         from voxe_b200 import _native as nat
         from voxe_b200.render_function import FusedGridSpec, FusedRenderSpec, pack_volume
 
@@ -293,7 +293,9 @@ class DeviceBench:
                                    postact=nat.POSTACT_RELU if WL["postact"] == "relu" else nat.POSTACT_SOFTPLUS)
         flags = nat.FLAG_WHITE_BKGD | (nat.FLAG_PERTURB if WL["perturb"] else 0)
         self.rspec = FusedRenderSpec(num_samples=WL["S"], near=WL["near"], far=WL["far"], flags=flags, sh_degree=WL["sh_degree"], n_colour=3)
-        self.gd, self.rd = self.gspec.to_native(), self.rspec.to_native()
+        self.gd = self.gspec.to_native()
+        self.rd = nat.VoxeRenderDesc.from_buffer_copy(self.rspec.native_bytes())  # private copy: rng_offset changes per launch
+        self.kernel_jitter = kernel_jitter and WL["perturb"]
         self.dens, self.feat = dens, feat
         self.packed = [pack_volume(self.gspec, dens, feat) for _ in range(self.N_GRID_COPIES)]
         self.packed_grad = torch.zeros_like(self.packed[0])
@@ -326,18 +328,28 @@ class DeviceBench:
     def _stream(self):
         return torch.cuda.current_stream(self.device).cuda_stream
 
+    def _jitter_arg(self, pose, b0):
+        """Explicit torch-drawn [R,S] jitter buffer, or None + a per-batch Philox offset for the in-kernel draws (the
+        descriptor is read at launch time, so forward and backward of a batch see the same offset)."""
+        if not WL["perturb"]:
+            return None
+        if self.kernel_jitter:
+            self.rd.rng_seed, self.rd.rng_offset = WL["seed"], (pose << 20) | b0
+            return None
+        return self.jitter.data_ptr()
+
     def _fwd(self, pose, copy, b0, b1, saved):
         o, d = self.rays[pose]
         self.nat.check(self.lib.voxe_render_fwd(
             self.gd, self.rd, self.packed[copy].data_ptr(), o[b0:b1].data_ptr(), d[b0:b1].data_ptr(),
-            self.jitter.data_ptr() if WL["perturb"] else None, None, self.colour[b0:b1].data_ptr(), self.depth[b0:b1].data_ptr(),
+            self._jitter_arg(pose, b0), None, self.colour[b0:b1].data_ptr(), self.depth[b0:b1].data_ptr(),
             self.acc[b0:b1].data_ptr(), self.disp[b0:b1].data_ptr(), saved.data_ptr(), b1 - b0, self._stream()), "voxe_render_fwd")
 
     def _bwd(self, pose, copy, b0, b1, saved):
         o, d = self.rays[pose]
         self.nat.check(self.lib.voxe_render_bwd(
             self.gd, self.rd, self.packed[copy].data_ptr(), o[b0:b1].data_ptr(), d[b0:b1].data_ptr(),
-            self.jitter.data_ptr() if WL["perturb"] else None, None, saved.data_ptr(), self.G[b0:b1].data_ptr(), None, None, None,
+            self._jitter_arg(pose, b0), None, saved.data_ptr(), self.G[b0:b1].data_ptr(), None, None, None,
             self.packed_grad.data_ptr(), b1 - b0, self._stream()), "voxe_render_bwd")
 
     def unpack(self):
@@ -361,7 +373,7 @@ class DeviceBench:
                 else:
                     self._bwd(pose, copy, b0, b1, saved)
             return
-        draw = WL["perturb"] and refresh_jitter
+        draw = WL["perturb"] and refresh_jitter and not self.kernel_jitter
         self.packed_grad.zero_()
         n = self.n_lanes
         lanes = [main] + self.lane_streams[: n - 1]
@@ -588,7 +600,8 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=device)
     torch.manual_seed(WL["seed"] + rank)
 
-    bench = DeviceBench(device, rank, world, count_s_in=not (args.ncu or args.sweep), n_lanes=args.lanes)
+    bench = DeviceBench(device, rank, world, count_s_in=not (args.ncu or args.sweep), n_lanes=args.lanes,
+                        kernel_jitter=args.jitter == "kernel")
     barrier = (lambda: dist.barrier()) if world > 1 else None
 
     if args.ncu:  # profiler mode: eager launches of whole frames, nothing else (numbers printed here are NOT bench values)
@@ -744,6 +757,8 @@ def main():
     ap.add_argument("--workload", choices=["cfg2", "cfg3", "cfg4", "cfg5"], default="cfg2",
                     help="cfg2 is the headline (the line the driver reads); the others are recorded in DESIGN.md")
     ap.add_argument("--lanes", type=int, default=3, help="ray batches in flight within a frame (streams)")
+    ap.add_argument("--jitter", choices=["kernel", "buffer"], default="kernel",
+                    help="stratified jitter of the device leg: generated inside the kernels (Philox) or torch-drawn [R,S] buffers")
     ap.add_argument("--sweep", type=str, default="", help="tuning sweep: 'L,rpc,cap;L,rpc,cap;...'")
     ap.add_argument("--tune", type=str, default="", help="L,rpc,regcap launch-shape override for tuning runs")
     args = ap.parse_args()

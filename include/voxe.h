@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define VOXE_ABI_VERSION 6
+#define VOXE_ABI_VERSION 7
 
 #if defined(__GNUC__)
 #define VOXE_API __attribute__((visibility("default")))
@@ -95,6 +95,8 @@ typedef struct VoxeRenderDesc {
   int32_t sh_degree;      /* 0..3                                                                           */
   int32_t n_colour;       /* 3 (RGB) or 1 (attn)                                                            */
   float noise_std;        /* stochastic_density_noise_std; != 0 needs `noise` [R,S] (standard normal)       */
+  uint64_t rng_seed;      /* VOXE_FLAG_PERTURB with jitter == NULL: the U[0,1) draws of sample.py:63 are generated */
+  uint64_t rng_offset;    /* inside the kernels, Philox4x32-7 keyed by rng_seed, counter (sample/4, ray, rng_offset) */
 } VoxeRenderDesc;
 
 VOXE_API int voxe_abi_version(void);
@@ -130,7 +132,8 @@ VOXE_API int64_t voxe_saved_floats(const VoxeRenderDesc* render, int64_t num_ray
 /* Forward render of R rays.
  *   packed   voxe_packed_floats() floats from voxe_pack_grid
  *   rays_o/d [R,3]       origins / (un-normalised) directions
- *   jitter   [R,S] or NULL   the U[0,1) draws of sample.py:63 (required with VOXE_FLAG_PERTURB)
+ *   jitter   [R,S] or NULL   the U[0,1) draws of sample.py:63; NULL with VOXE_FLAG_PERTURB: drawn in-kernel from
+ *                            (render->rng_seed, render->rng_offset) -- pass the same pair to the backward call
  *   noise    [R,S] or NULL   the N(0,1) draws of accumulate.py:59-62 (required when noise_std != 0)
  *   colour   [R,n_colour], depth [R], acc [R], disparity [R]   outputs (disparity may be NULL)
  *   saved    voxe_saved_floats() floats, or NULL when no backward will follow (inference) */
@@ -148,6 +151,9 @@ VOXE_API int voxe_render_bwd(const VoxeGridDesc* grid, const VoxeRenderDesc* ren
                     const float* rays_o, const float* rays_d, const float* jitter, const float* noise,
                     const float* saved, const float* g_colour, const float* g_depth, const float* g_acc,
                     const float* g_disp, float* packed_grad, int64_t num_rays, voxe_stream_t stream);
+
+/* The jitter the kernels generate for (render->rng_seed, render->rng_offset): out[R, S], for tests and replays. */
+VOXE_API int voxe_jitter_fill(const VoxeRenderDesc* render, float* out, int64_t num_rays, voxe_stream_t stream);
 
 /* Sparse hand-over of a packed gradient volume: every non-zero 16-byte vector of `packed_grad` is ADDED into
  * d_densities[X,Y,Z,1] / d_features[X,Y,Z,F] (either may be NULL) and then cleared, so that `packed_grad` is all-zero

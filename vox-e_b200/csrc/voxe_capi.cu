@@ -56,8 +56,7 @@ int check_render(const VoxeGridDesc* g, const VoxeRenderDesc* r, const float* ji
   const int k = (r->sh_degree + 1) * (r->sh_degree + 1);
   if (g->n_features != r->n_colour * k)
     return fail(VOXE_ERR_INVALID_ARGUMENT, "n_features %d does not match n_colour*(deg+1)^2 = %d", g->n_features, r->n_colour * k);
-  if ((r->flags & VOXE_FLAG_PERTURB) && !jitter)
-    return fail(VOXE_ERR_INVALID_ARGUMENT, "VOXE_FLAG_PERTURB needs the jitter buffer [R,S]");
+  (void)jitter;  // NULL with VOXE_FLAG_PERTURB: in-kernel draws from (rng_seed, rng_offset)
   if (r->noise_std != 0.f && !noise) return fail(VOXE_ERR_INVALID_ARGUMENT, "noise_std != 0 needs the noise buffer [R,S]");
   return VOXE_OK;
 }
@@ -106,6 +105,8 @@ int fill_params(const VoxeGridDesc* g, const VoxeRenderDesc* r, int64_t R, voxe:
   p.far = r->far;
   p.dscale = g->density_scale;
   p.noise_std = r->noise_std;
+  p.rng_seed = r->rng_seed;
+  p.rng_offset = r->rng_offset;
   p.lin_step = 1.0f / (float)(r->num_samples - 1);
   p.flags = r->flags;
   p.preact = g->preact;
@@ -169,6 +170,17 @@ int voxe_unpack_grad(const VoxeGridDesc* grid, const float* packed_grad, float* 
   cudaError_t e = voxe::launch_unpack_grad(packed_grad, d_densities, d_features, grid->dims, grid->n_features,
                                            grid->channels, accumulate != 0, (cudaStream_t)stream);
   if (e != cudaSuccess) return cuda_fail(e, "voxe_unpack_grad launch");
+  g_launches.fetch_add(1);
+  return VOXE_OK;
+}
+
+int voxe_jitter_fill(const VoxeRenderDesc* render, float* out, int64_t num_rays, voxe_stream_t stream) {
+  if (!render || render->num_samples < 1 || !out || num_rays < 0 || num_rays > 0x7fffffff)
+    return fail(VOXE_ERR_INVALID_ARGUMENT, "voxe_jitter_fill: bad arguments");
+  if (num_rays == 0) return VOXE_OK;
+  cudaError_t e = voxe::launch_jitter_fill((int)num_rays, render->num_samples, render->rng_seed, render->rng_offset, out,
+                                           (cudaStream_t)stream);
+  if (e != cudaSuccess) return cuda_fail(e, "voxe_jitter_fill launch");
   g_launches.fetch_add(1);
   return VOXE_OK;
 }

@@ -44,6 +44,7 @@ struct KParams {
   float near, far, dscale, noise_std, lin_step;
   int flags, preact, postact;
   int rpc, nseg, L;  // rays per CTA, sample segments per ray, samples per segment (threads = rpc * nseg -> x32)
+  unsigned long long rng_seed, rng_offset;  // in-kernel jitter (kPerturb with jitter == nullptr)
   float* saved;      // workspace written by the forward / read by the backward (or null): [nseg*L][R] float4 sample
                      // vectors, then [NCOL+3][nseg][R] segment summaries (16-byte aligned)
 };
@@ -285,6 +286,48 @@ __device__ __forceinline__ void sample_range(const KParams& p, const RayCtx& rc,
   if (b < a) b = a;
 }
 
+// Philox4x32 with 7 rounds (Salmon et al., "Parallel random numbers: as easy as 1, 2, 3": Crush-resistant from 7 rounds).
+__device__ __forceinline__ uint4 philox4x32_7(uint4 ctr, uint2 key) {
+#pragma unroll
+  for (int r = 0; r < 7; ++r) {
+    const unsigned hi0 = __umulhi(0xD2511F53u, ctr.x), lo0 = 0xD2511F53u * ctr.x;
+    const unsigned hi1 = __umulhi(0xCD9E8D57u, ctr.z), lo1 = 0xCD9E8D57u * ctr.z;
+    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+    key.x += 0x9E3779B9u;
+    key.y += 0xBB67AE85u;
+  }
+  return ctr;
+}
+
+// Stratified-jitter draws u[ray][i] in [0, 1): either the caller's [R,S] buffer (torch.rand, sample.py:63) or generated
+// here -- one Philox block per 4 consecutive samples of a ray, 24 mantissa bits per draw like torch's uniform.  The
+// kernels walk i upwards, so the last block is kept.  Forward and backward regenerate identical values.
+struct JitterSource {
+  const float* row;
+  unsigned ray;
+  int blk_id;
+  uint4 blk;
+
+  __device__ __forceinline__ void init(const KParams& p, int ray_index) {
+    row = p.jitter ? p.jitter + (size_t)ray_index * p.S : nullptr;
+    ray = (unsigned)ray_index;
+    blk_id = -1;
+    blk = make_uint4(0u, 0u, 0u, 0u);
+  }
+  __device__ __forceinline__ float at(const KParams& p, int i) {
+    if (row != nullptr) return __ldg(row + i);
+    const int b = i >> 2;
+    if (b != blk_id) {
+      blk = philox4x32_7(make_uint4((unsigned)b, ray, (unsigned)p.rng_offset, (unsigned)(p.rng_offset >> 32)),
+                         make_uint2((unsigned)p.rng_seed, (unsigned)(p.rng_seed >> 32)));
+      blk_id = b;
+    }
+    const int k = i & 3;
+    const unsigned x = (k == 0) ? blk.x : (k == 1) ? blk.y : (k == 2) ? blk.z : blk.w;
+    return (float)(x >> 8) * (1.0f / 16777216.0f);
+  }
+};
+
 // Rolling evaluation of the (optionally jittered) sample depths along one ray: `cur` is the depth of sample i,
 // `next` the depth of sample i+1 (it closes the interval delta_i).  Stratified jitter follows sample.py:57-64:
 // z'_i = lower_i + (upper_i - lower_i) * u_i with lower/upper the mid-points to the neighbouring plain depths.
@@ -301,13 +344,13 @@ struct DepthWalker {
     const float upper = (i >= p.S - 1) ? mid : __fmul_rn(0.5f, __fadd_rn(hi, mid));
     return __fadd_rn(lower, __fmul_rn(__fsub_rn(upper, lower), u));
   }
-  __device__ __forceinline__ void init(const KParams& p, const RayCtx& rc, const float* u_row, int i) {
+  __device__ __forceinline__ void init(const KParams& p, const RayCtx& rc, JitterSource& u, int i) {
     b = plain(p, rc, i);
     c = plain(p, rc, i + 1);
     if (p.flags & kPerturb) {
-      const float u0 = __ldg(u_row + min(i, p.S - 1));
-      const float u1 = __ldg(u_row + min(i + 1, p.S - 1));
-      u_pre = __ldg(u_row + min(i + 2, p.S - 1));
+      const float u0 = u.at(p, min(i, p.S - 1));
+      const float u1 = u.at(p, min(i + 1, p.S - 1));
+      u_pre = u.at(p, min(i + 2, p.S - 1));
       a = plain(p, rc, i - 1);
       d = plain(p, rc, i + 2);
       cur = jittered(p, a, b, c, i, u0);
@@ -318,7 +361,7 @@ struct DepthWalker {
     }
   }
   // step from sample i to sample i+1
-  __device__ __forceinline__ void advance(const KParams& p, const RayCtx& rc, const float* u_row, int i) {
+  __device__ __forceinline__ void advance(const KParams& p, const RayCtx& rc, JitterSource& u, int i) {
     cur = next;
     if (p.flags & kPerturb) {
       a = b;
@@ -326,7 +369,7 @@ struct DepthWalker {
       c = d;
       d = plain(p, rc, i + 3);
       next = jittered(p, b, c, d, i + 2, u_pre);
-      u_pre = __ldg(u_row + min(i + 3, p.S - 1));
+      u_pre = u.at(p, min(i + 3, p.S - 1));
     } else {
       next = plain(p, rc, i + 2);
     }

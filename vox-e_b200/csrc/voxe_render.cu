@@ -185,7 +185,8 @@ __global__ void __launch_bounds__(Bounds<REGCAP>::kThreads, 1) render_fwd_kernel
     load_ray(p, ray, rc);
     int i0, i1;
     thread_samples(p, rc, seg, i0, i1);
-    const float* u_row = p.jitter ? p.jitter + (size_t)ray * p.S : nullptr;
+    JitterSource u_row;
+    u_row.init(p, ray);
     float4* samples = p.saved ? sample_slots(p, seg, ray) : nullptr;
     DepthWalker zw;
     if (i0 < i1) zw.init(p, rc, u_row, i0);
@@ -392,7 +393,8 @@ __global__ void __launch_bounds__(Bounds<REGCAP>::kThreads, 1) render_bwd_kernel
   int i0, i1;
   thread_samples(p, rc, seg, i0, i1);
   if (i0 >= i1) return;
-  const float* u_row = p.jitter ? p.jitter + (size_t)ray * p.S : nullptr;
+  JitterSource u_row;
+  u_row.init(p, ray);
   const float4* samples = sample_slots(p, seg, ray);
   DepthWalker zw;
   zw.init(p, rc, u_row, i0);
@@ -516,4 +518,27 @@ int max_threads_per_cta(int regcap) { return regcap <= 64 ? Bounds<64>::kThreads
 
 int saved_floats_per_segment(int ncol, int samples_per_segment) { return ncol + 3 + 4 * samples_per_segment; }
 
+}  // namespace voxe
+
+namespace voxe {
+namespace {
+__global__ void __launch_bounds__(256) jitter_fill_kernel(KParams p, float* out) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)p.R * p.S) return;
+  JitterSource u;
+  u.init(p, (int)(t / p.S));
+  out[t] = u.at(p, (int)(t % p.S));
+}
+}  // namespace
+
+cudaError_t launch_jitter_fill(int R, int S, unsigned long long seed, unsigned long long offset, float* out, cudaStream_t stream) {
+  KParams p{};
+  p.R = R;
+  p.S = S;
+  p.rng_seed = seed;
+  p.rng_offset = offset;
+  const long long n = (long long)R * S;
+  jitter_fill_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(p, out);
+  return cudaGetLastError();
+}
 }  // namespace voxe

@@ -17,6 +17,7 @@
 //   dense    otherwise: return dense gradients shaped like the parameters, exactly as autograd expects.
 #include <torch/extension.h>
 
+#include <ATen/cuda/CUDAGeneratorImpl.h>
 #include <c10/cuda/CUDAGuard.h>
 #include <c10/cuda/CUDAStream.h>
 #include <torch/csrc/autograd/graph_task.h>
@@ -105,7 +106,7 @@ class RenderFn : public torch::autograd::Function<RenderFn> {
                                const c10::optional<Tensor>& dirty_flag, const std::string& gdesc, const std::string& rdesc,
                                int64_t mode) {
     const auto gd = unpack_desc<VoxeGridDesc>(gdesc);
-    const auto rd = unpack_desc<VoxeRenderDesc>(rdesc);
+    const auto rd = unpack_desc<VoxeRenderDesc>(rdesc);  // carries this call's (rng_seed, rng_offset)
     const Tensor jit = jitter.value_or(Tensor()), noi = noise.value_or(Tensor());
     const int64_t R = rays_o.size(0);
     Tensor saved = at::empty({voxe_saved_floats(&rd, R)}, rays_o.options());
@@ -178,9 +179,11 @@ class RenderFn : public torch::autograd::Function<RenderFn> {
 
 // colour [R,C], depth [R,1], acc [R,1], disparity [R,1] = render(...).  `gdesc` / `rdesc` are the raw bytes of a
 // VoxeGridDesc / VoxeRenderDesc (built once per distinct description on the Python side).  `jitter` / `noise` may be
-// None: they are then drawn here with at::rand / at::randn from `generator` (or the device's default generator) -- the
-// same generator, shapes and order as sample.py:63 and accumulate.py:59-62.  `strict_rng` also draws (and discards) the
-// noise tensor when noise_std == 0, as the reference does.
+// None.  Stratified jitter is then generated inside the kernels from a (seed, offset) pair taken from `generator` (or
+// the device's default generator, which is advanced, so torch.manual_seed reproduces a run); with `strict_rng` the
+// reference's own draws are made instead -- at::rand [R,S] for the jitter and at::randn [R,S] for the density noise
+// (drawn and discarded when noise_std == 0), the same generator, shapes and order as sample.py:63 and
+// accumulate.py:59-62.  Density noise with noise_std != 0 is always an at::randn draw.
 std::vector<Tensor> render(const Tensor& densities, const Tensor& features, const Tensor& packed, const Tensor& rays_o_in,
                            const Tensor& rays_d_in, const c10::optional<Tensor>& jitter_in, const c10::optional<Tensor>& noise_in,
                            const c10::optional<Tensor>& grad_volume, const c10::optional<Tensor>& dirty_flag,
@@ -190,7 +193,7 @@ std::vector<Tensor> render(const Tensor& densities, const Tensor& features, cons
   TORCH_CHECK(dev.is_cuda(), "the fused Vox-E render path runs on CUDA only (tensors are on '", dev,
               "'); there is deliberately no CPU fallback in this package");
   TORCH_CHECK(gdesc.size() == sizeof(VoxeGridDesc) && rdesc.size() == sizeof(VoxeRenderDesc), "descriptor size mismatch (ABI)");
-  const auto rd = unpack_desc<VoxeRenderDesc>(rdesc);
+  auto rd = unpack_desc<VoxeRenderDesc>(rdesc);
   TORCH_CHECK(rays_o_in.dim() == 2 && rays_d_in.dim() == 2 && rays_o_in.size(1) == 3 && rays_o_in.sizes() == rays_d_in.sizes(),
               "Please note that the RENDER interface only works with FLAT RAYS!");
   const c10::cuda::CUDAGuard guard(dev);
@@ -201,9 +204,19 @@ std::vector<Tensor> render(const Tensor& densities, const Tensor& features, cons
     rays_d = prep(rays_d_in.detach(), dev, "ray directions");
     const int64_t R = rays_o.size(0), S = rd.num_samples;
     if (rd.flags & VOXE_FLAG_PERTURB) {
-      jitter = jitter_in.has_value() && jitter_in->defined() ? prep(jitter_in->detach(), dev, "jitter")
-                                                            : at::rand({R, S}, generator, rays_o.options());
-      TORCH_CHECK(jitter.dim() == 2 && jitter.size(0) == R && jitter.size(1) == S, "jitter must be [R, S]");
+      if (jitter_in.has_value() && jitter_in->defined()) {
+        jitter = prep(jitter_in->detach(), dev, "jitter");
+      } else if (strict_rng) {
+        jitter = at::rand({R, S}, generator, rays_o.options());
+      } else {  // in-kernel Philox draws: take (seed, offset) from the generator and advance it
+        auto* gen = at::get_generator_or_default<at::CUDAGeneratorImpl>(generator, at::cuda::detail::getDefaultCUDAGenerator(dev.index()));
+        std::lock_guard<std::mutex> lock(gen->mutex_);
+        const at::PhiloxCudaState st = gen->philox_cuda_state(4);
+        TORCH_CHECK(!st.captured_, "in-kernel jitter cannot be captured into a CUDA graph through this path; pass `jitter` explicitly");
+        rd.rng_seed = st.seed_.val;
+        rd.rng_offset = st.offset_.val;
+      }
+      TORCH_CHECK(!jitter.defined() || (jitter.dim() == 2 && jitter.size(0) == R && jitter.size(1) == S), "jitter must be [R, S]");
     }
     if (rd.noise_std != 0.f) {
       noise = noise_in.has_value() && noise_in->defined() ? prep(noise_in->detach(), dev, "noise")
@@ -215,13 +228,14 @@ std::vector<Tensor> render(const Tensor& densities, const Tensor& features, cons
   }
   const bool differentiable = at::GradMode::is_enabled() && ((densities.defined() && densities.requires_grad()) ||
                                                              (features.defined() && features.requires_grad()));
+  const std::string rdesc_call(reinterpret_cast<const char*>(&rd), sizeof(rd));  // with this call's RNG state
   if (!differentiable) {
     const auto gd = unpack_desc<VoxeGridDesc>(gdesc);
     Outputs o = run_forward(gd, rd, packed, rays_o, rays_d, jitter, noise, Tensor());
     return {o.colour, o.depth, o.acc, o.disp};
   }
   return RenderFn::apply(densities, features, packed, rays_o, rays_d, c10::optional<Tensor>(jitter),
-                         c10::optional<Tensor>(noise), grad_volume, dirty_flag, gdesc, rdesc, mode);
+                         c10::optional<Tensor>(noise), grad_volume, dirty_flag, gdesc, rdesc_call, mode);
 }
 
 }  // namespace

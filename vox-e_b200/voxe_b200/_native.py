@@ -16,7 +16,7 @@ _lock = threading.Lock()
 _lib: Optional[ctypes.CDLL] = None
 
 # ---- enums of include/voxe.h -------------------------------------------------------------------------------
-ABI_VERSION = 6
+ABI_VERSION = 7
 PREACT_IDENTITY, PREACT_ABS = 0, 1
 POSTACT_IDENTITY, POSTACT_RELU, POSTACT_SOFTPLUS = 0, 1, 2
 FLAG_PERTURB, FLAG_AABB_SAMPLING, FLAG_DISPARITY_SAMPLING = 1, 2, 4
@@ -51,6 +51,8 @@ class VoxeRenderDesc(ctypes.Structure):
         ("sh_degree", ctypes.c_int32),
         ("n_colour", ctypes.c_int32),
         ("noise_std", ctypes.c_float),
+        ("rng_seed", ctypes.c_uint64),
+        ("rng_offset", ctypes.c_uint64),
     ]
 
 
@@ -70,6 +72,7 @@ EXPORTS = {
     "voxe_pack_grid": (ctypes.c_int, [_GD, _P, _P, _P, _P]),
     "voxe_unpack_grad": (ctypes.c_int, [_GD, _P, _P, _P, ctypes.c_int, _P]),
     "voxe_consume_grad": (ctypes.c_int, [_GD, _P, _P, _P, _P]),
+    "voxe_jitter_fill": (ctypes.c_int, [_RD, _P, ctypes.c_int64, _P]),
     "voxe_adam_step": (ctypes.c_int, [_GD, ctypes.POINTER(VoxeAdamDesc), _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "voxe_saved_floats": (ctypes.c_int64, [_RD, ctypes.c_int64]),
     "voxe_render_fwd": (ctypes.c_int, [_GD, _RD, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, ctypes.c_int64, _P]),
