@@ -321,6 +321,11 @@ def test_generator_consumption_matches_the_reference_in_strict_mode():
     finally:
         rf.STRICT_REFERENCE_RNG = False
     assert torch.equal(got[0], want[0]) and torch.equal(got[1], want[1])
+    # default mode: the draws come from the same generator (seed, offset) but are generated inside the kernels -- another
+    # realisation of the same distribution, reproducible under torch.manual_seed (tests/test_kernel_jitter.py)
     torch.manual_seed(123)
     loose = [render_sh_voxel_grid(grid, rays, cfg).colour.detach() for _ in range(2)]
-    assert torch.equal(loose[0], want[0]) and not torch.equal(loose[1], want[1])  # default mode: first call identical only
+    torch.manual_seed(123)
+    again = [render_sh_voxel_grid(grid, rays, cfg).colour.detach() for _ in range(2)]
+    assert torch.equal(loose[0], again[0]) and torch.equal(loose[1], again[1]) and not torch.equal(loose[0], loose[1])
+    assert not torch.equal(loose[0], want[0]) and float((loose[0] - want[0]).abs().mean()) < 0.05
