@@ -447,7 +447,7 @@ class DeviceBench:
         return start.elapsed_time(stop)  # ms
 
 
-def e2e_leg(device, rank, world, steps, warmup, dist, deferred=False):
+def e2e_leg(device, rank, world, steps, warmup, dist, deferred=False, engine_threads=False):
     """The frame through the public API, inputs starting in pinned host memory.  ``deferred``: the opt-in gradient
     accumulation mode (VoxelGrid.accumulate_render_gradients) with one materialisation per frame."""
     from thre3d_atom.modules.volumetric_model import VolumetricModel
@@ -502,22 +502,28 @@ def e2e_leg(device, rank, world, steps, warmup, dist, deferred=False):
             dist.all_reduce(grid.features.grad)
         return float(loss_total.item())  # D2H of the step's result; also orders the colour copy
 
-    for k in range(warmup):
-        one_frame(k * world + rank)
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize(device)
-    t0 = time.perf_counter()
-    for k in range(steps):
-        one_frame((warmup + k) * world + rank)
-    torch.cuda.synchronize(device)
-    elapsed = time.perf_counter() - t0
+    # torch's autograd engine normally hands every backward() to a per-device worker thread and blocks the caller on it
+    # (two thread hops, ~25 us per call on these hosts, more than the kernels of a 4096-ray batch); the stock switch
+    # below runs the backward on the calling thread instead.  It is a caller-side setting, not part of the library.
+    with torch.autograd.set_multithreading_enabled(engine_threads):
+        for k in range(warmup):
+            one_frame(k * world + rank)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(device)
+        t0 = time.perf_counter()
+        for k in range(steps):
+            one_frame((warmup + k) * world + rank)
+        torch.cuda.synchronize(device)
+        elapsed = time.perf_counter() - t0
     if world > 1:
         t = torch.tensor([elapsed], device=device)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         elapsed = float(t.item())
     return {"value": world * R * steps / elapsed, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-            "ms_per_step": 1e3 * elapsed / steps, "steps": steps, "api": "per 4096-ray batch: VolumetricModel.render_rays(Rays) -> out.colour.backward(dL/dcolour); per frame: "
+            "ms_per_step": 1e3 * elapsed / steps, "steps": steps,
+            "autograd_engine": "worker threads (torch default)" if engine_threads else "calling thread (torch.autograd.set_multithreading_enabled(False))",
+            "api": "per 4096-ray batch: VolumetricModel.render_rays(Rays) -> out.colour.backward(dL/dcolour); per frame: "
             "one pinned H2D copy of rays + upstream gradients, one D2H copy of the rendered colours and the loss"}
 
 
@@ -710,6 +716,9 @@ def run_ours(args):
         e2e_deferred = e2e_leg(device, rank, world, max(2, min(args.steps, args.e2e_steps)), min(args.warmup, 3), dist, deferred=True)
         e2e["deferred_grads"] = {"value": e2e_deferred["value"], "ms_per_step": e2e_deferred["ms_per_step"],
                                  "note": "same loop with VoxelGrid.accumulate_render_gradients(): gradients materialised once per frame"}
+        e2e_threads = e2e_leg(device, rank, world, max(2, min(args.steps, args.e2e_steps)), min(args.warmup, 3), dist, engine_threads=True)
+        e2e["default_engine_threads"] = {"value": e2e_threads["value"], "ms_per_step": e2e_threads["ms_per_step"],
+                                         "note": "same loop with torch's default multi-threaded autograd engine (host-bound: ~50 us of engine overhead per backward())"}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu and args.workload == "cfg2":

@@ -75,3 +75,7 @@ t("bridge.render + colour.backward(g)", lambda: fwd_bwd(lambda: bridge_call(True
 t("vm.render_rays + colour.backward(g)", lambda: fwd_bwd(lambda: vm.render_rays(rays0)))
 x = torch.randn(B, 3, device=dev, requires_grad=True)
 t("reference point: (x*2).backward(g) on a [4096,3] tensor", lambda: (x * 2).backward(g0))
+with torch.autograd.set_multithreading_enabled(False):
+    t("[single-threaded engine] bridge.render + colour.backward(g)", lambda: fwd_bwd(lambda: bridge_call(True)))
+    t("[single-threaded engine] vm.render_rays + colour.backward(g)", lambda: fwd_bwd(lambda: vm.render_rays(rays0)))
+    t("[single-threaded engine] (x*2).backward(g)", lambda: (x * 2).backward(g0))
