@@ -27,7 +27,7 @@
 #include "voxe_launch.h"
 
 #ifndef VOXE_UNROLL
-#define VOXE_UNROLL 1
+#define VOXE_UNROLL 2
 #endif
 
 namespace voxe {
@@ -194,6 +194,10 @@ __global__ void __launch_bounds__(Bounds<REGCAP>::kThreads, 1) render_fwd_kernel
     float Y[LT::K];
     const float inv = 1.0f / rc.dnorm;
     sh_basis<DEG>(rc.d[0] * inv, rc.d[1] * inv, rc.d[2] * inv, (p.flags & kDiffuse) != 0, Y);
+    // The body is straight-line code (no early exits): a batch keeps only ~13 warps on an SM, so the kernel is bound by
+    // the dependent-instruction latency of one sample; unrolled by two, the loads and arithmetic of two consecutive
+    // samples interleave.  Samples outside the box are rare here (thread_samples) and are masked, not skipped: their
+    // corner addresses are clamped into the volume and their sigma / colour are forced to 0 (process.py:80-91).
 #pragma unroll(kSampleUnroll)
     for (int i = i0; i < i1; ++i, zw.advance(p, rc, u_row, i - 1)) {
       const float zi = zw.cur;
@@ -201,25 +205,19 @@ __global__ void __launch_bounds__(Bounds<REGCAP>::kThreads, 1) render_fwd_kernel
       const float py = __fadd_rn(rc.o[1], __fmul_rn(rc.d[1], zi));
       const float pz = __fadd_rn(rc.o[2], __fmul_rn(rc.d[2], zi));
       const bool in = inside_aabb(p, px, py, pz);
-      if (!in && !use_noise) continue;  // alpha == 0 exactly (process.py:80-91)
-      float sigma = 0.f, col[NCOL];
+      Corners c;
+      make_corners(p, px, py, pz, c);
+      float raw[NCOL], dpost, col[NCOL];
+      unsigned signs;
+      const float sraw = gather_sample<DEG, NCOL>(p, c, Y, raw, signs);
+      float sigma = in ? post_act(p.postact, sraw, dpost) : 0.f;
 #pragma unroll
-      for (int k = 0; k < NCOL; ++k) col[k] = 0.f;   // sigmoid(-1e10) == 0 outside the grid
-      if (in) {
-        Corners c;
-        make_corners(p, px, py, pz, c);
-        float raw[NCOL], dpost;
-        unsigned signs;
-        const float sraw = gather_sample<DEG, NCOL>(p, c, Y, raw, signs);
-        sigma = post_act(p.postact, sraw, dpost);
-#pragma unroll
-        for (int k = 0; k < NCOL; ++k) col[k] = sigmoid_fast(raw[k]);
-        if (samples != nullptr) {  // what the backward needs of this sample: colour(s) and the raw density
-          float4 sv = make_float4(col[0], 0.f, 0.f, sraw);
-          if (NCOL > 1) sv.y = col[1];
-          if (NCOL > 2) sv.z = col[2];
-          samples[(size_t)(i - i0) * p.R] = sv;
-        }
+      for (int k = 0; k < NCOL; ++k) col[k] = in ? sigmoid_fast(raw[k]) : 0.f;   // sigmoid(-1e10) == 0 outside the grid
+      if (samples != nullptr && in) {  // what the backward needs of this sample: colour(s) and the raw density
+        float4 sv = make_float4(col[0], 0.f, 0.f, sraw);
+        if (NCOL > 1) sv.y = col[1];
+        if (NCOL > 2) sv.z = col[2];
+        samples[(size_t)(i - i0) * p.R] = sv;
       }
       if (use_noise) sigma = fmaf(__ldg(p.noise + (size_t)ray * p.S + i), p.noise_std, sigma);
       const float delta = ((i == p.S - 1) ? kInfinity : __fsub_rn(zw.next, zi)) * rc.dnorm;  // accumulate.py:49-55
@@ -404,8 +402,11 @@ __global__ void __launch_bounds__(Bounds<REGCAP>::kThreads, 1) render_bwd_kernel
   sh_basis<DEG>(rc.d[0] * inv, rc.d[1] * inv, rc.d[2] * inv, (p.flags & kDiffuse) != 0, Y);
   float prefix = 0.f;  // sum of w*q over this segment's samples up to and including the current one
 
+  float4 sv_next = __ldg(samples);  // the sample vectors are fetched one iteration ahead of their use
 #pragma unroll(kSampleUnroll)
   for (int i = i0; i < i1; ++i, zw.advance(p, rc, u_row, i - 1)) {
+    const float4 sv = sv_next;
+    if (i + 1 < i1) sv_next = __ldg(samples + (size_t)(i + 1 - i0) * p.R);
     const float zi = zw.cur;
     const float px = __fadd_rn(rc.o[0], __fmul_rn(rc.d[0], zi));
     const float py = __fadd_rn(rc.o[1], __fmul_rn(rc.d[1], zi));
@@ -416,8 +417,7 @@ __global__ void __launch_bounds__(Bounds<REGCAP>::kThreads, 1) render_bwd_kernel
 #pragma unroll
     for (int k = 0; k < NCOL; ++k) col[k] = 0.f;
     if (in) {
-      const float4 sv = __ldg(samples + (size_t)(i - i0) * p.R);  // colour(s) + raw density stored by the forward
-      col[0] = sv.x;
+      col[0] = sv.x;  // colour(s) + raw density stored by the forward
       if (NCOL > 1) col[1] = sv.y;
       if (NCOL > 2) col[2] = sv.z;
       sigma = post_act(p.postact, sv.w, dpost);
