@@ -7,15 +7,16 @@ density scale 33.333, world box [-1.5,1.5]^3; 400x400 pinhole camera f=555.5 on 
 background; every frame is rendered as 40 consecutive flat-index batches of <= 4096 rays, each batch forward AND backward
 (upstream gradient = a fixed dense dL/dcolour, i.e. loss = <colour, G>).
 
-A *step* is one frame = 160 000 rays = 40 x (jitter draw, forward kernel, backward kernel accumulating into the packed
-gradient volume) + one gradient zero-fill + one unpack of the packed gradient into d_densities / d_features (+ one NCCL
-all-reduce of the packed gradient when N > 1: each rank renders its own pose -- weak scaling).
+A *step* is one frame = 160 000 rays = 40 x (forward kernel, backward kernel accumulating into the packed gradient
+volume; the stratified jitter is generated inside both kernels, ``--jitter buffer`` draws it with torch.rand instead)
++ one gradient zero-fill + one unpack of the packed gradient into d_densities / d_features (+ one NCCL all-reduce of
+the packed gradient when N > 1: each rank renders its own pose -- weak scaling).
 
   value     device-resident throughput: the step above replayed as a CUDA graph over C-ABI launches, inputs in HBM;
-            two batches are in flight on two streams (--lanes 2; the strictly serialised number is reported as
-            ``serialized``) and the jitter draws run ahead on a side stream
-  e2e       the same frame through the public API (``VolumetricModel.render_rays`` + ``.backward()``) with rays and
-            upstream gradients starting in pinned HOST memory and loss + colour read back every step
+            three batches are in flight on three streams (--lanes 3; the strictly serialised number is reported as
+            ``serialized``)
+  e2e       the same frame through the public API (``VolumetricModel.render_rays`` + ``.backward()`` per 4096-ray batch)
+            with rays and upstream gradients starting in pinned HOST memory and loss + colour read back every step
   roofline  the backward kernel (dominant) timed alone with CUDA events: algorithmic bytes / duration vs measured HBM peak
   cpu_baseline  the oracle port (PyTorch fp32, all host threads) on a bounded sample of the same batches
 
@@ -323,13 +324,15 @@ class DeviceBench:
         self.saved_lane = [self.saved] + [torch.empty_like(self.saved) for _ in range(self.n_lanes - 1)]
         self.batches = [(s, min(s + WL["batch"], self.R)) for s in range(0, self.R, WL["batch"])]
         self.s_in = [count_inside_samples(o, d) for (o, d) in self.rays] if count_s_in else None
+        # forward + backward per batch, the unpack, and (buffer mode only) one torch.rand per batch; the memset of the
+        # gradient volume is not a kernel of this library
         self.kernels_per_step = 2 * len(self.batches) + 1
 
     def _stream(self):
         return torch.cuda.current_stream(self.device).cuda_stream
 
     def _jitter_arg(self, pose, b0):
-        """Explicit torch-drawn [R,S] jitter buffer, or None + a per-batch Philox offset for the in-kernel draws (the
+        """Explicit torch-drawn [R,S] jitter buffer, or None + a per-batch RNG offset for the in-kernel draws (the
         descriptor is read at launch time, so forward and backward of a batch see the same offset)."""
         if not WL["perturb"]:
             return None
@@ -734,7 +737,7 @@ def run_ours(args):
             "metric": "rays/s fwd+bwd, 160^3 SH-0 grid, 400x400 render", "value": rays_per_s, "unit": "rays/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WL["name"], "step": f"one {WL['height']}x{WL['width']} frame = {len(bench.batches)} batches x (jitter, fwd, bwd) + grad zero-fill + unpack"
+            "config": {"workload": WL["name"], "step": f"one {WL['height']}x{WL['width']} frame = {len(bench.batches)} batches x (fwd, bwd; jitter {'generated in-kernel' if bench.kernel_jitter else 'drawn by torch.rand'}) + grad zero-fill + unpack"
                        + (" + 1 NCCL all-reduce of packed voxel grads" if world > 1 else ""),
                        "batches_in_flight": f"{bench.n_lanes} (each launch is one <=4096-ray batch with its own workspace; gradients accumulate "
                                             "over the frame, so batch k+1's forward does not wait for batch k's backward)",
@@ -767,7 +770,7 @@ def main():
                     help="cfg2 is the headline (the line the driver reads); the others are recorded in DESIGN.md")
     ap.add_argument("--lanes", type=int, default=3, help="ray batches in flight within a frame (streams)")
     ap.add_argument("--jitter", choices=["kernel", "buffer"], default="kernel",
-                    help="stratified jitter of the device leg: generated inside the kernels (Philox) or torch-drawn [R,S] buffers")
+                    help="stratified jitter of the device leg: generated inside the kernels (counter-based hash) or torch-drawn [R,S] buffers")
     ap.add_argument("--sweep", type=str, default="", help="tuning sweep: 'L,rpc,cap;L,rpc,cap;...'")
     ap.add_argument("--tune", type=str, default="", help="L,rpc,regcap launch-shape override for tuning runs")
     args = ap.parse_args()

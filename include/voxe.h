@@ -96,7 +96,7 @@ typedef struct VoxeRenderDesc {
   int32_t n_colour;       /* 3 (RGB) or 1 (attn)                                                            */
   float noise_std;        /* stochastic_density_noise_std; != 0 needs `noise` [R,S] (standard normal)       */
   uint64_t rng_seed;      /* VOXE_FLAG_PERTURB with jitter == NULL: the U[0,1) draws of sample.py:63 are generated */
-  uint64_t rng_offset;    /* inside the kernels, Philox4x32-7 keyed by rng_seed, counter (sample/4, ray, rng_offset) */
+  uint64_t rng_offset;    /* inside the kernels: a counter-based PCG hash of (rng_seed, rng_offset, ray, sample)     */
 } VoxeRenderDesc;
 
 VOXE_API int voxe_abi_version(void);

@@ -1,4 +1,4 @@
-"""Stratified jitter generated inside the kernels (Philox4x32-7 keyed by the torch generator's seed / offset): the draws
+"""Stratified jitter generated inside the kernels (a counter-based PCG hash keyed by the torch generator's seed / offset): the draws
 are uniform, reproducible under torch.manual_seed, identical in forward and backward, and a render that uses them is
 bit-identical to a render that is handed the same draws as an explicit [R,S] buffer (which is the path the reference
 goldens pin)."""

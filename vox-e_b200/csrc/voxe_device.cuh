@@ -286,45 +286,33 @@ __device__ __forceinline__ void sample_range(const KParams& p, const RayCtx& rc,
   if (b < a) b = a;
 }
 
-// Philox4x32 with 7 rounds (Salmon et al., "Parallel random numbers: as easy as 1, 2, 3": Crush-resistant from 7 rounds).
-__device__ __forceinline__ uint4 philox4x32_7(uint4 ctr, uint2 key) {
-#pragma unroll
-  for (int r = 0; r < 7; ++r) {
-    const unsigned hi0 = __umulhi(0xD2511F53u, ctr.x), lo0 = 0xD2511F53u * ctr.x;
-    const unsigned hi1 = __umulhi(0xCD9E8D57u, ctr.z), lo1 = 0xCD9E8D57u * ctr.z;
-    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
-    key.x += 0x9E3779B9u;
-    key.y += 0xBB67AE85u;
-  }
-  return ctr;
+// PCG output hash (O'Neill's PCG-RXS-M-XS-32 permutation; the best quality-per-instruction 32-bit hash in Jarzynski &
+// Olano, "Hash Functions for GPU Rendering", JCGT 2020): ~7 integer instructions, no state.
+__device__ __forceinline__ unsigned pcg_hash(unsigned v) {
+  const unsigned state = v * 747796405u + 2891336453u;
+  const unsigned word = ((state >> ((state >> 28u) + 4u)) ^ state) * 277803737u;
+  return (word >> 22u) ^ word;
 }
 
 // Stratified-jitter draws u[ray][i] in [0, 1): either the caller's [R,S] buffer (torch.rand, sample.py:63) or generated
-// here -- one Philox block per 4 consecutive samples of a ray, 24 mantissa bits per draw like torch's uniform.  The
-// kernels walk i upwards, so the last block is kept.  Forward and backward regenerate identical values.
+// here as a counter-based hash of (seed, offset, ray, sample) -- 24 mantissa bits per draw like torch's uniform.  The
+// kernels are bound by per-thread instruction latency, so the generator is a short hash rather than a Philox block
+// (measured: Philox4x32-7 added 22 % to the instruction count of the forward kernel).  Forward and backward regenerate
+// identical values; a draw depends on (seed, offset, ray, sample) only.
 struct JitterSource {
   const float* row;
-  unsigned ray;
-  int blk_id;
-  uint4 blk;
+  unsigned base;
 
   __device__ __forceinline__ void init(const KParams& p, int ray_index) {
     row = p.jitter ? p.jitter + (size_t)ray_index * p.S : nullptr;
-    ray = (unsigned)ray_index;
-    blk_id = -1;
-    blk = make_uint4(0u, 0u, 0u, 0u);
+    unsigned k = pcg_hash((unsigned)p.rng_seed ^ pcg_hash((unsigned)(p.rng_seed >> 32)));
+    k = pcg_hash(k ^ (unsigned)p.rng_offset);
+    k = pcg_hash(k ^ (unsigned)(p.rng_offset >> 32));
+    base = pcg_hash(k ^ (unsigned)ray_index) + (unsigned)ray_index * 0x9E3779B9u;  // per-ray stream start
   }
-  __device__ __forceinline__ float at(const KParams& p, int i) {
+  __device__ __forceinline__ float at(const KParams& p, int i) const {
     if (row != nullptr) return __ldg(row + i);
-    const int b = i >> 2;
-    if (b != blk_id) {
-      blk = philox4x32_7(make_uint4((unsigned)b, ray, (unsigned)p.rng_offset, (unsigned)(p.rng_offset >> 32)),
-                         make_uint2((unsigned)p.rng_seed, (unsigned)(p.rng_seed >> 32)));
-      blk_id = b;
-    }
-    const int k = i & 3;
-    const unsigned x = (k == 0) ? blk.x : (k == 1) ? blk.y : (k == 2) ? blk.z : blk.w;
-    return (float)(x >> 8) * (1.0f / 16777216.0f);
+    return (float)(pcg_hash(base + (unsigned)i) >> 8) * (1.0f / 16777216.0f);
   }
 };
 

@@ -208,7 +208,7 @@ std::vector<Tensor> render(const Tensor& densities, const Tensor& features, cons
         jitter = prep(jitter_in->detach(), dev, "jitter");
       } else if (strict_rng) {
         jitter = at::rand({R, S}, generator, rays_o.options());
-      } else {  // in-kernel Philox draws: take (seed, offset) from the generator and advance it
+      } else {  // in-kernel draws: take (seed, offset) from the generator and advance it
         auto* gen = at::get_generator_or_default<at::CUDAGeneratorImpl>(generator, at::cuda::detail::getDefaultCUDAGenerator(dev.index()));
         std::lock_guard<std::mutex> lock(gen->mutex_);
         const at::PhiloxCudaState st = gen->philox_cuda_state(4);
