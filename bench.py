@@ -702,8 +702,8 @@ def run_ours(args):
         roof = {
             "bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
             # dram__bytes_read.sum + dram__bytes_write.sum per backward launch from the committed ncu --set full capture
-            # (profiles/r1_bwd_kernel_metrics.txt); the grid is L2-resident at 160^3, hence far below the algorithmic bytes
-            "traffic": 12.9e6 if args.workload == "cfg2" else None,
+            # (profiles/r1b_bwd_kernel_metrics.txt); the grid is L2-resident at 160^3, hence far below the algorithmic bytes
+            "traffic": 14.2e6 if args.workload == "cfg2" else None,
             "peak_source": peak_note, "kernel": "render_bwd_kernel<DEG=0,NCOL=3>", "us_per_launch": round(bwd_us, 2),
             "algorithmic_bytes_per_launch": round(bwd_bytes), "fwd_kernel": {"us_per_launch": round(fwd_us, 2),
             "achieved": round(fwd_bytes / (fwd_us * 1e-6) / 1e9, 1), "frac": round(fwd_bytes / (fwd_us * 1e-6) / 1e9 / peak, 4)},
