@@ -450,7 +450,7 @@ class DeviceBench:
         return start.elapsed_time(stop)  # ms
 
 
-def e2e_leg(device, rank, world, steps, warmup, dist, deferred=False, engine_threads=False):
+def e2e_leg(device, rank, world, steps, warmup, dist, deferred=False, engine_threads=False, whole_frame=False):
     """The frame through the public API, inputs starting in pinned host memory.  ``deferred``: the opt-in gradient
     accumulation mode (VoxelGrid.accumulate_render_gradients) with one materialisation per frame."""
     from thre3d_atom.modules.volumetric_model import VolumetricModel
@@ -474,6 +474,8 @@ def e2e_leg(device, rank, world, steps, warmup, dist, deferred=False, engine_thr
         o, d = frame_rays(p, torch.device("cpu"))
         host.append((o.pin_memory(), d.pin_memory(), torch.randn(o.shape[0], 3, generator=g).pin_memory()))
     R, B = host[0][0].shape[0], WL["batch"]
+    if whole_frame:
+        B = R  # one render_rays + one backward per frame (how the SDS edit loop calls it, sds_trainer.py:283)
     colour_host = torch.empty(R, 3).pin_memory()
     h2d = R * (12 + 12 + 12)
     d2h = R * 12 + 4
@@ -719,6 +721,10 @@ def run_ours(args):
         e2e_deferred = e2e_leg(device, rank, world, max(2, min(args.steps, args.e2e_steps)), min(args.warmup, 3), dist, deferred=True)
         e2e["deferred_grads"] = {"value": e2e_deferred["value"], "ms_per_step": e2e_deferred["ms_per_step"],
                                  "note": "same loop with VoxelGrid.accumulate_render_gradients(): gradients materialised once per frame"}
+        e2e_frame = e2e_leg(device, rank, world, max(2, min(args.steps, args.e2e_steps)), min(args.warmup, 3), dist, whole_frame=True)
+        e2e["whole_frame_call"] = {"value": e2e_frame["value"], "ms_per_step": e2e_frame["ms_per_step"],
+                                   "note": "not the headline workload: the same frame as ONE render_rays(160000 rays) + ONE backward() "
+                                           "(the SDS edit loop's calling pattern) -- what the API delivers when the caller does not split into 4096-ray batches"}
         e2e_threads = e2e_leg(device, rank, world, max(2, min(args.steps, args.e2e_steps)), min(args.warmup, 3), dist, engine_threads=True)
         e2e["default_engine_threads"] = {"value": e2e_threads["value"], "ms_per_step": e2e_threads["ms_per_step"],
                                          "note": "same loop with torch's default multi-threaded autograd engine (host-bound: ~50 us of engine overhead per backward())"}

@@ -213,8 +213,9 @@ __global__ void __launch_bounds__(Bounds<REGCAP>::kThreads, 1) render_fwd_kernel
       float sigma = in ? post_act(p.postact, sraw, dpost) : 0.f;
 #pragma unroll
       for (int k = 0; k < NCOL; ++k) col[k] = in ? sigmoid_fast(raw[k]) : 0.f;   // sigmoid(-1e10) == 0 outside the grid
-      if (samples != nullptr && in) {  // what the backward needs of this sample: colour(s) and the raw density
-        float4 sv = make_float4(col[0], 0.f, 0.f, sraw);
+      if (samples != nullptr) {  // what the backward needs of this sample: colour(s) and the raw density (every slot
+        // of the thread's range is written, so the backward's one-ahead prefetch never reads uninitialised memory)
+        float4 sv = make_float4(col[0], 0.f, 0.f, in ? sraw : 0.f);
         if (NCOL > 1) sv.y = col[1];
         if (NCOL > 2) sv.z = col[2];
         samples[(size_t)(i - i0) * p.R] = sv;

@@ -114,9 +114,25 @@ class VolumetricModel:
     # ------------------------------------------------------------------------------------------------------
     # whole-camera renders (no grad)
     # ------------------------------------------------------------------------------------------------------
-    def _render_camera(self, render_chunk, collate, reshape, camera_pose, camera_intrinsics, chunk_size, gpu_render, verbose):
+    def _whole_camera_in_one_launch(self, noise_std: float, attn: bool) -> bool:
+        """True for the fused render procedures, unless a call would have to materialise [R, S] random draws
+        (reference-RNG replay, density noise); any other procedure keeps the caller's chunking."""
+        from thre3d_atom.thre3d_reprs.renderers import render_sh_voxel_grid
+        from voxe_b200 import render_function as rf
+
+        procedure = self._render_procedure_attn if attn else self._render_procedure
+        fused = procedure is (render_sh_voxel_grid_attn if attn else render_sh_voxel_grid)
+        return fused and not rf.STRICT_REFERENCE_RNG and noise_std == 0.0
+
+    def _render_camera(self, render_chunk, collate, reshape, camera_pose, camera_intrinsics, chunk_size, gpu_render, verbose,
+                       kwargs_noise_std=0.0, attn=False):
         flat_rays = flatten_rays(cast_rays(camera_intrinsics=camera_intrinsics, pose=camera_pose, device=self._device))
         chunk_size = len(flat_rays) if chunk_size is None else chunk_size
+        if self._whole_camera_in_one_launch(kwargs_noise_std, attn):
+            # The reference chunks rays (32768 per call, volumetric_model.py:170-186) to bound the [R, S, .] tensors of its
+            # pipeline; the fused forward kernel keeps O(R) state, so under no_grad the whole camera is ONE launch and,
+            # with gpu_render=False, one device->host copy instead of one per chunk.
+            chunk_size = max(chunk_size, len(flat_rays))
         starts = range(0, len(flat_rays), chunk_size)
         if verbose:
             from tqdm import tqdm
@@ -144,6 +160,7 @@ class VolumetricModel:
             lambda rays: self.render_rays(rays, parallel_points_chunk_size, **kwargs),
             collate_rendered_output, reshape_rendered_output,
             camera_pose, camera_intrinsics, parallel_rays_chunk_size, gpu_render, verbose,
+            kwargs_noise_std=float(kwargs.get("stochastic_density_noise_std", getattr(self._render_config, "stochastic_density_noise_std", 0.0))),
         )
 
     def render_attn(
@@ -161,6 +178,8 @@ class VolumetricModel:
             lambda rays: self.render_rays_attn(rays, parallel_points_chunk_size, orig_densities, **kwargs),
             collate_rendered_output_attn, reshape_rendered_output_attn,
             camera_pose, camera_intrinsics, parallel_rays_chunk_size, gpu_render, verbose,
+            kwargs_noise_std=float(kwargs.get("stochastic_density_noise_std", getattr(self._render_config, "stochastic_density_noise_std", 0.0))),
+            attn=True,
         )
 
 
