@@ -779,8 +779,11 @@ def main():
                     help="stratified jitter of the device leg: generated inside the kernels (counter-based hash) or torch-drawn [R,S] buffers")
     ap.add_argument("--sweep", type=str, default="", help="tuning sweep: 'L,rpc,cap;L,rpc,cap;...'")
     ap.add_argument("--tune", type=str, default="", help="L,rpc,regcap launch-shape override for tuning runs")
+    ap.add_argument("--batch", type=int, default=0, help="rays per launch override (tuning / ray-batch sweeps; not a bench line)")
     args = ap.parse_args()
     select_workload(args.workload)
+    if args.batch > 0:
+        WL["batch"] = args.batch
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
     if args.tune:

@@ -186,9 +186,10 @@ VOXE_API int voxe_adam_step(const VoxeGridDesc* grid, const VoxeAdamDesc* adam, 
                             float* packed, float* packed_grad, const float* dense_d_densities,
                             const float* dense_d_features, float* packed_m, float* packed_v, voxe_stream_t stream);
 
-/* Launch-shape override for tuning runs: samples per thread (1..64), rays per CTA (power of two <= 32) and the
- * register budget of the kernel variant (64 or 128); 0 restores the built-in choice of that knob.  Does not change
- * results beyond fp32 summation order. */
+/* Launch-shape override for tuning runs: samples per thread (1..64; the number of depth segments per ray is
+ * ceil(S / samples_per_thread)), rays per CTA (power of two <= 32) and the register budget of the kernel variant
+ * (64, 80, 96 or 128); 0 restores the built-in choice of that knob.  Does not change results beyond fp32 summation
+ * order.  The 80- and 96-register variants are limited to 128 threads per CTA. */
 VOXE_API int voxe_set_tuning(int samples_per_thread, int rays_per_cta, int register_cap);
 
 /* Number of kernels this library has launched on the calling process since load (for bench accounting). */

@@ -269,6 +269,19 @@ def test_volumetric_model_render_matches_reference_golden():
     assert (out.extra["accumulated_weight"].cpu() - a["accumulated_weight"]).abs().max().item() <= ACC_TOL
     with pytest.raises(ValueError):
         vm.render_rays(None, bogus_field=1)
+    # the fused procedure renders the camera in one launch whatever the chunk size; a replay of the reference's RNG
+    # consumption keeps the caller's chunks -- the two must agree bit for bit without jitter, on the host copy too
+    import voxe_b200.render_function as rf
+
+    pose, cam = pose_spherical(meta["yaw"], meta["pitch"], meta["radius"]), CameraIntrinsics(meta["height"], meta["width"], meta["focal"])
+    try:
+        rf.STRICT_REFERENCE_RNG = True
+        chunked = vm.render(pose, cam, parallel_rays_chunk_size=meta["chunk"], gpu_render=False,
+                            num_samples_per_ray=meta["S_override"], optimized_sampling=True)
+    finally:
+        rf.STRICT_REFERENCE_RNG = False
+    assert chunked.colour.device.type == "cpu"
+    assert torch.equal(chunked.colour, out.colour.cpu()) and torch.equal(chunked.depth, out.depth.cpu())
 
 
 def test_no_grad_and_partial_inputs():

@@ -157,14 +157,16 @@ __device__ __forceinline__ void thread_samples(const KParams& p, const RayCtx& r
 
 template <int REGCAP>
 struct Bounds {
-  static constexpr int kThreads = (REGCAP <= 64) ? 1024 : 512;
+  // register budget of the variant = 65536 / (kThreads * kMinBlocks): 64 | 80 (85) | 96 (102) | 128
+  static constexpr int kThreads = (REGCAP <= 64) ? 1024 : (REGCAP >= 128 ? 512 : 128);
+  static constexpr int kMinBlocks = (REGCAP == 80) ? 6 : (REGCAP == 96 ? 5 : 1);
 };
 
 // ---------------------------------------------------------------------------------------------------------
 // forward
 // ---------------------------------------------------------------------------------------------------------
 template <int DEG, int NCOL, int REGCAP>
-__global__ void __launch_bounds__(Bounds<REGCAP>::kThreads, 1) render_fwd_kernel(const __grid_constant__ KParams p) {
+__global__ void __launch_bounds__(Bounds<REGCAP>::kThreads, Bounds<REGCAP>::kMinBlocks) render_fwd_kernel(const __grid_constant__ KParams p) {
   using LT = Layout<DEG, NCOL>;
   constexpr int NV = LT::NV;
   extern __shared__ float smem[];
@@ -293,7 +295,7 @@ __global__ void __launch_bounds__(Bounds<REGCAP>::kThreads, 1) render_fwd_kernel
 // backward
 // ---------------------------------------------------------------------------------------------------------
 template <int DEG, int NCOL, int REGCAP>
-__global__ void __launch_bounds__(Bounds<REGCAP>::kThreads, 1) render_bwd_kernel(const __grid_constant__ KParams p) {
+__global__ void __launch_bounds__(Bounds<REGCAP>::kThreads, Bounds<REGCAP>::kMinBlocks) render_bwd_kernel(const __grid_constant__ KParams p) {
   using LT = Layout<DEG, NCOL>;
   constexpr int NV = LT::NV;
   extern __shared__ float smem[];
@@ -512,10 +514,14 @@ cudaError_t dispatch_deg(const KParams& p, int deg, int ncol, bool backward, cud
 
 cudaError_t launch_render(const KParams& p, int deg, int ncol, int regcap, bool backward, cudaStream_t stream) {
   if (regcap <= 64) return dispatch_deg<64>(p, deg, ncol, backward, stream);
+  if (regcap == 80) return dispatch_deg<80>(p, deg, ncol, backward, stream);
+  if (regcap == 96) return dispatch_deg<96>(p, deg, ncol, backward, stream);
   return dispatch_deg<128>(p, deg, ncol, backward, stream);
 }
 
-int max_threads_per_cta(int regcap) { return regcap <= 64 ? Bounds<64>::kThreads : Bounds<128>::kThreads; }
+int max_threads_per_cta(int regcap) {
+  return regcap <= 64 ? Bounds<64>::kThreads : (regcap == 80 ? Bounds<80>::kThreads : (regcap == 96 ? Bounds<96>::kThreads : Bounds<128>::kThreads));
+}
 
 int saved_floats_per_segment(int ncol, int samples_per_segment) { return ncol + 3 + 4 * samples_per_segment; }
 
