@@ -605,6 +605,16 @@ def run_ours(args):
     device = torch.device(f"cuda:{local}")
     torch.cuda.set_device(device)
     dist = None
+    pinned_cpus = None
+    if world > 1 and not args.no_pin and hasattr(os, "sched_setaffinity"):
+        # one rank per GPU on a shared host: give every rank its own slice of the host's CPUs (what numactl / taskset
+        # would do), so that eight Python loops and their NCCL helper threads do not migrate over each other
+        cpus = sorted(os.sched_getaffinity(0))
+        local_world = int(os.environ.get("LOCAL_WORLD_SIZE", world))
+        per = len(cpus) // max(1, local_world)
+        if per >= 1:
+            pinned_cpus = cpus[local * per:(local + 1) * per]
+            os.sched_setaffinity(0, pinned_cpus)
     if world > 1:
         import torch.distributed as dist
 
@@ -748,7 +758,8 @@ def run_ours(args):
                        "batches_in_flight": f"{bench.n_lanes} (each launch is one <=4096-ray batch with its own workspace; gradients accumulate "
                                             "over the frame, so batch k+1's forward does not wait for batch k's backward)",
                        "l2": "3 rotating grid copies (197 MB) + 65.5 MB gradient volume > 126 MB L2; 8 poses rotate",
-                       "parallelism": f"ray/view data parallel x{world}", "timing": "CUDA events around K graph replays, max over ranks"},
+                       "parallelism": f"ray/view data parallel x{world}", "timing": "CUDA events around K graph replays, max over ranks",
+                       "host_cpus_per_rank": len(pinned_cpus) if pinned_cpus else "unpinned"},
             "e2e": e2e, "gpu_launches": args.steps * bench.kernels_per_step, "roofline": roof, "clocks": clocks,
         }
         if cpu:
@@ -779,6 +790,7 @@ def main():
                     help="stratified jitter of the device leg: generated inside the kernels (counter-based hash) or torch-drawn [R,S] buffers")
     ap.add_argument("--sweep", type=str, default="", help="tuning sweep: 'L,rpc,cap;L,rpc,cap;...'")
     ap.add_argument("--tune", type=str, default="", help="L,rpc,regcap launch-shape override for tuning runs")
+    ap.add_argument("--no-pin", action="store_true", help="N > 1: do not pin each rank to its own slice of the host CPUs")
     ap.add_argument("--batch", type=int, default=0, help="rays per launch override (tuning / ray-batch sweeps; not a bench line)")
     args = ap.parse_args()
     select_workload(args.workload)
