@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define VOXE_ABI_VERSION 7
+#define VOXE_ABI_VERSION 8
 
 #if defined(__GNUC__)
 #define VOXE_API __attribute__((visibility("default")))
@@ -151,6 +151,25 @@ VOXE_API int voxe_render_bwd(const VoxeGridDesc* grid, const VoxeRenderDesc* ren
                     const float* rays_o, const float* rays_d, const float* jitter, const float* noise,
                     const float* saved, const float* g_colour, const float* g_depth, const float* g_acc,
                     const float* g_disp, float* packed_grad, int64_t num_rays, voxe_stream_t stream);
+
+/* Pinhole camera of voxe_render_camera (CameraIntrinsics + CameraPose, utils/imaging_utils.py:17-30). */
+typedef struct VoxeCameraDesc {
+  int32_t height, width;
+  float focal;
+  float rotation[9];      /* camera-to-world rotation, row-major                                            */
+  float translation[3];   /* camera position                                                                */
+} VoxeCameraDesc;
+
+/* Whole-camera inference render (no backward follows): pixels [first_pixel, first_pixel + num_pixels) in flat
+ * row-major order (index = y * W + x, as flatten_rays(cast_rays(...)) orders them).  Replaces, for
+ * VolumetricModel.render (modules/volumetric_model.py:135-193), cast_rays (rendering/volumetric/utils/misc.py:12-50),
+ * the 32768-ray chunk loop and the per-chunk render: rays are generated inside the kernel, one thread per pixel walks
+ * its ray front to back and stops once the transmittance drops below `min_transmittance` (early termination: changes a
+ * pixel by less than that value; pass 0 to evaluate every sample).  Outputs as voxe_render_fwd; stratified jitter, when
+ * VOXE_FLAG_PERTURB is set, comes from (render->rng_seed, render->rng_offset); density noise is not supported here. */
+VOXE_API int voxe_render_camera(const VoxeGridDesc* grid, const VoxeRenderDesc* render, const VoxeCameraDesc* camera,
+                       const float* packed, int64_t first_pixel, int64_t num_pixels, float* colour, float* depth,
+                       float* acc, float* disparity, float min_transmittance, voxe_stream_t stream);
 
 /* The jitter the kernels generate for (render->rng_seed, render->rng_offset): out[R, S], for tests and replays. */
 VOXE_API int voxe_jitter_fill(const VoxeRenderDesc* render, float* out, int64_t num_rays, voxe_stream_t stream);

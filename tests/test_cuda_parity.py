@@ -281,7 +281,11 @@ def test_volumetric_model_render_matches_reference_golden():
     finally:
         rf.STRICT_REFERENCE_RNG = False
     assert chunked.colour.device.type == "cpu"
-    assert torch.equal(chunked.colour, out.colour.cpu()) and torch.equal(chunked.depth, out.depth.cpu())
+    # default route = whole-camera kernel (rays generated in-kernel, early termination at T < 1e-5); chunked route = the
+    # training kernels on cast_rays() tensors: same picture to rounding + the termination threshold
+    assert (chunked.colour - out.colour.cpu()).abs().max().item() <= 3e-5
+    assert (chunked.depth - out.depth.cpu()).abs().max().item() <= 2e-4
+    assert (chunked.colour - a["colour"]).abs().max().item() <= PIXEL_TOL
 
 
 def test_no_grad_and_partial_inputs():

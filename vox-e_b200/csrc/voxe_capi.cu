@@ -247,6 +247,42 @@ int voxe_render_fwd(const VoxeGridDesc* grid, const VoxeRenderDesc* render, cons
   return VOXE_OK;
 }
 
+int voxe_render_camera(const VoxeGridDesc* grid, const VoxeRenderDesc* render, const VoxeCameraDesc* camera,
+                       const float* packed, int64_t first_pixel, int64_t num_pixels, float* colour, float* depth,
+                       float* acc, float* disparity, float min_transmittance, voxe_stream_t stream) {
+  if (int rc = check_grid(grid)) return rc;
+  if (int rc = check_render(grid, render, nullptr, nullptr)) return rc;
+  if (!camera || camera->height < 1 || camera->width < 1 || !(camera->focal > 0.f))
+    return fail(VOXE_ERR_INVALID_ARGUMENT, "voxe_render_camera: camera needs height, width >= 1 and focal > 0");
+  if (render->noise_std != 0.f) return fail(VOXE_ERR_UNSUPPORTED, "voxe_render_camera does not take density noise; use voxe_render_fwd");
+  const int64_t total = (int64_t)camera->height * camera->width;
+  if (first_pixel < 0 || num_pixels < 0 || first_pixel + num_pixels > total || num_pixels > 0x7fffffff)
+    return fail(VOXE_ERR_INVALID_ARGUMENT, "voxe_render_camera: pixel range outside the %d x %d image", camera->height, camera->width);
+  if (num_pixels == 0) return VOXE_OK;
+  if (!packed || !colour || !depth || !acc) return fail(VOXE_ERR_INVALID_ARGUMENT, "voxe_render_camera: NULL buffer");
+  if (!(min_transmittance >= 0.f)) return fail(VOXE_ERR_INVALID_ARGUMENT, "voxe_render_camera: min_transmittance must be >= 0");
+  voxe::KParams p;
+  int regcap = 0;
+  if (int rc = fill_params(grid, render, num_pixels, p, regcap)) return rc;
+  p.grid = reinterpret_cast<const float4*>(packed);
+  p.colour = colour;
+  p.depth = depth;
+  p.acc = acc;
+  p.disp = disparity;
+  voxe::CameraParams cam;
+  cam.H = camera->height;
+  cam.W = camera->width;
+  cam.focal = camera->focal;
+  for (int k = 0; k < 9; ++k) cam.rot[k] = camera->rotation[k];
+  for (int k = 0; k < 3; ++k) cam.trans[k] = camera->translation[k];
+  cam.first_pixel = first_pixel;
+  cam.min_transmittance = min_transmittance;
+  cudaError_t e = voxe::launch_camera(p, cam, render->sh_degree, render->n_colour, (cudaStream_t)stream);
+  if (e != cudaSuccess) return cuda_fail(e, "voxe_render_camera launch");
+  g_launches.fetch_add(1);
+  return VOXE_OK;
+}
+
 int voxe_render_bwd(const VoxeGridDesc* grid, const VoxeRenderDesc* render, const float* packed,
                     const float* rays_o, const float* rays_d, const float* jitter, const float* noise,
                     const float* saved, const float* g_colour, const float* g_depth, const float* g_acc,

@@ -228,14 +228,8 @@ struct RayCtx {
   bool disparity;
 };
 
-__device__ __forceinline__ void load_ray(const KParams& p, int ray, RayCtx& rc) {
-  const float* po = p.rays_o + 3 * (size_t)ray;
-  const float* pd = p.rays_d + 3 * (size_t)ray;
-#pragma unroll
-  for (int a = 0; a < 3; ++a) {
-    rc.o[a] = __ldg(po + a);
-    rc.d[a] = __ldg(pd + a);
-  }
+// Everything derived from a ray's origin and direction (rc.o, rc.d already set).
+__device__ __forceinline__ void finish_ray(const KParams& p, RayCtx& rc) {
   ray_interval(p, rc.o, rc.d, rc.near, rc.far);
   rc.disparity = (p.flags & kDisparity) && !(p.flags & kAabb);  // renderers.py:66-78
   rc.inv_near = rc.inv_far = 0.f;
@@ -245,6 +239,27 @@ __device__ __forceinline__ void load_ray(const KParams& p, int ray, RayCtx& rc) 
   }
   rc.dnorm = sqrtf(rc.d[0] * rc.d[0] + rc.d[1] * rc.d[1] + rc.d[2] * rc.d[2]);
 }
+
+__device__ __forceinline__ void load_ray(const KParams& p, int ray, RayCtx& rc) {
+  const float* po = p.rays_o + 3 * (size_t)ray;
+  const float* pd = p.rays_d + 3 * (size_t)ray;
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    rc.o[a] = __ldg(po + a);
+    rc.d[a] = __ldg(pd + a);
+  }
+  finish_ray(p, rc);
+}
+
+// Pinhole camera of the whole-camera inference kernel (cast_rays, rendering/volumetric/utils/misc.py:12-50).
+struct CameraParams {
+  int H, W;
+  float focal;
+  float rot[9];    // camera-to-world rotation, row-major
+  float trans[3];  // camera position
+  long long first_pixel;  // flat pixel index (row * W + col) of ray 0 of this launch
+  float min_transmittance;  // early termination: stop a ray once T < this (0 = never)
+};
 
 // Conservative index range [a, b) of the samples of one ray that can lie inside the grid AABB.  Samples outside the
 // box contribute exactly nothing (sigma = 0 -> alpha = 0, process.py:80-91), so the kernels only distribute [a, b)

@@ -511,6 +511,93 @@ __global__ void __launch_bounds__(Bounds<REGCAP>::kThreads, Bounds<REGCAP>::kMin
   if constexpr (LT::CV > 1) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // staging slots die with the CTA
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// whole-camera inference
+// ---------------------------------------------------------------------------------------------------------
+// Forward-only render of a pinhole camera: one thread per pixel.  The ray is generated in the kernel from the pose and
+// the intrinsics (cast_rays, misc.py:12-50: pixel centres, dir = ((x+.5-W/2)/f, -(y+.5-H/2)/f, -1), d = R dir, not
+// normalised), so no ray tensors exist; the thread walks the ray's in-grid sample range front to back with a running
+// transmittance and may stop once T < min_transmittance (the remaining samples can change a pixel by less than that;
+// 0 disables it).  With a whole camera in one launch there are enough rays to fill the machine without splitting a ray
+// over threads, and the 32 lanes of a warp are 32 neighbouring pixels at the same depth index -- the most coherent gather
+// this volume layout can get.  Shares every device function with the training kernels; never used when a backward follows.
+template <int DEG, int NCOL>
+__global__ void __launch_bounds__(128, 5) render_camera_kernel(const __grid_constant__ KParams p, const __grid_constant__ CameraParams cam) {
+  using LT = Layout<DEG, NCOL>;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= p.R) return;
+  const long long pixel = cam.first_pixel + t;
+  const int row = (int)(pixel / cam.W), col = (int)(pixel - (long long)row * cam.W);
+  RayCtx rc;
+  {
+    const float dx = __fdiv_rn(__fsub_rn((float)col + 0.5f, (float)cam.W * 0.5f), cam.focal);
+    const float dy = -__fdiv_rn(__fsub_rn((float)row + 0.5f, (float)cam.H * 0.5f), cam.focal);
+    const float dz = -1.0f;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      rc.o[a] = cam.trans[a];
+      rc.d[a] = fmaf(cam.rot[3 * a + 2], dz, fmaf(cam.rot[3 * a + 1], dy, cam.rot[3 * a + 0] * dx));
+    }
+  }
+  finish_ray(p, rc);
+  int a, b;
+  sample_range(p, rc, a, b);
+  JitterSource u_row;
+  u_row.init(p, (int)t);
+  float Y[LT::K];
+  const float inv = 1.0f / rc.dnorm;
+  sh_basis<DEG>(rc.d[0] * inv, rc.d[1] * inv, rc.d[2] * inv, (p.flags & kDiffuse) != 0, Y);
+  float T = 1.f, V[LT::NV];
+#pragma unroll
+  for (int k = 0; k < LT::NV; ++k) V[k] = 0.f;
+  DepthWalker zw;
+  if (a < b) zw.init(p, rc, u_row, a);
+#pragma unroll(kSampleUnroll)
+  for (int i = a; i < b; ++i, zw.advance(p, rc, u_row, i - 1)) {
+    const float zi = zw.cur;
+    const float px = __fadd_rn(rc.o[0], __fmul_rn(rc.d[0], zi));
+    const float py = __fadd_rn(rc.o[1], __fmul_rn(rc.d[1], zi));
+    const float pz = __fadd_rn(rc.o[2], __fmul_rn(rc.d[2], zi));
+    const bool in = inside_aabb(p, px, py, pz);
+    Corners c;
+    make_corners(p, px, py, pz, c);
+    float raw[NCOL], dpost, col_k[NCOL];
+    unsigned signs;
+    const float sraw = gather_sample<DEG, NCOL>(p, c, Y, raw, signs);
+    const float sigma = in ? post_act(p.postact, sraw, dpost) : 0.f;
+#pragma unroll
+    for (int k = 0; k < NCOL; ++k) col_k[k] = in ? sigmoid_fast(raw[k]) : 0.f;
+    const float delta = ((i == p.S - 1) ? kInfinity : __fsub_rn(zw.next, zi)) * rc.dnorm;
+    const float alpha = 1.0f - exp_fast(-(sigma * delta));
+    const float w = alpha * T;
+#pragma unroll
+    for (int k = 0; k < NCOL; ++k) V[k] = fmaf(w, col_k[k], V[k]);
+    V[NCOL] = fmaf(w, zi, V[NCOL]);
+    V[NCOL + 1] += w;
+    T *= (1.0f - alpha);
+    if (T < cam.min_transmittance) break;
+  }
+  const float acc = V[NCOL + 1], depth = V[NCOL];
+  const bool white = (p.flags & kWhite) && !(p.flags & kAttn);
+#pragma unroll
+  for (int k = 0; k < NCOL; ++k) p.colour[(size_t)t * NCOL + k] = white ? V[k] + (1.0f - acc) : V[k];
+  p.depth[t] = depth;
+  p.acc[t] = acc;
+  if (p.disp != nullptr) {
+    const float q = depth / acc;
+    const float m = (q != q) ? q : fmaxf(kZeroPlus, q);
+    p.disp[t] = 1.0f / m;
+  }
+}
+
+template <int DEG, int NCOL>
+cudaError_t launch_camera_t(const KParams& p, const CameraParams& cam, cudaStream_t stream) {
+  const int threads = 128;
+  const long long blocks = ((long long)p.R + threads - 1) / threads;
+  render_camera_kernel<DEG, NCOL><<<(unsigned)blocks, threads, 0, stream>>>(p, cam);
+  return cudaGetLastError();
+}
+
 template <int DEG, int NCOL, int REGCAP>
 cudaError_t launch_pair(const KParams& p, bool backward, cudaStream_t stream) {
   using LT = Layout<DEG, NCOL>;
@@ -554,6 +641,17 @@ cudaError_t launch_render(const KParams& p, int deg, int ncol, int regcap, bool 
   if (regcap == 80) return dispatch_deg<80>(p, deg, ncol, backward, stream);
   if (regcap == 96) return dispatch_deg<96>(p, deg, ncol, backward, stream);
   return dispatch_deg<128>(p, deg, ncol, backward, stream);
+}
+
+cudaError_t launch_camera(const KParams& p, const CameraParams& cam, int deg, int ncol, cudaStream_t stream) {
+  if (ncol == 1) return deg == 0 ? launch_camera_t<0, 1>(p, cam, stream) : cudaErrorInvalidValue;
+  switch (deg) {
+    case 0: return launch_camera_t<0, 3>(p, cam, stream);
+    case 1: return launch_camera_t<1, 3>(p, cam, stream);
+    case 2: return launch_camera_t<2, 3>(p, cam, stream);
+    case 3: return launch_camera_t<3, 3>(p, cam, stream);
+  }
+  return cudaErrorInvalidValue;
 }
 
 int max_threads_per_cta(int regcap) {

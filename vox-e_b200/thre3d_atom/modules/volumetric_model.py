@@ -32,7 +32,7 @@ from thre3d_atom.thre3d_reprs.constants import (
     STATE_DICT,
     THRE3D_REPR,
 )
-from thre3d_atom.thre3d_reprs.renderers import RenderConfig, RenderProcedure, render_sh_voxel_grid_attn
+from thre3d_atom.thre3d_reprs.renderers import RenderConfig, RenderProcedure, render_sh_voxel_grid_attn, render_sh_voxel_grid_camera
 from thre3d_atom.utils.constants import EXTRA_INFO
 from thre3d_atom.utils.imaging_utils import CameraIntrinsics, CameraPose
 
@@ -125,7 +125,12 @@ class VolumetricModel:
         return fused and not rf.STRICT_REFERENCE_RNG and noise_std == 0.0
 
     def _render_camera(self, render_chunk, collate, reshape, camera_pose, camera_intrinsics, chunk_size, gpu_render, verbose,
-                       kwargs_noise_std=0.0, attn=False):
+                       kwargs_noise_std=0.0, attn=False, camera_fast_path=None):
+        if camera_fast_path is not None and self._whole_camera_in_one_launch(kwargs_noise_std, attn):
+            # fused procedure, nothing to differentiate: rays are generated inside the kernel and the camera is one launch
+            with torch.no_grad():
+                out = camera_fast_path()
+            return reshape(out if gpu_render else out.to(torch.device("cpu")), camera_intrinsics=camera_intrinsics)
         flat_rays = flatten_rays(cast_rays(camera_intrinsics=camera_intrinsics, pose=camera_pose, device=self._device))
         chunk_size = len(flat_rays) if chunk_size is None else chunk_size
         if self._whole_camera_in_one_launch(kwargs_noise_std, attn):
@@ -161,6 +166,8 @@ class VolumetricModel:
             collate_rendered_output, reshape_rendered_output,
             camera_pose, camera_intrinsics, parallel_rays_chunk_size, gpu_render, verbose,
             kwargs_noise_std=float(kwargs.get("stochastic_density_noise_std", getattr(self._render_config, "stochastic_density_noise_std", 0.0))),
+            camera_fast_path=lambda: render_sh_voxel_grid_camera(
+                self._thre3d_repr, camera_intrinsics, camera_pose, self._update_render_config(self._render_config, kwargs)),
         )
 
     def render_attn(

@@ -140,6 +140,22 @@ def render_sh_voxel_grid(
     return RenderOut(colour=colour, depth=depth, extra={EXTRA_DISPARITY: disparity, EXTRA_ACCUMULATED_WEIGHTS: acc})
 
 
+def render_sh_voxel_grid_camera(voxel_grid: VoxelGrid, camera_intrinsics, camera_pose, render_config: SHVoxGridRenderConfig) -> RenderOut:
+    """Whole-camera inference render for ``VolumetricModel.render`` (forward only, flat [H*W, .] outputs in
+    ``flatten_rays`` order): one kernel generates the rays (``cast_rays``) and renders them, see
+    ``voxe_b200.render_function.fused_render_camera``."""
+    from voxe_b200.render_function import fused_render_camera
+
+    features, densities = voxel_grid.features, voxel_grid.densities
+    spec = _render_spec(render_config, features.shape[-1], attn=False, per_call_sampling_flags=True)
+    height, width, focal = camera_intrinsics
+    colour, depth, acc, disparity = fused_render_camera(
+        voxel_grid.fused_spec(), spec, densities.detach(), features.detach(), height, width, focal, camera_pose.rotation,
+        camera_pose.translation, cache=voxel_grid.packed_cache(),
+    )
+    return RenderOut(colour=colour, depth=depth, extra={EXTRA_DISPARITY: disparity, EXTRA_ACCUMULATED_WEIGHTS: acc})
+
+
 def render_sh_voxel_grid_attn(
     voxel_grid: VoxelGrid,
     rays: Rays,

@@ -16,7 +16,7 @@ _lock = threading.Lock()
 _lib: Optional[ctypes.CDLL] = None
 
 # ---- enums of include/voxe.h -------------------------------------------------------------------------------
-ABI_VERSION = 7
+ABI_VERSION = 8
 PREACT_IDENTITY, PREACT_ABS = 0, 1
 POSTACT_IDENTITY, POSTACT_RELU, POSTACT_SOFTPLUS = 0, 1, 2
 FLAG_PERTURB, FLAG_AABB_SAMPLING, FLAG_DISPARITY_SAMPLING = 1, 2, 4
@@ -56,6 +56,11 @@ class VoxeRenderDesc(ctypes.Structure):
     ]
 
 
+class VoxeCameraDesc(ctypes.Structure):
+    _fields_ = [("height", ctypes.c_int32), ("width", ctypes.c_int32), ("focal", ctypes.c_float), ("rotation", ctypes.c_float * 9),
+                ("translation", ctypes.c_float * 3)]
+
+
 class VoxeAdamDesc(ctypes.Structure):
     _fields_ = [("lr", ctypes.c_double), ("beta1", ctypes.c_double), ("beta2", ctypes.c_double), ("eps", ctypes.c_double),
                 ("step", ctypes.c_int32)]
@@ -76,6 +81,8 @@ EXPORTS = {
     "voxe_adam_step": (ctypes.c_int, [_GD, ctypes.POINTER(VoxeAdamDesc), _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "voxe_saved_floats": (ctypes.c_int64, [_RD, ctypes.c_int64]),
     "voxe_render_fwd": (ctypes.c_int, [_GD, _RD, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, ctypes.c_int64, _P]),
+    "voxe_render_camera": (ctypes.c_int, [_GD, _RD, ctypes.POINTER(VoxeCameraDesc), _P, ctypes.c_int64, ctypes.c_int64, _P, _P, _P, _P,
+                                          ctypes.c_float, _P]),
     "voxe_render_bwd": (ctypes.c_int, [_GD, _RD, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, ctypes.c_int64, _P]),
     "voxe_set_tuning": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int]),
     "voxe_launch_count": (ctypes.c_int64, []),

@@ -320,6 +320,63 @@ def fused_render(
     return colour, depth, acc, disparity
 
 
+# Early termination of the whole-camera inference render (``fused_render_camera``): a ray stops once its transmittance
+# falls below this value; what the skipped samples could still add to a pixel is smaller than it (north-star pixel
+# tolerance: 1e-4).  0.0 evaluates every sample.  Never applied to renders that are differentiated.
+INFERENCE_MIN_TRANSMITTANCE = 1e-5
+
+
+def fused_render_camera(
+    gspec: FusedGridSpec,
+    rspec: FusedRenderSpec,
+    densities: Tensor,
+    features: Tensor,
+    height: int,
+    width: int,
+    focal: float,
+    rotation,
+    translation,
+    cache: Optional[PackedVolumeCache] = None,
+    first_pixel: int = 0,
+    num_pixels: Optional[int] = None,
+    generator: Optional[torch.Generator] = None,
+) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+    """Forward-only render of a pinhole camera through ``voxe_render_camera``: rays are generated inside the kernel
+    (``cast_rays``, misc.py:12-50), one launch for the pixel range.  Returns flat (colour [P,C], depth [P,1], acc [P,1],
+    disparity [P,1]) in ``flatten_rays`` order.  ``rotation`` [3,3] / ``translation`` [3] or [3,1]: tensors or arrays."""
+    dev = densities.device
+    if dev.type != "cuda":
+        _require_cuda(densities, features)
+    if rspec.noise_std != 0.0:
+        raise NotImplementedError("fused_render_camera does not take density noise; render rays through fused_render")
+    lib = nat.load_library()
+    packed = (cache or PackedVolumeCache()).get(gspec, densities, features)
+    total = int(height) * int(width)
+    num_pixels = total - first_pixel if num_pixels is None else int(num_pixels)
+    rot = np.asarray(rotation.detach().cpu() if isinstance(rotation, Tensor) else rotation, dtype=np.float32).reshape(3, 3)
+    trans = np.asarray(translation.detach().cpu() if isinstance(translation, Tensor) else translation, dtype=np.float32).reshape(3)
+    cam = nat.VoxeCameraDesc()
+    cam.height, cam.width, cam.focal = int(height), int(width), float(focal)
+    cam.rotation[:] = rot.reshape(-1).tolist()
+    cam.translation[:] = trans.tolist()
+    rd = nat.VoxeRenderDesc.from_buffer_copy(rspec.native_bytes())
+    if rspec.flags & nat.FLAG_PERTURB:  # in-kernel draws: (seed, offset) from the device generator, which is advanced
+        gen = generator if generator is not None else torch.cuda.default_generators[dev.index if dev.index is not None else torch.cuda.current_device()]
+        rd.rng_seed, rd.rng_offset = int(gen.initial_seed()) & (2**64 - 1), int(gen.get_offset())
+        gen.set_offset(gen.get_offset() + 4)
+    colour = torch.empty((num_pixels, rspec.n_colour), dtype=torch.float32, device=dev)
+    depth = torch.empty((num_pixels, 1), dtype=torch.float32, device=dev)
+    acc = torch.empty((num_pixels, 1), dtype=torch.float32, device=dev)
+    disp = torch.empty((num_pixels, 1), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        nat.check(
+            lib.voxe_render_camera(gspec.to_native(), rd, cam, packed.data_ptr(), int(first_pixel), num_pixels, colour.data_ptr(),
+                                   depth.data_ptr(), acc.data_ptr(), disp.data_ptr(), float(INFERENCE_MIN_TRANSMITTANCE), _stream_ptr(dev)),
+            "voxe_render_camera",
+        )
+    return colour, depth, acc, disp
+
+
 def fused_render_attn(*args, **kwargs):
     """Attention-grid twin (renderers.py:108-163): same kernels with VOXE_FLAG_ATTN set in the render spec and the
     1-channel attention volume passed as ``features``."""
