@@ -532,6 +532,48 @@ def e2e_leg(device, rank, world, steps, warmup, dist, deferred=False, engine_thr
             "one pinned H2D copy of rays + upstream gradients, one D2H copy of the rendered colours and the loss"}
 
 
+def inference_leg(device, frames=24):
+    """Rows f3/f4: ``VolumetricModel.render`` of the benchmark camera under no_grad.  The whole-camera kernel (rays
+    generated in-kernel, early termination at T < 1e-5) against the reference's structure of the same call -- cast_rays
+    tensors walked in 32768-ray chunks (modules/volumetric_model.py:170-186) through the training kernels."""
+    from thre3d_atom.modules.volumetric_model import VolumetricModel
+    from thre3d_atom.rendering.volumetric.utils.misc import cast_rays, flatten_rays
+    from thre3d_atom.thre3d_reprs.renderers import SHVoxGridRenderConfig, render_sh_voxel_grid
+    from thre3d_atom.thre3d_reprs.voxels import VoxelGrid, VoxelSize
+    from thre3d_atom.utils.imaging_utils import CameraBounds, CameraIntrinsics
+
+    dens, feat = make_grid_tensors(device)
+    grid = VoxelGrid(dens, feat, VoxelSize(*(w / d for w, d in zip(WL["world"], WL["dims"]))), density_preactivation=torch.nn.Identity(),
+                     density_postactivation=torch.nn.ReLU(), expected_density_scale=WL["density_scale"], tunable=False)
+    vm = VolumetricModel(grid, render_sh_voxel_grid,
+                         SHVoxGridRenderConfig(num_samples_per_ray=WL["S"], camera_bounds=CameraBounds(WL["near"], WL["far"]),
+                                               white_bkgd=True, perturb_sampled_points=False), device=device)
+    cam = CameraIntrinsics(WL["height"], WL["width"], WL["focal"])
+    poses = make_poses()
+
+    def chunked(pose):
+        rays = flatten_rays(cast_rays(cam, pose, device=device))
+        with torch.no_grad():
+            return [vm.render_rays(rays[s:s + 32768]).colour for s in range(0, len(rays), 32768)]
+
+    def timed(fn):
+        for k in range(3):
+            fn(poses[k % len(poses)])
+        torch.cuda.synchronize(device)
+        t0 = time.perf_counter()
+        for k in range(frames):
+            fn(poses[k % len(poses)])
+        torch.cuda.synchronize(device)
+        return (time.perf_counter() - t0) / frames
+
+    t_cam = timed(lambda pose: vm.render(pose, cam))
+    t_chunk = timed(chunked)
+    rays = WL["height"] * WL["width"]
+    return {"api": "VolumetricModel.render (no_grad), 400x400, S=256", "ms_per_frame": round(1e3 * t_cam, 3), "rays_per_s": rays / t_cam,
+            "chunked_ray_tensor_route": {"ms_per_frame": round(1e3 * t_chunk, 3), "rays_per_s": rays / t_chunk,
+                                         "note": "cast_rays + 32768-ray chunks through the training kernels (the structure of the reference's render())"}}
+
+
 def fused_step_leg(device, peak):
     """Row f2: the optimiser-step grid pass.  Fused kernel (consume packed grads + Adam + repack + zero) against the
     unfused sequence the reference-style loop runs (zero-fill, unpack, torch.optim.Adam.step, repack), CUDA events."""
@@ -748,6 +790,10 @@ def run_ours(args):
     if rank == 0 and world == 1 and args.workload == "cfg2":
         fused_step = fused_step_leg(device, peak)
 
+    inference = None
+    if rank == 0 and world == 1 and args.workload == "cfg2":
+        inference = inference_leg(device)
+
     if rank == 0:
         line = {
             "metric": "rays/s fwd+bwd, 160^3 SH-0 grid, 400x400 render", "value": rays_per_s, "unit": "rays/s", "n_gpus": world,
@@ -768,6 +814,8 @@ def run_ours(args):
             line["fused_step"] = fused_step
         if serialized:
             line["serialized"] = serialized
+        if inference:
+            line["inference"] = inference
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

@@ -171,6 +171,14 @@ VOXE_API int voxe_render_camera(const VoxeGridDesc* grid, const VoxeRenderDesc* 
                        const float* packed, int64_t first_pixel, int64_t num_pixels, float* colour, float* depth,
                        float* acc, float* disparity, float min_transmittance, voxe_stream_t stream);
 
+/* The same inference kernel on caller-supplied rays [R,3] (forward only, one thread per ray, early termination): for
+ * callers that already hold ray tensors, and for AABB-bound sampling (VOXE_FLAG_AABB_SAMPLING), where the first / last
+ * sample sits exactly on a grid face and the picture depends on the last bit of the ray direction -- the rays must then
+ * be the very tensors cast_rays produced.  `jitter` [R,S] or NULL as in voxe_render_fwd. */
+VOXE_API int voxe_render_infer(const VoxeGridDesc* grid, const VoxeRenderDesc* render, const float* packed,
+                      const float* rays_o, const float* rays_d, const float* jitter, float* colour, float* depth,
+                      float* acc, float* disparity, int64_t num_rays, float min_transmittance, voxe_stream_t stream);
+
 /* The jitter the kernels generate for (render->rng_seed, render->rng_offset): out[R, S], for tests and replays. */
 VOXE_API int voxe_jitter_fill(const VoxeRenderDesc* render, float* out, int64_t num_rays, voxe_stream_t stream);
 

@@ -283,6 +283,36 @@ int voxe_render_camera(const VoxeGridDesc* grid, const VoxeRenderDesc* render, c
   return VOXE_OK;
 }
 
+int voxe_render_infer(const VoxeGridDesc* grid, const VoxeRenderDesc* render, const float* packed, const float* rays_o,
+                      const float* rays_d, const float* jitter, float* colour, float* depth, float* acc, float* disparity,
+                      int64_t num_rays, float min_transmittance, voxe_stream_t stream) {
+  if (int rc = check_grid(grid)) return rc;
+  if (int rc = check_render(grid, render, jitter, nullptr)) return rc;
+  if (render->noise_std != 0.f) return fail(VOXE_ERR_UNSUPPORTED, "voxe_render_infer does not take density noise; use voxe_render_fwd");
+  if (num_rays < 0 || num_rays > 0x7fffffff) return fail(VOXE_ERR_INVALID_ARGUMENT, "num_rays out of range");
+  if (num_rays == 0) return VOXE_OK;
+  if (!packed || !rays_o || !rays_d || !colour || !depth || !acc) return fail(VOXE_ERR_INVALID_ARGUMENT, "voxe_render_infer: NULL buffer");
+  if (!(min_transmittance >= 0.f)) return fail(VOXE_ERR_INVALID_ARGUMENT, "voxe_render_infer: min_transmittance must be >= 0");
+  voxe::KParams p;
+  int regcap = 0;
+  if (int rc = fill_params(grid, render, num_rays, p, regcap)) return rc;
+  p.grid = reinterpret_cast<const float4*>(packed);
+  p.rays_o = rays_o;
+  p.rays_d = rays_d;
+  p.jitter = (render->flags & VOXE_FLAG_PERTURB) ? jitter : nullptr;
+  p.colour = colour;
+  p.depth = depth;
+  p.acc = acc;
+  p.disp = disparity;
+  voxe::CameraParams cam{};
+  cam.W = 1;
+  cam.min_transmittance = min_transmittance;
+  cudaError_t e = voxe::launch_camera(p, cam, render->sh_degree, render->n_colour, (cudaStream_t)stream);
+  if (e != cudaSuccess) return cuda_fail(e, "voxe_render_infer launch");
+  g_launches.fetch_add(1);
+  return VOXE_OK;
+}
+
 int voxe_render_bwd(const VoxeGridDesc* grid, const VoxeRenderDesc* render, const float* packed,
                     const float* rays_o, const float* rays_d, const float* jitter, const float* noise,
                     const float* saved, const float* g_colour, const float* g_depth, const float* g_acc,

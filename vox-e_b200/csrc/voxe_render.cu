@@ -527,9 +527,11 @@ __global__ void __launch_bounds__(128, 5) render_camera_kernel(const __grid_cons
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= p.R) return;
   const long long pixel = cam.first_pixel + t;
-  const int row = (int)(pixel / cam.W), col = (int)(pixel - (long long)row * cam.W);
+  const int row = (int)(pixel / max(cam.W, 1)), col = (int)(pixel - (long long)row * cam.W);
   RayCtx rc;
-  {
+  if (p.rays_o != nullptr) {  // caller-supplied rays (bit-identical geometry to the training kernels), see voxe_render_infer
+    load_ray(p, (int)t, rc);
+  } else {
     const float dx = __fdiv_rn(__fsub_rn((float)col + 0.5f, (float)cam.W * 0.5f), cam.focal);
     const float dy = -__fdiv_rn(__fsub_rn((float)row + 0.5f, (float)cam.H * 0.5f), cam.focal);
     const float dz = -1.0f;
@@ -538,8 +540,8 @@ __global__ void __launch_bounds__(128, 5) render_camera_kernel(const __grid_cons
       rc.o[a] = cam.trans[a];
       rc.d[a] = fmaf(cam.rot[3 * a + 2], dz, fmaf(cam.rot[3 * a + 1], dy, cam.rot[3 * a + 0] * dx));
     }
+    finish_ray(p, rc);
   }
-  finish_ray(p, rc);
   int a, b;
   sample_range(p, rc, a, b);
   JitterSource u_row;

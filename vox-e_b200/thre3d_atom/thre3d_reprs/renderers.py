@@ -144,15 +144,25 @@ def render_sh_voxel_grid_camera(voxel_grid: VoxelGrid, camera_intrinsics, camera
     """Whole-camera inference render for ``VolumetricModel.render`` (forward only, flat [H*W, .] outputs in
     ``flatten_rays`` order): one kernel generates the rays (``cast_rays``) and renders them, see
     ``voxe_b200.render_function.fused_render_camera``."""
-    from voxe_b200.render_function import fused_render_camera
+    from thre3d_atom.rendering.volumetric.utils.misc import cast_rays, flatten_rays
+    from voxe_b200.render_function import fused_render_camera, fused_render_infer
 
     features, densities = voxel_grid.features, voxel_grid.densities
     spec = _render_spec(render_config, features.shape[-1], attn=False, per_call_sampling_flags=True)
     height, width, focal = camera_intrinsics
-    colour, depth, acc, disparity = fused_render_camera(
-        voxel_grid.fused_spec(), spec, densities.detach(), features.detach(), height, width, focal, camera_pose.rotation,
-        camera_pose.translation, cache=voxel_grid.packed_cache(),
-    )
+    if render_config.optimized_sampling:
+        # AABB-bound sampling puts the first / last sample exactly on a grid face, and the last bit of the ray direction
+        # decides whether it counts as inside (DESIGN.md section 3): use the very tensors cast_rays produces
+        rays = flatten_rays(cast_rays(camera_intrinsics, camera_pose, device=densities.device))
+        colour, depth, acc, disparity = fused_render_infer(
+            voxel_grid.fused_spec(), spec, densities.detach(), features.detach(), rays.origins, rays.directions,
+            cache=voxel_grid.packed_cache(),
+        )
+    else:
+        colour, depth, acc, disparity = fused_render_camera(
+            voxel_grid.fused_spec(), spec, densities.detach(), features.detach(), height, width, focal, camera_pose.rotation,
+            camera_pose.translation, cache=voxel_grid.packed_cache(),
+        )
     return RenderOut(colour=colour, depth=depth, extra={EXTRA_DISPARITY: disparity, EXTRA_ACCUMULATED_WEIGHTS: acc})
 
 

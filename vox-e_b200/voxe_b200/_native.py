@@ -83,6 +83,7 @@ EXPORTS = {
     "voxe_render_fwd": (ctypes.c_int, [_GD, _RD, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, ctypes.c_int64, _P]),
     "voxe_render_camera": (ctypes.c_int, [_GD, _RD, ctypes.POINTER(VoxeCameraDesc), _P, ctypes.c_int64, ctypes.c_int64, _P, _P, _P, _P,
                                           ctypes.c_float, _P]),
+    "voxe_render_infer": (ctypes.c_int, [_GD, _RD, _P, _P, _P, _P, _P, _P, _P, _P, ctypes.c_int64, ctypes.c_float, _P]),
     "voxe_render_bwd": (ctypes.c_int, [_GD, _RD, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, ctypes.c_int64, _P]),
     "voxe_set_tuning": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int]),
     "voxe_launch_count": (ctypes.c_int64, []),

@@ -377,6 +377,48 @@ def fused_render_camera(
     return colour, depth, acc, disp
 
 
+def fused_render_infer(gspec: FusedGridSpec, rspec: FusedRenderSpec, densities: Tensor, features: Tensor, rays_o: Tensor,
+                       rays_d: Tensor, cache: Optional[PackedVolumeCache] = None, jitter: Optional[Tensor] = None,
+                       generator: Optional[torch.Generator] = None) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+    """Forward-only render of caller-supplied flat rays through the inference kernel (``voxe_render_infer``: one thread
+    per ray, early termination at ``INFERENCE_MIN_TRANSMITTANCE``).  Same outputs as ``fused_render``; nothing to
+    differentiate."""
+    dev = densities.device
+    if dev.type != "cuda" or rays_o.device != dev:
+        _require_cuda(densities, features, rays_o, rays_d)
+    if rspec.noise_std != 0.0:
+        raise NotImplementedError("fused_render_infer does not take density noise; render rays through fused_render")
+    rays_o, rays_d = _prep_rays(rays_o, rays_d)
+    rays_o, rays_d = rays_o.detach().contiguous(), rays_d.detach().contiguous()
+    lib = nat.load_library()
+    packed = (cache or PackedVolumeCache()).get(gspec, densities, features)
+    R = rays_o.shape[0]
+    rd = nat.VoxeRenderDesc.from_buffer_copy(rspec.native_bytes())
+    if rspec.flags & nat.FLAG_PERTURB:
+        if jitter is not None:
+            assert jitter.shape == (R, rspec.num_samples)
+            jitter = jitter.detach().float().contiguous()
+        else:
+            gen = generator if generator is not None else torch.cuda.default_generators[dev.index if dev.index is not None else torch.cuda.current_device()]
+            rd.rng_seed, rd.rng_offset = int(gen.initial_seed()) & (2**64 - 1), int(gen.get_offset())
+            gen.set_offset(gen.get_offset() + 4)
+    else:
+        jitter = None
+    colour = torch.empty((R, rspec.n_colour), dtype=torch.float32, device=dev)
+    depth = torch.empty((R, 1), dtype=torch.float32, device=dev)
+    acc = torch.empty((R, 1), dtype=torch.float32, device=dev)
+    disp = torch.empty((R, 1), dtype=torch.float32, device=dev)
+    if R:
+        with torch.cuda.device(dev):
+            nat.check(
+                lib.voxe_render_infer(gspec.to_native(), rd, packed.data_ptr(), rays_o.data_ptr(), rays_d.data_ptr(), _ptr(jitter),
+                                      colour.data_ptr(), depth.data_ptr(), acc.data_ptr(), disp.data_ptr(), R,
+                                      float(INFERENCE_MIN_TRANSMITTANCE), _stream_ptr(dev)),
+                "voxe_render_infer",
+            )
+    return colour, depth, acc, disp
+
+
 def fused_render_attn(*args, **kwargs):
     """Attention-grid twin (renderers.py:108-163): same kernels with VOXE_FLAG_ATTN set in the render spec and the
     1-channel attention volume passed as ``features``."""
