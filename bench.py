@@ -489,11 +489,11 @@ def e2e_leg(device, rank, world, steps, warmup, dist, deferred=False, engine_thr
         d = d_h.to(device, non_blocking=True)
         gc = g_h.to(device, non_blocking=True)
         colours = []
-        for s in range(0, R, B):
-            out = vm.render_rays(Rays(o[s : s + B], d[s : s + B]))
+        for o_b, d_b, g_b in zip(o.split(B), d.split(B), gc.split(B)):  # 4096-ray batches (views, no copies)
+            out = vm.render_rays(Rays(o_b, d_b))
             # loss = <colour, G>: the upstream gradient is handed to autograd directly, as the SDS step does
             # (thre3d_reprs/sd.py:20-34 SpecifyGradient)
-            out.colour.backward(gc[s : s + B])
+            out.colour.backward(g_b)
             colours.append(out.colour.detach())
         colour = torch.cat(colours)
         loss_total = (colour * gc).sum()
