@@ -89,3 +89,30 @@ def test_pixel_ranges_tile_the_image_and_jitter_is_reproducible():
         assert torch.equal(f[1000:1777], q)
     with pytest.raises(Exception):
         rf.fused_render_camera(*args2, cache=g2.packed_cache(), first_pixel=48 * 52 - 10, num_pixels=11)
+
+
+@pytest.mark.parametrize("overrides,hw", [
+    (dict(num_samples_per_ray=2), (9, 7)),
+    (dict(linear_disparity_sampling=True), (31, 29)),
+    (dict(render_diffuse=True, white_bkgd=False), (31, 29)),
+    (dict(num_samples_per_ray=513), (1, 1)),
+    (dict(num_samples_per_ray=1024, white_bkgd=False), (17, 40)),
+])
+def test_camera_kernel_config_corners(overrides, hw):
+    """Every sample evaluated (no early termination): sampling modes, tiny / odd sample counts, 1x1 images."""
+    import voxe_b200.render_function as rf
+    from thre3d_atom.utils.imaging_utils import CameraIntrinsics, pose_spherical
+
+    vm = _model(deg=1)
+    cam, pose = CameraIntrinsics(hw[0], hw[1], 40.0), pose_spherical(-120.0, -35.0, 4.0311)
+    want = _rays_route(vm, pose, cam, **overrides)
+    saved = rf.INFERENCE_MIN_TRANSMITTANCE
+    try:
+        rf.INFERENCE_MIN_TRANSMITTANCE = 0.0
+        got = vm.render(pose, cam, **overrides)
+    finally:
+        rf.INFERENCE_MIN_TRANSMITTANCE = saved
+    assert got.colour.shape == (hw[0], hw[1], 3)
+    assert (got.colour.reshape(-1, 3) - want.colour).abs().max().item() <= 2e-5
+    assert (got.extra["accumulated_weight"].reshape(-1, 1) - want.extra["accumulated_weight"]).abs().max().item() <= 2e-5
+    assert (got.depth.reshape(-1, 1) - want.depth).abs().max().item() <= 3e-4

@@ -229,16 +229,28 @@ class VoxelGrid(Module):
     # ------------------------------------------------------------------------------------------------------
     # bridge to the fused kernels
     # ------------------------------------------------------------------------------------------------------
+    # attributes a FusedGridSpec is derived from: assigning any of them drops the cached descriptions (render calls ask
+    # for the description every time, and looking these up through nn.Module's attribute machinery costs more than the
+    # rest of the call's Python)
+    _SPEC_INPUTS = frozenset({
+        "_density_preactivation", "_density_postactivation", "_feature_preactivation", "_feature_postactivation", "_aabb",
+        "_expected_density_scale", "width_x", "depth_y", "height_z", "_features", "attn", "_grid_location", "_voxel_size",
+    })
+
+    def __setattr__(self, name, value):
+        if name in VoxelGrid._SPEC_INPUTS:
+            self.__dict__.pop("_fused_spec_cache", None)
+        super().__setattr__(name, value)
+
     def fused_spec(self, n_features: Optional[int] = None) -> FusedGridSpec:
         """Describe this grid to the CUDA kernels; rejects activations the kernels do not fuse."""
-        nf = int(self._features.shape[-1]) if n_features is None else int(n_features)
-        key = (nf, id(self._density_preactivation), id(self._density_postactivation), id(self._feature_preactivation),
-               id(self._feature_postactivation), self._aabb, self._expected_density_scale, self.grid_dims)
-        cached = getattr(self, "_fused_spec_cache", None)
-        if cached is not None and cached[0] == key:
-            return cached[1]
-        spec = self._build_fused_spec(nf)
-        self._fused_spec_cache = (key, spec)
+        cache = self.__dict__.get("_fused_spec_cache")
+        if cache is None:
+            cache = self.__dict__["_fused_spec_cache"] = {}
+        spec = cache.get(n_features)
+        if spec is None:
+            nf = int(self._features.shape[-1]) if n_features is None else int(n_features)
+            spec = cache[n_features] = self._build_fused_spec(nf)
         return spec
 
     def _build_fused_spec(self, n_features: int) -> FusedGridSpec:
