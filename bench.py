@@ -803,7 +803,8 @@ def run_ours(args):
                        + (" + 1 NCCL all-reduce of packed voxel grads" if world > 1 else ""),
                        "batches_in_flight": f"{bench.n_lanes} (each launch is one <=4096-ray batch with its own workspace; gradients accumulate "
                                             "over the frame, so batch k+1's forward does not wait for batch k's backward)",
-                       "l2": "3 rotating grid copies (197 MB) + 65.5 MB gradient volume > 126 MB L2; 8 poses rotate",
+                       "l2": f"{bench.N_GRID_COPIES} rotating packed-volume copies ({bench.N_GRID_COPIES * bench.packed[0].numel() * 4 / 1e6:.0f} MB) + "
+                             f"{bench.packed_grad.numel() * 4 / 1e6:.0f} MB gradient volume + per-batch workspaces > 126 MB L2; {len(bench.poses)} poses rotate",
                        "parallelism": f"ray/view data parallel x{world}", "timing": "CUDA events around K graph replays, max over ranks",
                        "host_cpus_per_rank": len(pinned_cpus) if pinned_cpus else "unpinned"},
             "e2e": e2e, "gpu_launches": args.steps * bench.kernels_per_step, "roofline": roof, "clocks": clocks,
