@@ -638,6 +638,70 @@ def fused_step_leg(device, peak):
             "unfused_us": round(unfused_us, 1), "unfused": "unpack(+=) + zero-fill + torch.optim.Adam.step + repack + grad zero", "packed_floats": channels}
 
 
+def regularizers_leg(device, peak):
+    """Row f2: the per-step regularisers of the edit loop on the benchmark grid -- density-correlation loss (weight 200 by
+    default in the reference's edit script) and total variation of ReLU(densities) and of the features -- loss + gradient
+    accumulated into .grad, against the same formulas as torch ops on the same GPU (the reference's code path:
+    sds_trainer.py:290-326 + autograd).  CUDA events, mean of 20."""
+    from voxe_b200 import regularizers as reg
+
+    def timed(fn, n=20, warm=3, graph=False):
+        """Mean time of fn() in us, CUDA events.  graph=True: n calls captured into one CUDA graph and replayed, i.e. the
+        kernels back to back without the Python / ctypes time of the call (which exceeds the kernels' at this grid size)."""
+        for _ in range(warm):
+            fn()
+        run = lambda: [fn() for _ in range(n)]  # noqa: E731
+        if graph:
+            g = torch.cuda.CUDAGraph()
+            side = torch.cuda.Stream(device)
+            side.wait_stream(torch.cuda.current_stream(device))
+            with torch.cuda.stream(side), torch.cuda.graph(g, stream=side):
+                run()
+            torch.cuda.current_stream(device).wait_stream(side)
+            run = g.replay
+            run()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(device)
+        a.record()
+        run()
+        b.record()
+        torch.cuda.synchronize(device)
+        return 1e3 * a.elapsed_time(b) / n  # us
+
+    dens, feat = make_grid_tensors(device)
+    pre = (dens + 0.1 * torch.randn_like(dens)).contiguous()
+    dens, feat = torch.nn.Parameter(dens), torch.nn.Parameter(feat)
+    dens.grad, feat.grad = torch.zeros_like(dens), torch.zeros_like(feat)
+
+    def tv_torch(g):
+        return (g.diff(dim=0).abs().mean() + g.diff(dim=1).abs().mean() + g.diff(dim=2).abs().mean()) / 3
+
+    def corr_torch(a, b):  # sds_trainer.py:507-524
+        cov = (a - torch.mean(a)) * (b - torch.mean(b))
+        den = torch.sqrt(torch.mean((a - torch.mean(a)) ** 2) * torch.mean((b - torch.mean(b)) ** 2))
+        return 1.0 - torch.mean(cov / (den + 1e-7))
+
+    out = {}
+    cases = [
+        ("density_correlation", lambda: reg.accumulate_density_loss_gradient(dens, pre, 200.0),
+         lambda: (corr_torch(dens, pre) * 200.0).backward(), 4.0 * dens.numel() * (2 + 2 + 2)),  # stats: a,b; grad: a,b + .grad rmw
+        ("tv_relu_densities", lambda: reg.accumulate_tv_gradient(dens, 1.0, relu=True),
+         lambda: tv_torch(torch.relu(dens)).backward(), 4.0 * dens.numel() * 3),  # grid read + .grad rmw
+        ("tv_features", lambda: reg.accumulate_tv_gradient(feat, 1.0),
+         lambda: tv_torch(feat).backward(), 4.0 * feat.numel() * 3),
+    ]
+    for name, ours, theirs, nbytes in cases:
+        call_us = timed(ours)
+        us = timed(ours, graph=True)
+        torch_us = timed(theirs, n=5, warm=2)
+        out[name] = {"us": round(us, 1), "call_us": round(call_us, 1), "torch_ops_us": round(torch_us, 1), "bytes": int(nbytes),
+                     "achieved": round(nbytes / (us * 1e-6) / 1e9, 1), "unit": "GB/s", "frac": round(nbytes / (us * 1e-6) / 1e9 / peak, 4)}
+    out["note"] = ("loss + weight * gradient accumulated into .grad (voxe_pair_loss + voxe_pair_loss_grad / voxe_tv_regularizer); "
+                   "us = kernels back to back (graph replay), call_us = through the Python call; "
+                   "torch_ops_us = the reference's formulas as torch ops + autograd on the same GPU")
+    return out
+
+
 def run_ours(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -794,6 +858,10 @@ def run_ours(args):
     if rank == 0 and world == 1 and args.workload == "cfg2":
         inference = inference_leg(device)
 
+    regularizers = None
+    if rank == 0 and world == 1 and args.workload == "cfg2":
+        regularizers = regularizers_leg(device, peak)
+
     if rank == 0:
         line = {
             "metric": "rays/s fwd+bwd, 160^3 SH-0 grid, 400x400 render", "value": rays_per_s, "unit": "rays/s", "n_gpus": world,
@@ -817,6 +885,8 @@ def run_ours(args):
             line["serialized"] = serialized
         if inference:
             line["inference"] = inference
+        if regularizers:
+            line["regularizers"] = regularizers
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

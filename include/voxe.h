@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define VOXE_ABI_VERSION 8
+#define VOXE_ABI_VERSION 9
 
 #if defined(__GNUC__)
 #define VOXE_API __attribute__((visibility("default")))
@@ -212,6 +212,36 @@ typedef struct VoxeAdamDesc {
 VOXE_API int voxe_adam_step(const VoxeGridDesc* grid, const VoxeAdamDesc* adam, float* densities, float* features,
                             float* packed, float* packed_grad, const float* dense_d_densities,
                             const float* dense_d_features, float* packed_m, float* packed_v, voxe_stream_t stream);
+
+/* ---- per-step full-grid regularisers of the edit loop --------------------------------------------
+ * `workspace` is VOXE_REG_WORKSPACE_DOUBLES doubles of device memory owned by the caller (per-CTA partial sums of the
+ * reductions -- no atomics, so a loss is bitwise reproducible -- and, for the pair loss, the statistics its gradient call
+ * reads back; it needs no initialisation); `loss` is ONE device float.  `upstream` (one device float,
+ * dL/dloss as autograd hands it over; NULL = 1) and the host scalar `scale` (a loss weight) multiply the gradient, which
+ * is ADDED into `grad` when accumulate != 0 and overwrites it otherwise. */
+#define VOXE_REG_WORKSPACE_DOUBLES 8192
+
+/* Total-variation loss of a channel-last grid [X,Y,Z,C] and/or its gradient, one streaming pass:
+ *   loss = (mean|diff_x h| + mean|diff_y h| + mean|diff_z h|) / 3,  h = relu ? max(grid, 0) : grid
+ * -- `_tv_loss_on_grid` (thre3d_atom/modules/sds_trainer.py:563-567, attn_grid_trainer.py:659-663, grid_refine.py:709-713)
+ * as applied to ReLU(_densities) and _features at sds_trainer.py:318-326 and to the attention grids at
+ * attn_grid_trainer.py:361-366.  `loss` NULL: gradient only; `grad` NULL: loss only; both: one pass for both.  An axis of
+ * extent 1 makes the loss NaN (torch's mean over an empty tensor) and contributes no gradient. */
+VOXE_API int voxe_tv_regularizer(const float* grid, const int32_t dims[3], int32_t channels, int32_t relu, double* workspace,
+                                 float* loss, const float* upstream, float scale, float* grad, int32_t accumulate,
+                                 voxe_stream_t stream);
+
+/* Loss between the edited density grid `a` and the frozen pretrained one `b` (n floats each):
+ *   VOXE_PAIR_CORRELATION  1 - mean((a-mean a)(b-mean b)) / (sqrt(var a * var b) + 1e-7)   `_density_correlation_loss`,
+ *                          sds_trainer.py:507-524; `correlation_grid` (n floats or NULL) receives its second return value
+ *   VOXE_PAIR_L2 / _L1     mse_loss / l1_loss(a, b)                                        sds_trainer.py:498-503
+ * voxe_pair_loss_grad writes dloss/da; in correlation mode it reads the statistics voxe_pair_loss left in `workspace`
+ * (same a, b), so call it after voxe_pair_loss on the same stream. */
+enum { VOXE_PAIR_CORRELATION = 0, VOXE_PAIR_L2 = 1, VOXE_PAIR_L1 = 2 };
+VOXE_API int voxe_pair_loss(const float* a, const float* b, int64_t n, int32_t mode, double* workspace, float* loss,
+                            float* correlation_grid, voxe_stream_t stream);
+VOXE_API int voxe_pair_loss_grad(const float* a, const float* b, int64_t n, int32_t mode, const double* workspace,
+                                 const float* upstream, float scale, float* grad, int32_t accumulate, voxe_stream_t stream);
 
 /* Launch-shape override for tuning runs: samples per thread (1..64; the number of depth segments per ray is
  * ceil(S / samples_per_thread)), rays per CTA (power of two <= 32) and the register budget of the kernel variant

@@ -218,6 +218,50 @@ int voxe_adam_step(const VoxeGridDesc* grid, const VoxeAdamDesc* adam, float* de
   return VOXE_OK;
 }
 
+int voxe_tv_regularizer(const float* grid, const int32_t dims[3], int32_t channels, int32_t relu, double* workspace,
+                        float* loss, const float* upstream, float scale, float* grad, int32_t accumulate, voxe_stream_t stream) {
+  if (!grid || !dims) return fail(VOXE_ERR_INVALID_ARGUMENT, "voxe_tv_regularizer: NULL grid / dims");
+  if (dims[0] < 1 || dims[1] < 1 || dims[2] < 1 || channels < 1)
+    return fail(VOXE_ERR_INVALID_ARGUMENT, "voxe_tv_regularizer: dims and channels must be >= 1");
+  if ((int64_t)dims[2] * channels > 0x7fffffff || (int64_t)dims[0] * dims[1] > 0x7fffffff)
+    return fail(VOXE_ERR_UNSUPPORTED, "voxe_tv_regularizer: grid rows out of range");
+  if (!loss && !grad) return VOXE_OK;
+  if (loss && !workspace) return fail(VOXE_ERR_INVALID_ARGUMENT, "voxe_tv_regularizer: the loss needs the workspace");
+  const int d[3] = {dims[0], dims[1], dims[2]};
+  int launches = 0;
+  cudaError_t e = voxe::launch_tv(grid, d, channels, relu != 0, workspace, loss, upstream, scale, grad, accumulate != 0,
+                                  (cudaStream_t)stream, &launches);
+  g_launches.fetch_add(launches);
+  if (e != cudaSuccess) return cuda_fail(e, "voxe_tv_regularizer launch");
+  return VOXE_OK;
+}
+
+int voxe_pair_loss(const float* a, const float* b, int64_t n, int32_t mode, double* workspace, float* loss,
+                   float* correlation_grid, voxe_stream_t stream) {
+  if (!a || !b || !workspace || !loss) return fail(VOXE_ERR_INVALID_ARGUMENT, "voxe_pair_loss: NULL buffer");
+  if (n < 1) return fail(VOXE_ERR_INVALID_ARGUMENT, "voxe_pair_loss: n must be >= 1");
+  if (mode < VOXE_PAIR_CORRELATION || mode > VOXE_PAIR_L1) return fail(VOXE_ERR_INVALID_ARGUMENT, "voxe_pair_loss: unknown mode %d", mode);
+  int launches = 0;
+  cudaError_t e = voxe::launch_pair_loss(a, b, n, mode, 1e-7f, workspace, loss, correlation_grid, (cudaStream_t)stream, &launches);
+  g_launches.fetch_add(launches);
+  if (e != cudaSuccess) return cuda_fail(e, "voxe_pair_loss launch");
+  return VOXE_OK;
+}
+
+int voxe_pair_loss_grad(const float* a, const float* b, int64_t n, int32_t mode, const double* workspace, const float* upstream,
+                        float scale, float* grad, int32_t accumulate, voxe_stream_t stream) {
+  if (!a || !b || !grad) return fail(VOXE_ERR_INVALID_ARGUMENT, "voxe_pair_loss_grad: NULL buffer");
+  if (n < 1) return fail(VOXE_ERR_INVALID_ARGUMENT, "voxe_pair_loss_grad: n must be >= 1");
+  if (mode < VOXE_PAIR_CORRELATION || mode > VOXE_PAIR_L1)
+    return fail(VOXE_ERR_INVALID_ARGUMENT, "voxe_pair_loss_grad: unknown mode %d", mode);
+  if (mode == VOXE_PAIR_CORRELATION && !workspace)
+    return fail(VOXE_ERR_INVALID_ARGUMENT, "voxe_pair_loss_grad: correlation mode reads the workspace voxe_pair_loss filled");
+  cudaError_t e = voxe::launch_pair_grad(a, b, n, mode, 1e-7f, workspace, upstream, scale, grad, accumulate != 0, (cudaStream_t)stream);
+  if (e != cudaSuccess) return cuda_fail(e, "voxe_pair_loss_grad launch");
+  g_launches.fetch_add(1);
+  return VOXE_OK;
+}
+
 int voxe_render_fwd(const VoxeGridDesc* grid, const VoxeRenderDesc* render, const float* packed,
                     const float* rays_o, const float* rays_d, const float* jitter, const float* noise,
                     float* colour, float* depth, float* acc, float* disparity, float* saved, int64_t num_rays,

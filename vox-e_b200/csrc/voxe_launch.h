@@ -29,4 +29,12 @@ cudaError_t launch_adam_step(float* packed, float* packed_grad, float* packed_m,
                              float* features, const float* dense_gd, const float* dense_gf, const int dims[3], int n_features,
                              int channels, double lr, double beta1, double beta2, double eps, int step, cudaStream_t stream);
 
+// per-step regularisers (voxe_regularizers.cu); *launches = kernels enqueued
+cudaError_t launch_tv(const float* grid, const int dims[3], int channels, bool relu, double* workspace, float* loss,
+                      const float* upstream, float scale, float* grad, bool accumulate, cudaStream_t stream, int* launches);
+cudaError_t launch_pair_loss(const float* a, const float* b, int64_t n, int mode, float eps, double* workspace, float* loss,
+                             float* corr_grid, cudaStream_t stream, int* launches);
+cudaError_t launch_pair_grad(const float* a, const float* b, int64_t n, int mode, float eps, const double* workspace,
+                             const float* upstream, float scale, float* grad, bool accumulate, cudaStream_t stream);
+
 }  // namespace voxe

@@ -1,0 +1,356 @@
+// voxe_regularizers.cu -- the per-step full-grid regularisers of Vox-E's edit loop as streaming kernels (sm_100a).
+//
+// SURVEY.md row f2.  The reference evaluates, once per optimiser step and over the WHOLE grid (sds_trainer.py:290-326):
+//   * the density-correlation loss between the edited and the pretrained density grid (sds_trainer.py:494-524;
+//     weight 200 by default, edit_pretrained_relu_field.py:171) or its L2 / L1 variants (:498-503), and
+//   * total-variation losses on ReLU(_densities) and on _features (sds_trainer.py:318-326, :563-567; the same function
+//     regularises the attention grids, attn_grid_trainer.py:659, grid_refine.py:709),
+// each as ~10-25 elementwise / reduction launches over [X,Y,Z,C] tensors plus their autograd backward.  Here a loss is
+// one read of the grid (+ one 3-to-5-value reduction) and its gradient is one more read fused with the accumulation
+// into the dense gradient: pure HBM streams.
+#include <cmath>
+#include <cstdint>
+
+#include "voxe_launch.h"
+
+namespace voxe {
+namespace {
+
+__device__ __forceinline__ float sgn(float d) { return (float)(d > 0.f) - (float)(d < 0.f); }  // torch.sign: 0 at 0
+
+constexpr int kMaxCtas = 148 * 8;   // persistent launch: one wave of 8 resident 256-thread CTAs per SM
+constexpr int kPrefetch = 6;       // iterations (of 256 elements per CTA) the TV kernel prefetches ahead into L2
+constexpr int kPartials = 16;       // workspace: [0, 16) results / statistics, then N partial sums per CTA
+
+// Block-reduce N per-thread doubles and store them as this CTA's partial sums (no atomics: 25 600 same-address double
+// atomics cost more than the whole streaming pass, and per-CTA slots make the loss bitwise reproducible).
+template <int N>
+__device__ __forceinline__ void block_store(double (&val)[N], double* __restrict__ ws) {
+  __shared__ double part[N][8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < N; ++k) {
+    double v = val[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) part[k][warp] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < N) {
+    double v = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) v += part[threadIdx.x][w];
+    ws[kPartials + (size_t)blockIdx.x * N + threadIdx.x] = v;
+  }
+}
+
+// Sum the per-CTA partials (one CTA of 256 threads): thread 0 returns with the N totals.
+template <int N>
+__device__ __forceinline__ void gather_partials(const double* __restrict__ ws, int n_ctas, double (&tot)[N]) {
+  __shared__ double part[N][8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < N; ++k) {
+    double v = 0.0;
+    for (int c = threadIdx.x; c < n_ctas; c += blockDim.x) v += ws[kPartials + (size_t)c * N + k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) part[k][warp] = v;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < N; ++k) {
+    double v = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) v += part[k][w];
+    tot[k] = v;
+  }
+}
+
+// ---- total variation -------------------------------------------------------------------------------------------
+// grid [X,Y,Z,C], z fastest, channels innermost, taken as X*Y rows of Z*C contiguous floats.  Persistent launch: CTA b
+// owns the flat element span [b * chunk, (b+1) * chunk); its threads walk the span 256 elements at a time, so every load
+// instruction of a warp is one contiguous 128-byte request, and each thread carries its (x, y, offset-in-row) along
+// incrementally (no divisions in the loop).  An element's six axis neighbours sit at +-C (z), +-Z*C (y), +-Y*Z*C (x):
+// the z neighbours are the same lines in L1, the y / x neighbours are lines other CTAs stream at the same time (L2), so
+// DRAM sees the grid once.
+//   loss  = (mean|d_x h| + mean|d_y h| + mean|d_z h|) / 3,  h = RELU ? max(g, 0) : g      (sds_trainer.py:563-567)
+//   dloss/dg[v] = [g[v] > 0] * sum_a 1/(3 n_a) * (sign(h[v] - h[v-1_a]) - sign(h[v+1_a] - h[v]))
+template <bool RELU, bool DO_SUM, bool DO_GRAD>
+__global__ void __launch_bounds__(256) tv_kernel(const float* __restrict__ g, float* __restrict__ grad, double* __restrict__ ws,
+                                                 int X, int Y, int ZC, int C, int64_t sx, int64_t total, int64_t chunk,
+                                                 float cx, float cy, float cz, const float* __restrict__ upstream, int accumulate) {
+  const int64_t begin = (int64_t)blockIdx.x * chunk;
+  const int64_t end = begin + chunk < total ? begin + chunk : total;
+  int64_t idx = begin + threadIdx.x;
+  int64_t row = idx / ZC;
+  int e = (int)(idx - row * ZC);
+  int x = (int)(row / Y), y = (int)(row - (int64_t)x * Y);
+  float up = 1.f;
+  if (DO_GRAD && upstream) up = __ldg(upstream);
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+  for (; idx < end; idx += 256) {
+    // Branch-free: a missing neighbour (grid face) reads the element itself, so its difference -- and with it |d| and
+    // sign(d) -- is exactly 0; all loads of an iteration are independent and issued up front.
+    const float* r = g + idx;
+    // A thread touches 4 fresh bytes of the grid (and of the gradient) per iteration -- far too little in flight to cover
+    // DRAM latency even at full occupancy (measured: 1.8 TB/s).  So each warp pulls the lines it will need kPrefetch
+    // iterations from now into L2; the loads below then see L2 latency only.
+    if (idx + kPrefetch * 256 < end) {
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(r + kPrefetch * 256));
+      if (DO_GRAD && accumulate) asm volatile("prefetch.global.L2 [%0];" ::"l"(grad + idx + kPrefetch * 256));
+    }
+    float old = 0.f;
+    if (DO_GRAD && accumulate) old = grad[idx];
+    const float raw = __ldg(r);
+    float zp = __ldg(e + C < ZC ? r + C : r);
+    float yp = __ldg(y < Y - 1 ? r + ZC : r);
+    float xp = __ldg(x < X - 1 ? r + sx : r);
+    float zm = raw, ym = raw, xm = raw;
+    if (DO_GRAD) {
+      zm = __ldg(e >= C ? r - C : r);
+      ym = __ldg(y > 0 ? r - ZC : r);
+      xm = __ldg(x > 0 ? r - sx : r);
+    }
+    float v = raw;
+    if (RELU) {
+      v = fmaxf(raw, 0.f);
+      zp = fmaxf(zp, 0.f); yp = fmaxf(yp, 0.f); xp = fmaxf(xp, 0.f);
+      zm = fmaxf(zm, 0.f); ym = fmaxf(ym, 0.f); xm = fmaxf(xm, 0.f);
+    }
+    const float dzp = zp - v, dyp = yp - v, dxp = xp - v;
+    if (DO_SUM) {
+      s2 += fabsf(dzp);
+      s1 += fabsf(dyp);
+      s0 += fabsf(dxp);
+    }
+    if (DO_GRAD) {
+      const float gz = sgn(v - zm) - sgn(dzp), gy = sgn(v - ym) - sgn(dyp), gx = sgn(v - xm) - sgn(dxp);
+      float t = (cx * gx + cy * gy + cz * gz) * up;
+      if (RELU && !(raw > 0.f)) t = 0.f;
+      grad[idx] = old + t;
+    }
+    e += 256;  // advance (x, y, e) with the flat index
+    while (e >= ZC) {
+      e -= ZC;
+      if (++y == Y) {
+        y = 0;
+        ++x;
+      }
+    }
+  }
+  if (DO_SUM) {
+    double v[3] = {(double)s0, (double)s1, (double)s2};
+    block_store<3>(v, ws);
+  }
+}
+
+__global__ void __launch_bounds__(256) tv_finalize_kernel(const double* __restrict__ ws, int n_ctas, float* __restrict__ loss,
+                                                          double n0, double n1, double n2) {
+  double tot[3];
+  gather_partials<3>(ws, n_ctas, tot);
+  if (threadIdx.x != 0) return;
+  // mean over an empty difference tensor (an axis of extent 1) is NaN in torch; 0/0 reproduces that
+  const float m0 = (float)(tot[0] / n0), m1 = (float)(tot[1] / n1), m2 = (float)(tot[2] / n2);
+  *loss = (m0 + m1 + m2) / 3.f;
+}
+
+// ---- density correlation / L2 / L1 between two grids --------------------------------------------------------------
+// workspace doubles: [5] mean_a, [6] mean_b, [7] var_a, [8] var_b, [9] cov, [10] sqrt(var_a*var_b); per-CTA partials from 16 on
+enum { kCorr = 0, kL2 = 1, kL1 = 2 };
+
+template <int MODE>
+__device__ __forceinline__ void pair_accumulate(float xf, float yf, double (&acc)[5]) {
+  if (MODE == kCorr) {
+    const double x = (double)xf, y = (double)yf;
+    acc[0] += x;
+    acc[1] += y;
+    acc[2] = fma(x, x, acc[2]);
+    acc[3] = fma(y, y, acc[3]);
+    acc[4] = fma(x, y, acc[4]);
+  } else if (MODE == kL2) {
+    const double d = (double)(xf - yf);  // the fp32 difference the reference squares
+    acc[0] = fma(d, d, acc[0]);
+  } else {
+    acc[0] += (double)fabsf(xf - yf);
+  }
+}
+
+// n4 = number of whole float4 groups the vector loop covers (0 when the pointers are not 16-byte aligned)
+template <int MODE>
+__global__ void __launch_bounds__(256) pair_stats_kernel(const float* __restrict__ a, const float* __restrict__ b, int64_t n,
+                                                         int64_t n4, double* __restrict__ sums) {
+  double acc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x, t0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const float4* a4 = reinterpret_cast<const float4*>(a);
+  const float4* b4 = reinterpret_cast<const float4*>(b);
+  for (int64_t i = t0; i < n4; i += stride) {
+    const float4 x = __ldg(a4 + i), y = __ldg(b4 + i);
+    pair_accumulate<MODE>(x.x, y.x, acc);
+    pair_accumulate<MODE>(x.y, y.y, acc);
+    pair_accumulate<MODE>(x.z, y.z, acc);
+    pair_accumulate<MODE>(x.w, y.w, acc);
+  }
+  for (int64_t i = 4 * n4 + t0; i < n; i += stride) pair_accumulate<MODE>(__ldg(a + i), __ldg(b + i), acc);
+  block_store<5>(acc, sums);
+}
+
+__global__ void __launch_bounds__(256) pair_finalize_kernel(double* __restrict__ ws, int n_ctas, float* __restrict__ loss, double n,
+                                                            int mode, float eps) {
+  double tot[5];
+  gather_partials<5>(ws, n_ctas, tot);
+  if (threadIdx.x != 0) return;
+  if (mode != kCorr) {
+    *loss = (float)(tot[0] / n);
+    return;
+  }
+  const double ma = tot[0] / n, mb = tot[1] / n;
+  const double va = fmax(tot[2] / n - ma * ma, 0.0), vb = fmax(tot[3] / n - mb * mb, 0.0);
+  const double cov = tot[4] / n - ma * mb;
+  const double d = sqrt(va * vb);
+  ws[5] = ma; ws[6] = mb; ws[7] = va; ws[8] = vb; ws[9] = cov; ws[10] = d;
+  // 1 - mean(covariance_grid / (denominator + eps))                                   (sds_trainer.py:520-524)
+  *loss = 1.f - (float)(cov / (d + (double)eps));
+}
+
+// correlation_grid = (a - mean_a)(b - mean_b) / (denominator + eps): the second return value of the reference function
+__global__ void __launch_bounds__(256) corr_grid_kernel(const float* __restrict__ a, const float* __restrict__ b, int64_t n,
+                                                        const double* __restrict__ ws, float* __restrict__ out, float eps) {
+  const float ma = (float)ws[5], mb = (float)ws[6];
+  const float inv = 1.f / ((float)ws[10] + eps);
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    out[i] = (__ldg(a + i) - ma) * (__ldg(b + i) - mb) * inv;
+}
+
+// dloss/da.  Correlation mode, with D = d + eps, d = sqrt(var_a var_b):
+//   dloss/da_i = -[(b_i - mean_b) / D - cov * var_b * (a_i - mean_a) / (D^2 d)] / n
+template <int MODE>
+__global__ void __launch_bounds__(256) pair_grad_kernel(const float* __restrict__ a, const float* __restrict__ b, int64_t n,
+                                                        int64_t n4, const double* __restrict__ ws, const float* __restrict__ upstream,
+                                                        float scale, float eps, float* __restrict__ grad, int accumulate) {
+  float up = scale;
+  if (upstream) up *= __ldg(upstream);
+  float k1 = 0.f, k2 = 0.f, ma = 0.f, mb = 0.f;
+  if (MODE == kCorr) {
+    const double d = ws[10], D = d + (double)eps, cov = ws[9], vb = ws[8];
+    ma = (float)ws[5];
+    mb = (float)ws[6];
+    k1 = (float)(-(double)up / (D * (double)n));
+    k2 = (float)((double)up * cov * vb / (D * D * d * (double)n));  // d == 0 (a constant grid): inf / NaN, as autograd's
+  } else if (MODE == kL2) {
+    k1 = (float)(2.0 * (double)up / (double)n);
+  } else {
+    k1 = (float)((double)up / (double)n);
+  }
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x, t0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  auto one = [&](float x, float y) -> float {
+    if (MODE == kCorr) return k1 * (y - mb) + k2 * (x - ma);
+    if (MODE == kL2) return k1 * (x - y);
+    return k1 * sgn(x - y);
+  };
+  const float4* a4 = reinterpret_cast<const float4*>(a);
+  const float4* b4 = reinterpret_cast<const float4*>(b);
+  float4* g4 = reinterpret_cast<float4*>(grad);
+  for (int64_t i = t0; i < n4; i += stride) {
+    const float4 x = __ldg(a4 + i), y = __ldg(b4 + i);
+    float4 o = accumulate ? g4[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+    o.x += one(x.x, y.x);
+    o.y += one(x.y, y.y);
+    o.z += one(x.z, y.z);
+    o.w += one(x.w, y.w);
+    g4[i] = o;
+  }
+  for (int64_t i = 4 * n4 + t0; i < n; i += stride) {
+    const float t = one(__ldg(a + i), __ldg(b + i));
+    grad[i] = accumulate ? (grad[i] + t) : t;
+  }
+}
+
+// whole float4 groups a vector loop may cover: all of them when every pointer is 16-byte aligned, none otherwise
+int64_t vec_groups(int64_t n, const void* p0, const void* p1, const void* p2) {
+  const uintptr_t bits = (uintptr_t)p0 | (uintptr_t)p1 | (uintptr_t)p2;
+  return (bits & 15) ? 0 : n / 4;
+}
+
+int stream_blocks(int64_t n) {
+  const int64_t want = (n + 255) / 256;
+  const int64_t cap = kMaxCtas;  // threads stride over the rest
+  return (int)(want < cap ? (want > 0 ? want : 1) : cap);
+}
+
+}  // namespace
+
+cudaError_t launch_tv(const float* grid, const int dims[3], int channels, bool relu, double* workspace, float* loss,
+                      const float* upstream, float scale, float* grad, bool accumulate, cudaStream_t stream, int* launches) {
+  const int X = dims[0], Y = dims[1], Z = dims[2], C = channels;
+  const int ZC = Z * C;
+  const double per = (double)C;
+  const double n0 = (double)(X - 1) * Y * Z * per, n1 = (double)X * (Y - 1) * Z * per, n2 = (double)X * Y * (Z - 1) * per;
+  const float cx = X > 1 ? (float)((double)scale / (3.0 * n0)) : 0.f;
+  const float cy = Y > 1 ? (float)((double)scale / (3.0 * n1)) : 0.f;
+  const float cz = Z > 1 ? (float)((double)scale / (3.0 * n2)) : 0.f;
+  const int64_t total = (int64_t)X * Y * ZC;
+  const int n_ctas = stream_blocks(total);
+  const int64_t chunk = (((total + n_ctas - 1) / n_ctas + 255) / 256) * 256;  // whole 256-element strides per CTA
+  cudaError_t e = cudaSuccess;
+  *launches = 0;
+#define VOXE_TV_LAUNCH(R_, S_, G_)                                                                                       \
+  tv_kernel<R_, S_, G_><<<n_ctas, 256, 0, stream>>>(grid, grad, workspace, X, Y, ZC, C, (int64_t)Y * ZC, total, chunk, cx, cy, \
+                                                    cz, upstream, accumulate ? 1 : 0)
+  const bool do_sum = loss != nullptr, do_grad = grad != nullptr;
+  if (relu) {
+    if (do_sum && do_grad) VOXE_TV_LAUNCH(true, true, true);
+    else if (do_sum) VOXE_TV_LAUNCH(true, true, false);
+    else VOXE_TV_LAUNCH(true, false, true);
+  } else {
+    if (do_sum && do_grad) VOXE_TV_LAUNCH(false, true, true);
+    else if (do_sum) VOXE_TV_LAUNCH(false, true, false);
+    else VOXE_TV_LAUNCH(false, false, true);
+  }
+#undef VOXE_TV_LAUNCH
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  ++*launches;
+  if (loss) {
+    tv_finalize_kernel<<<1, 256, 0, stream>>>(workspace, n_ctas, loss, n0, n1, n2);
+    e = cudaGetLastError();
+    if (e == cudaSuccess) ++*launches;
+  }
+  return e;
+}
+
+cudaError_t launch_pair_loss(const float* a, const float* b, int64_t n, int mode, float eps, double* workspace, float* loss,
+                             float* corr_grid, cudaStream_t stream, int* launches) {
+  *launches = 0;
+  cudaError_t e = cudaSuccess;
+  const int64_t n4 = vec_groups(n, a, b, nullptr);
+  const int blocks = stream_blocks(n4 ? n4 : n);
+  if (mode == kCorr) pair_stats_kernel<kCorr><<<blocks, 256, 0, stream>>>(a, b, n, n4, workspace);
+  else if (mode == kL2) pair_stats_kernel<kL2><<<blocks, 256, 0, stream>>>(a, b, n, n4, workspace);
+  else pair_stats_kernel<kL1><<<blocks, 256, 0, stream>>>(a, b, n, n4, workspace);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  ++*launches;
+  pair_finalize_kernel<<<1, 256, 0, stream>>>(workspace, blocks, loss, (double)n, mode, eps);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  ++*launches;
+  if (corr_grid && mode == kCorr) {
+    corr_grid_kernel<<<blocks, 256, 0, stream>>>(a, b, n, workspace, corr_grid, eps);
+    e = cudaGetLastError();
+    if (e == cudaSuccess) ++*launches;
+  }
+  return e;
+}
+
+cudaError_t launch_pair_grad(const float* a, const float* b, int64_t n, int mode, float eps, const double* workspace,
+                             const float* upstream, float scale, float* grad, bool accumulate, cudaStream_t stream) {
+  const int64_t n4 = vec_groups(n, a, b, grad);
+  const int blocks = stream_blocks(n4 ? n4 : n);
+  const int acc = accumulate ? 1 : 0;
+  if (mode == kCorr) pair_grad_kernel<kCorr><<<blocks, 256, 0, stream>>>(a, b, n, n4, workspace, upstream, scale, eps, grad, acc);
+  else if (mode == kL2) pair_grad_kernel<kL2><<<blocks, 256, 0, stream>>>(a, b, n, n4, workspace, upstream, scale, eps, grad, acc);
+  else pair_grad_kernel<kL1><<<blocks, 256, 0, stream>>>(a, b, n, n4, workspace, upstream, scale, eps, grad, acc);
+  return cudaGetLastError();
+}
+
+}  // namespace voxe

@@ -16,11 +16,13 @@ _lock = threading.Lock()
 _lib: Optional[ctypes.CDLL] = None
 
 # ---- enums of include/voxe.h -------------------------------------------------------------------------------
-ABI_VERSION = 8
+ABI_VERSION = 9
 PREACT_IDENTITY, PREACT_ABS = 0, 1
 POSTACT_IDENTITY, POSTACT_RELU, POSTACT_SOFTPLUS = 0, 1, 2
 FLAG_PERTURB, FLAG_AABB_SAMPLING, FLAG_DISPARITY_SAMPLING = 1, 2, 4
 FLAG_WHITE_BKGD, FLAG_RENDER_DIFFUSE, FLAG_ATTN = 8, 16, 32
+PAIR_CORRELATION, PAIR_L2, PAIR_L1 = 0, 1, 2
+REG_WORKSPACE_DOUBLES = 8192
 
 
 class NativeLibraryError(RuntimeError):
@@ -85,6 +87,10 @@ EXPORTS = {
                                           ctypes.c_float, _P]),
     "voxe_render_infer": (ctypes.c_int, [_GD, _RD, _P, _P, _P, _P, _P, _P, _P, _P, ctypes.c_int64, ctypes.c_float, _P]),
     "voxe_render_bwd": (ctypes.c_int, [_GD, _RD, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, ctypes.c_int64, _P]),
+    "voxe_tv_regularizer": (ctypes.c_int, [_P, ctypes.POINTER(ctypes.c_int32 * 3), ctypes.c_int32, ctypes.c_int32, _P, _P, _P,
+                                           ctypes.c_float, _P, ctypes.c_int32, _P]),
+    "voxe_pair_loss": (ctypes.c_int, [_P, _P, ctypes.c_int64, ctypes.c_int32, _P, _P, _P, _P]),
+    "voxe_pair_loss_grad": (ctypes.c_int, [_P, _P, ctypes.c_int64, ctypes.c_int32, _P, _P, ctypes.c_float, _P, ctypes.c_int32, _P]),
     "voxe_set_tuning": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int]),
     "voxe_launch_count": (ctypes.c_int64, []),
 }
