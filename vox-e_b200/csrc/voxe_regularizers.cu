@@ -143,6 +143,115 @@ __global__ void __launch_bounds__(256) tv_kernel(const float* __restrict__ g, fl
   }
 }
 
+// Vector variant (rows of Z*C floats with Z*C % 4 == 0, 16-byte aligned buffers -- every grid the renderer packs):
+// a thread owns FOUR consecutive floats of a row per iteration, so the index / predicate arithmetic is paid once per 16
+// bytes and every load is a 16-byte one (the scalar kernel above spends ~110 instructions per float and is issue-bound at
+// 2 TB/s).  The y / x neighbours of an aligned group are aligned groups.  The z neighbours sit +-C floats away:
+//   ZMODE 1..3  C = ZMODE: they lie in the window [previous group | own group | next group]
+//   ZMODE 4     C % 4 == 0: aligned groups at +-C
+//   ZMODE 0     any other C: eight scalar loads
+// A neighbour beyond a grid face is replaced by the element itself (difference exactly 0), as in the scalar kernel.
+template <bool RELU, bool DO_SUM, bool DO_GRAD, int ZMODE>
+__global__ void __launch_bounds__(256) tv_vec_kernel(const float* __restrict__ g, float* __restrict__ grad, double* __restrict__ ws,
+                                                     int X, int Y, int GR, int C, int64_t sxg, int64_t total_g, int64_t chunk,
+                                                     float cx, float cy, float cz, const float* __restrict__ upstream,
+                                                     int accumulate) {
+  const float4* g4 = reinterpret_cast<const float4*>(g);
+  float4* grad4 = reinterpret_cast<float4*>(grad);
+  const int64_t begin = (int64_t)blockIdx.x * chunk;
+  const int64_t end = begin + chunk < total_g ? begin + chunk : total_g;
+  int64_t idx = begin + threadIdx.x;  // group index
+  int64_t row = idx / GR;
+  int eg = (int)(idx - row * GR);
+  int x = (int)(row / Y), y = (int)(row - (int64_t)x * Y);
+  const int ZC = 4 * GR;
+  float up = 1.f;
+  if (DO_GRAD && upstream) up = __ldg(upstream);
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+  for (; idx < end; idx += 256) {
+    const float4* r = g4 + idx;
+    if (idx + kPrefetch * 256 < end) {
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(r + kPrefetch * 256));
+      if (DO_GRAD && accumulate) asm volatile("prefetch.global.L2 [%0];" ::"l"(grad4 + idx + kPrefetch * 256));
+    }
+    float4 old4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (DO_GRAD && accumulate) old4 = grad4[idx];
+    const float4 own4 = __ldg(r);
+    const float4 yp4 = __ldg(y < Y - 1 ? r + GR : r), xp4 = __ldg(x < X - 1 ? r + sxg : r);
+    float4 ym4 = own4, xm4 = own4;
+    if (DO_GRAD) {
+      ym4 = __ldg(y > 0 ? r - GR : r);
+      xm4 = __ldg(x > 0 ? r - sxg : r);
+    }
+    float own[4] = {own4.x, own4.y, own4.z, own4.w};
+    float zp[4], zm[4];
+    const int e0 = 4 * eg;
+    if (ZMODE >= 1 && ZMODE <= 3) {
+      const float4 nx4 = __ldg(eg < GR - 1 ? r + 1 : r);
+      float4 pv4 = own4;
+      if (DO_GRAD) pv4 = __ldg(eg > 0 ? r - 1 : r);
+      const float w[12] = {pv4.x, pv4.y, pv4.z, pv4.w, own4.x, own4.y, own4.z, own4.w, nx4.x, nx4.y, nx4.z, nx4.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        zp[k] = (e0 + k + ZMODE < ZC) ? w[4 + k + ZMODE] : own[k];
+        zm[k] = (e0 + k >= ZMODE) ? w[4 + k - ZMODE] : own[k];
+      }
+    } else if (ZMODE == 4) {
+      const int cg = C >> 2;
+      const float4 a4 = __ldg(eg + cg < GR ? r + cg : r);
+      float4 b4 = own4;
+      if (DO_GRAD) b4 = __ldg(eg >= cg ? r - cg : r);
+      zp[0] = a4.x; zp[1] = a4.y; zp[2] = a4.z; zp[3] = a4.w;
+      zm[0] = b4.x; zm[1] = b4.y; zm[2] = b4.z; zm[3] = b4.w;
+    } else {
+      const float* rs = g + 4 * idx;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        zp[k] = __ldg(e0 + k + C < ZC ? rs + k + C : rs + k);
+        zm[k] = DO_GRAD ? __ldg(e0 + k >= C ? rs + k - C : rs + k) : own[k];
+      }
+    }
+    const float yp[4] = {yp4.x, yp4.y, yp4.z, yp4.w}, ym[4] = {ym4.x, ym4.y, ym4.z, ym4.w};
+    const float xp[4] = {xp4.x, xp4.y, xp4.z, xp4.w}, xm[4] = {xm4.x, xm4.y, xm4.z, xm4.w};
+    float out[4] = {old4.x, old4.y, old4.z, old4.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float raw = own[k];
+      float v = raw, a = zp[k], b = yp[k], c = xp[k], d = zm[k], e = ym[k], f = xm[k];
+      if (RELU) {
+        v = fmaxf(v, 0.f);
+        a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); c = fmaxf(c, 0.f);
+        d = fmaxf(d, 0.f); e = fmaxf(e, 0.f); f = fmaxf(f, 0.f);
+      }
+      const float dzp = a - v, dyp = b - v, dxp = c - v;
+      if (DO_SUM) {
+        s2 += fabsf(dzp);
+        s1 += fabsf(dyp);
+        s0 += fabsf(dxp);
+      }
+      if (DO_GRAD) {
+        const float gz = sgn(v - d) - sgn(dzp), gy = sgn(v - e) - sgn(dyp), gx = sgn(v - f) - sgn(dxp);
+        float t = (cx * gx + cy * gy + cz * gz) * up;
+        if (RELU && !(raw > 0.f)) t = 0.f;
+        out[k] += t;
+      }
+    }
+    if (DO_GRAD) grad4[idx] = make_float4(out[0], out[1], out[2], out[3]);
+    eg += 256;  // advance (x, y, eg) with the group index
+    while (eg >= GR) {
+      eg -= GR;
+      if (++y == Y) {
+        y = 0;
+        ++x;
+      }
+    }
+  }
+  if (DO_SUM) {
+    double v[3] = {(double)s0, (double)s1, (double)s2};
+    block_store<3>(v, ws);
+  }
+}
+
 __global__ void __launch_bounds__(256) tv_finalize_kernel(const double* __restrict__ ws, int n_ctas, float* __restrict__ loss,
                                                           double n0, double n1, double n2) {
   double tot[3];
@@ -271,9 +380,9 @@ int64_t vec_groups(int64_t n, const void* p0, const void* p1, const void* p2) {
   return (bits & 15) ? 0 : n / 4;
 }
 
-int stream_blocks(int64_t n) {
+int stream_blocks(int64_t n, int ctas_per_sm = 8) {
   const int64_t want = (n + 255) / 256;
-  const int64_t cap = kMaxCtas;  // threads stride over the rest
+  const int64_t cap = 148 * ctas_per_sm;  // <= kMaxCtas; threads stride over the rest
   return (int)(want < cap ? (want > 0 ? want : 1) : cap);
 }
 
@@ -289,24 +398,49 @@ cudaError_t launch_tv(const float* grid, const int dims[3], int channels, bool r
   const float cy = Y > 1 ? (float)((double)scale / (3.0 * n1)) : 0.f;
   const float cz = Z > 1 ? (float)((double)scale / (3.0 * n2)) : 0.f;
   const int64_t total = (int64_t)X * Y * ZC;
-  const int n_ctas = stream_blocks(total);
-  const int64_t chunk = (((total + n_ctas - 1) / n_ctas + 255) / 256) * 256;  // whole 256-element strides per CTA
+  const bool vec = (ZC % 4 == 0) && vec_groups(4, grid, grad, nullptr) != 0;
+  const int64_t units = vec ? total / 4 : total;  // float4 groups or floats
+  const int n_ctas = stream_blocks(units, vec ? 4 : 8);  // the vector kernel holds 57 registers: 4 resident CTAs per SM
+  const int64_t chunk = (((units + n_ctas - 1) / n_ctas + 255) / 256) * 256;  // whole 256-unit strides per CTA
   cudaError_t e = cudaSuccess;
   *launches = 0;
+  const bool do_sum = loss != nullptr, do_grad = grad != nullptr;
+  const int acc = accumulate ? 1 : 0;
+  if (vec) {
+    const int zmode = C <= 3 ? C : (C % 4 == 0 ? 4 : 0);
+#define VOXE_TV_VEC(R_, S_, G_, Z_)                                                                                          \
+  tv_vec_kernel<R_, S_, G_, Z_><<<n_ctas, 256, 0, stream>>>(grid, grad, workspace, X, Y, ZC / 4, C, (int64_t)Y * (ZC / 4), units, \
+                                                            chunk, cx, cy, cz, upstream, acc)
+#define VOXE_TV_VEC_Z(R_, S_, G_)              \
+  switch (zmode) {                             \
+    case 1: VOXE_TV_VEC(R_, S_, G_, 1); break; \
+    case 2: VOXE_TV_VEC(R_, S_, G_, 2); break; \
+    case 3: VOXE_TV_VEC(R_, S_, G_, 3); break; \
+    case 4: VOXE_TV_VEC(R_, S_, G_, 4); break; \
+    default: VOXE_TV_VEC(R_, S_, G_, 0);       \
+  }
+    if (relu) {
+      if (do_sum && do_grad) { VOXE_TV_VEC_Z(true, true, true) } else if (do_sum) { VOXE_TV_VEC_Z(true, true, false) } else { VOXE_TV_VEC_Z(true, false, true) }
+    } else {
+      if (do_sum && do_grad) { VOXE_TV_VEC_Z(false, true, true) } else if (do_sum) { VOXE_TV_VEC_Z(false, true, false) } else { VOXE_TV_VEC_Z(false, false, true) }
+    }
+#undef VOXE_TV_VEC_Z
+#undef VOXE_TV_VEC
+  } else {
 #define VOXE_TV_LAUNCH(R_, S_, G_)                                                                                       \
   tv_kernel<R_, S_, G_><<<n_ctas, 256, 0, stream>>>(grid, grad, workspace, X, Y, ZC, C, (int64_t)Y * ZC, total, chunk, cx, cy, \
-                                                    cz, upstream, accumulate ? 1 : 0)
-  const bool do_sum = loss != nullptr, do_grad = grad != nullptr;
-  if (relu) {
-    if (do_sum && do_grad) VOXE_TV_LAUNCH(true, true, true);
-    else if (do_sum) VOXE_TV_LAUNCH(true, true, false);
-    else VOXE_TV_LAUNCH(true, false, true);
-  } else {
-    if (do_sum && do_grad) VOXE_TV_LAUNCH(false, true, true);
-    else if (do_sum) VOXE_TV_LAUNCH(false, true, false);
-    else VOXE_TV_LAUNCH(false, false, true);
-  }
+                                                    cz, upstream, acc)
+    if (relu) {
+      if (do_sum && do_grad) VOXE_TV_LAUNCH(true, true, true);
+      else if (do_sum) VOXE_TV_LAUNCH(true, true, false);
+      else VOXE_TV_LAUNCH(true, false, true);
+    } else {
+      if (do_sum && do_grad) VOXE_TV_LAUNCH(false, true, true);
+      else if (do_sum) VOXE_TV_LAUNCH(false, true, false);
+      else VOXE_TV_LAUNCH(false, false, true);
+    }
 #undef VOXE_TV_LAUNCH
+  }
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   ++*launches;
