@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define VOXE_ABI_VERSION 9
+#define VOXE_ABI_VERSION 10
 
 #if defined(__GNUC__)
 #define VOXE_API __attribute__((visibility("default")))
@@ -242,6 +242,31 @@ VOXE_API int voxe_pair_loss(const float* a, const float* b, int64_t n, int32_t m
                             float* correlation_grid, voxe_stream_t stream);
 VOXE_API int voxe_pair_loss_grad(const float* a, const float* b, int64_t n, int32_t mode, const double* workspace,
                                  const float* upstream, float scale, float* grad, int32_t accumulate, voxe_stream_t stream);
+
+/* ---- training-side ray-batch sampling ---------------------------------------------------------------
+ * Replaces `sample_random_rays_and_pixels_synchronously` (thre3d_atom/rendering/volumetric/utils/misc.py:126-138, called
+ * every iteration at thre3d_atom/modules/trainers.py:311) and the per-view `cast_rays` + `collate_rays` that feed it
+ * (trainers.py:290-301; misc.py:12-50): `sample_size` threads each take the i-th element of a keyed pseudo-random
+ * permutation of [0, num_pixels) -- distinct indices, like `torch.randperm(N)[:sample_size]`, without the O(N) shuffle --
+ * and produce that pixel's ray and colour.
+ *   camera mode (poses != NULL)   poses [B,3,4] = [R | t] per image (the dataset's pose matrices, trainers.py:293-295);
+ *                                 index = (b*H + row)*W + col; the ray is generated as cast_rays does; no ray tensors exist
+ *   gather mode (poses == NULL)   rays are gathered from src_rays_o / src_rays_d [num_pixels,3] (the reference signature)
+ *   pixels [num_pixels, C] -> pixels_out [sample_size, C] (both may be NULL)
+ *   indices_in [sample_size] or NULL: use these indices instead of drawing (replays, parity tests);
+ *   indices_out [sample_size] or NULL: the indices used;  rays_o / rays_d [sample_size,3] (may be NULL: indices only). */
+typedef struct VoxeSamplerDesc {
+  int64_t num_pixels;
+  int32_t height, width;   /* camera mode only */
+  float focal;
+  int32_t pixel_channels;
+  uint64_t rng_seed;       /* the permutation is a function of (rng_seed, rng_offset, num_pixels) only */
+  uint64_t rng_offset;
+} VoxeSamplerDesc;
+
+VOXE_API int voxe_sample_rays(const VoxeSamplerDesc* sampler, const float* poses, const float* src_rays_o,
+                              const float* src_rays_d, const float* pixels, const int64_t* indices_in, int64_t sample_size,
+                              int64_t* indices_out, float* rays_o, float* rays_d, float* pixels_out, voxe_stream_t stream);
 
 /* Launch-shape override for tuning runs: samples per thread (1..64; the number of depth segments per ray is
  * ceil(S / samples_per_thread)), rays per CTA (power of two <= 32) and the register budget of the kernel variant

@@ -42,10 +42,10 @@ def test_struct_layouts_match_the_header(tmp_path):
     src = tmp_path / "layout.c"
     src.write_text(
         '#include <stdio.h>\n#include <stddef.h>\n#include "voxe.h"\n'
-        'int main(void){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(VoxeGridDesc), offsetof(VoxeGridDesc, aabb_lo),'
+        'int main(void){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(VoxeGridDesc), offsetof(VoxeGridDesc, aabb_lo),'
         " offsetof(VoxeGridDesc, density_scale), sizeof(VoxeRenderDesc), offsetof(VoxeRenderDesc, flags),"
         " offsetof(VoxeRenderDesc, noise_std), offsetof(VoxeRenderDesc, rng_offset), sizeof(VoxeCameraDesc),"
-        " offsetof(VoxeCameraDesc, translation), sizeof(VoxeAdamDesc));return 0;}\n"
+        " offsetof(VoxeCameraDesc, translation), sizeof(VoxeAdamDesc), sizeof(VoxeSamplerDesc), offsetof(VoxeSamplerDesc, rng_seed));return 0;}\n"
     )
     exe = tmp_path / "layout"
     subprocess.run(["gcc", "-std=c99", f"-I{ROOT / 'include'}", str(src), "-o", str(exe)], check=True)  # header is plain C
@@ -53,7 +53,7 @@ def test_struct_layouts_match_the_header(tmp_path):
     want = [ctypes.sizeof(nat.VoxeGridDesc), nat.VoxeGridDesc.aabb_lo.offset, nat.VoxeGridDesc.density_scale.offset,
             ctypes.sizeof(nat.VoxeRenderDesc), nat.VoxeRenderDesc.flags.offset, nat.VoxeRenderDesc.noise_std.offset,
             nat.VoxeRenderDesc.rng_offset.offset, ctypes.sizeof(nat.VoxeCameraDesc), nat.VoxeCameraDesc.translation.offset,
-            ctypes.sizeof(nat.VoxeAdamDesc)]
+            ctypes.sizeof(nat.VoxeAdamDesc), ctypes.sizeof(nat.VoxeSamplerDesc), nat.VoxeSamplerDesc.rng_seed.offset]
     assert got == want
 
 

@@ -262,6 +262,37 @@ int voxe_pair_loss_grad(const float* a, const float* b, int64_t n, int32_t mode,
   return VOXE_OK;
 }
 
+int voxe_sample_rays(const VoxeSamplerDesc* sampler, const float* poses, const float* src_rays_o, const float* src_rays_d,
+                     const float* pixels, const int64_t* indices_in, int64_t sample_size, int64_t* indices_out, float* rays_o,
+                     float* rays_d, float* pixels_out, voxe_stream_t stream) {
+  if (!sampler) return fail(VOXE_ERR_INVALID_ARGUMENT, "voxe_sample_rays: NULL descriptor");
+  if (sampler->num_pixels < 1) return fail(VOXE_ERR_INVALID_ARGUMENT, "voxe_sample_rays: num_pixels must be >= 1");
+  if (sample_size < 0 || sample_size > 0x7fffffff) return fail(VOXE_ERR_INVALID_ARGUMENT, "voxe_sample_rays: sample_size out of range");
+  if (!indices_in && sample_size > sampler->num_pixels)
+    return fail(VOXE_ERR_INVALID_ARGUMENT, "voxe_sample_rays: cannot draw %lld distinct indices out of %lld",
+                (long long)sample_size, (long long)sampler->num_pixels);
+  if ((rays_o == nullptr) != (rays_d == nullptr)) return fail(VOXE_ERR_INVALID_ARGUMENT, "voxe_sample_rays: rays_o and rays_d go together");
+  if (rays_o) {
+    if (poses) {
+      const int64_t per = (int64_t)sampler->height * sampler->width;
+      if (sampler->height < 1 || sampler->width < 1 || !(sampler->focal > 0.f) || sampler->num_pixels % per != 0)
+        return fail(VOXE_ERR_INVALID_ARGUMENT, "voxe_sample_rays: camera mode needs H, W >= 1, focal > 0 and num_pixels = B*H*W");
+    } else if (!src_rays_o || !src_rays_d) {
+      return fail(VOXE_ERR_INVALID_ARGUMENT, "voxe_sample_rays: give poses (camera mode) or source rays (gather mode)");
+    }
+  }
+  if (pixels_out && (!pixels || sampler->pixel_channels < 1))
+    return fail(VOXE_ERR_INVALID_ARGUMENT, "voxe_sample_rays: pixels_out needs pixels and pixel_channels >= 1");
+  if (sample_size == 0) return VOXE_OK;
+  cudaError_t e = voxe::launch_sample_rays(sampler->num_pixels, sample_size, sampler->height, sampler->width, sampler->pixel_channels,
+                                           sampler->focal, sampler->rng_seed, sampler->rng_offset, poses, src_rays_o, src_rays_d,
+                                           pixels, reinterpret_cast<const long long*>(indices_in),
+                                           reinterpret_cast<long long*>(indices_out), rays_o, rays_d, pixels_out, (cudaStream_t)stream);
+  if (e != cudaSuccess) return cuda_fail(e, "voxe_sample_rays launch");
+  g_launches.fetch_add(1);
+  return VOXE_OK;
+}
+
 int voxe_render_fwd(const VoxeGridDesc* grid, const VoxeRenderDesc* render, const float* packed,
                     const float* rays_o, const float* rays_d, const float* jitter, const float* noise,
                     float* colour, float* depth, float* acc, float* disparity, float* saved, int64_t num_rays,

@@ -37,4 +37,10 @@ cudaError_t launch_pair_loss(const float* a, const float* b, int64_t n, int mode
 cudaError_t launch_pair_grad(const float* a, const float* b, int64_t n, int mode, float eps, const double* workspace,
                              const float* upstream, float scale, float* grad, bool accumulate, cudaStream_t stream);
 
+// training-side ray-batch sampling (voxe_sampler.cu)
+cudaError_t launch_sample_rays(long long n, long long k, int H, int W, int C, float focal, unsigned long long seed,
+                               unsigned long long offset, const float* poses, const float* src_o, const float* src_d,
+                               const float* pixels, const long long* idx_in, long long* idx_out, float* rays_o, float* rays_d,
+                               float* pixels_out, cudaStream_t stream);
+
 }  // namespace voxe

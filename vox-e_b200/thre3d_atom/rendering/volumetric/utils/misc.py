@@ -59,7 +59,15 @@ def compute_expected_density_scale_for_relu_field_grid(grid_world_size: Tuple[fl
 
 
 def sample_random_rays_and_pixels_synchronously(rays: Rays, pixels: Tensor, sample_size: int) -> Tuple[Rays, Tensor]:
-    """Random ray batch for reconstruction training: the first ``sample_size`` entries of a permutation of all pixels."""
+    """Random ray batch for reconstruction training: the first ``sample_size`` entries of a permutation of all pixels.
+    fp32 CUDA tensors take one launch of ``voxe_sample_rays`` (distinct indices from a keyed permutation evaluated on demand,
+    rays and pixels gathered in the same kernel) instead of a shuffle of all B*H*W pixels; see ``voxe_b200.sampling`` --
+    its ``sample_rays_from_cameras`` also removes the per-view ``cast_rays`` this signature presupposes."""
+    if pixels.is_cuda and pixels.dtype == torch.float32 and rays.origins.dtype == torch.float32 and pixels.dim() == 2:
+        from voxe_b200.sampling import sample_random_rays_and_pixels
+
+        origins, directions, picked, _ = sample_random_rays_and_pixels(rays.origins, rays.directions, pixels, sample_size)
+        return Rays(origins, directions), picked
     chosen = torch.randperm(pixels.shape[0], dtype=torch.long, device=pixels.device)[:sample_size]
     return Rays(rays.origins[chosen, :], rays.directions[chosen, :]), pixels[chosen, :]
 

@@ -16,7 +16,7 @@ _lock = threading.Lock()
 _lib: Optional[ctypes.CDLL] = None
 
 # ---- enums of include/voxe.h -------------------------------------------------------------------------------
-ABI_VERSION = 9
+ABI_VERSION = 10
 PREACT_IDENTITY, PREACT_ABS = 0, 1
 POSTACT_IDENTITY, POSTACT_RELU, POSTACT_SOFTPLUS = 0, 1, 2
 FLAG_PERTURB, FLAG_AABB_SAMPLING, FLAG_DISPARITY_SAMPLING = 1, 2, 4
@@ -63,6 +63,11 @@ class VoxeCameraDesc(ctypes.Structure):
                 ("translation", ctypes.c_float * 3)]
 
 
+class VoxeSamplerDesc(ctypes.Structure):
+    _fields_ = [("num_pixels", ctypes.c_int64), ("height", ctypes.c_int32), ("width", ctypes.c_int32), ("focal", ctypes.c_float),
+                ("pixel_channels", ctypes.c_int32), ("rng_seed", ctypes.c_uint64), ("rng_offset", ctypes.c_uint64)]
+
+
 class VoxeAdamDesc(ctypes.Structure):
     _fields_ = [("lr", ctypes.c_double), ("beta1", ctypes.c_double), ("beta2", ctypes.c_double), ("eps", ctypes.c_double),
                 ("step", ctypes.c_int32)]
@@ -91,6 +96,7 @@ EXPORTS = {
                                            ctypes.c_float, _P, ctypes.c_int32, _P]),
     "voxe_pair_loss": (ctypes.c_int, [_P, _P, ctypes.c_int64, ctypes.c_int32, _P, _P, _P, _P]),
     "voxe_pair_loss_grad": (ctypes.c_int, [_P, _P, ctypes.c_int64, ctypes.c_int32, _P, _P, ctypes.c_float, _P, ctypes.c_int32, _P]),
+    "voxe_sample_rays": (ctypes.c_int, [ctypes.POINTER(VoxeSamplerDesc), _P, _P, _P, _P, _P, ctypes.c_int64, _P, _P, _P, _P, _P]),
     "voxe_set_tuning": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int]),
     "voxe_launch_count": (ctypes.c_int64, []),
 }
