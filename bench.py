@@ -702,6 +702,44 @@ def regularizers_leg(device, peak):
     return out
 
 
+def sampler_leg(device):
+    """Row f3: one training batch drawn from 8 views of 800x800 (the reference loop's shape, trainers.py:290-313): 4096
+    distinct pixels, their rays and colours.  Ours: one launch from poses (no ray tensors).  torch_ops_us: the reference's
+    per-iteration code on the same GPU -- randperm over all 5.12 M pixels and three gathers from pre-cast rays (the casting
+    itself, done once per loaded batch of views upstream, is not counted)."""
+    from thre3d_atom.utils.imaging_utils import CameraIntrinsics
+    from voxe_b200 import sampling
+
+    b, h, w, k = 8, 800, 800, 4096
+    n = b * h * w
+    intr = CameraIntrinsics(h, w, 1111.1)
+    poses = torch.eye(3, 4, device=device).repeat(b, 1, 1).contiguous()
+    pixels = torch.rand(n, 3, device=device)
+    rays_o, rays_d = torch.rand(n, 3, device=device), torch.rand(n, 3, device=device)
+
+    def timed(fn, n_it=50, warm=5):
+        for _ in range(warm):
+            fn()
+        a, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(device)
+        a.record()
+        for _ in range(n_it):
+            fn()
+        e.record()
+        torch.cuda.synchronize(device)
+        return 1e3 * a.elapsed_time(e) / n_it
+
+    def reference_ops():
+        chosen = torch.randperm(n, dtype=torch.long, device=device)[:k]
+        return rays_o[chosen, :], rays_d[chosen, :], pixels[chosen, :]
+
+    return {"us": round(timed(lambda: sampling.sample_rays_from_cameras(intr, poses, pixels, k)), 1),
+            "torch_ops_us": round(timed(reference_ops, n_it=10, warm=2), 1),
+            "shape": f"{k} of {b} x {h} x {w} pixels",
+            "note": "us = Python call to voxe_sample_rays (host-bound: the kernel is ~3 us); pre-cast rays avoided: "
+                    f"{n * 24 / 1e6:.0f} MB"}
+
+
 def run_ours(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -858,9 +896,10 @@ def run_ours(args):
     if rank == 0 and world == 1 and args.workload == "cfg2":
         inference = inference_leg(device)
 
-    regularizers = None
+    regularizers = sampler = None
     if rank == 0 and world == 1 and args.workload == "cfg2":
         regularizers = regularizers_leg(device, peak)
+        sampler = sampler_leg(device)
 
     if rank == 0:
         line = {
@@ -887,6 +926,8 @@ def run_ours(args):
             line["inference"] = inference
         if regularizers:
             line["regularizers"] = regularizers
+        if sampler:
+            line["batch_sampler"] = sampler
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
