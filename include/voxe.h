@@ -214,9 +214,10 @@ VOXE_API int voxe_adam_step(const VoxeGridDesc* grid, const VoxeAdamDesc* adam, 
                             const float* dense_d_features, float* packed_m, float* packed_v, voxe_stream_t stream);
 
 /* ---- per-step full-grid regularisers of the edit loop --------------------------------------------
- * `workspace` is VOXE_REG_WORKSPACE_DOUBLES doubles of device memory owned by the caller (per-CTA partial sums of the
- * reductions -- no atomics, so a loss is bitwise reproducible -- and, for the pair loss, the statistics its gradient call
- * reads back; it needs no initialisation); `loss` is ONE device float.  `upstream` (one device float,
+ * `workspace` is VOXE_REG_WORKSPACE_DOUBLES doubles of device memory owned by the caller, ZEROED ONCE when it is allocated
+ * (per-CTA partial sums of the reductions -- no floating-point atomics, so a loss is bitwise reproducible --, a ticket by
+ * which the last CTA of a launch folds them, left at zero again by every call, and, for the pair loss, the statistics its
+ * gradient call reads back); calls that share a workspace must be ordered on one stream; `loss` is ONE device float.  `upstream` (one device float,
  * dL/dloss as autograd hands it over; NULL = 1) and the host scalar `scale` (a loss weight) multiply the gradient, which
  * is ADDED into `grad` when accumulate != 0 and overwrites it otherwise. */
 #define VOXE_REG_WORKSPACE_DOUBLES 8192

@@ -20,6 +20,7 @@ __device__ __forceinline__ float sgn(float d) { return (float)(d > 0.f) - (float
 
 constexpr int kMaxCtas = 148 * 8;   // persistent launch: one wave of 8 resident 256-thread CTAs per SM
 constexpr int kPrefetch = 6;       // iterations (of 256 elements per CTA) the TV kernel prefetches ahead into L2
+constexpr int kTicket = 15;         // workspace slot of the last-CTA ticket
 constexpr int kPartials = 16;       // workspace: [0, 16) results / statistics, then N partial sums per CTA
 
 // Block-reduce N per-thread doubles and store them as this CTA's partial sums (no atomics: 25 600 same-address double
@@ -39,19 +40,47 @@ __device__ __forceinline__ void block_store(double (&val)[N], double* __restrict
   if (threadIdx.x < N) {
     double v = 0.0;
     for (int w = 0; w < (int)(blockDim.x >> 5); ++w) v += part[threadIdx.x][w];
-    ws[kPartials + (size_t)blockIdx.x * N + threadIdx.x] = v;
+    ws[kPartials + threadIdx.x * kMaxCtas + blockIdx.x] = v;  // [N][kMaxCtas]: the fold below reads each row coalesced
+    __threadfence();                                           // the partial before this CTA's ticket
   }
 }
 
-// Sum the per-CTA partials (one CTA of 256 threads): thread 0 returns with the N totals.
+// True in exactly one CTA of the grid: the last one to get here, after every CTA's partial sums are visible.  The ticket
+// (workspace slot 15, as an unsigned) wraps back to 0 on the last increment (atomicInc), so a workspace that was zeroed
+// once at allocation stays ready for every later call; the reduction needs no second launch.
+__device__ __forceinline__ bool last_cta_done(double* __restrict__ ws) {
+  __shared__ bool last;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned t = atomicInc(reinterpret_cast<unsigned*>(ws + kTicket), gridDim.x - 1);
+    last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (last) __threadfence();
+  return last;
+}
+
+// Sum the per-CTA partials (the 256 threads of the last CTA): every thread returns with the N totals.
 template <int N>
 __device__ __forceinline__ void gather_partials(const double* __restrict__ ws, int n_ctas, double (&tot)[N]) {
   __shared__ double part[N][8];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __syncthreads();  // block_store's use of its shared buffer is over
+  // all N * ceil(kMaxCtas / 256) loads are independent and issued together: one L2 round trip, not one per partial
+  constexpr int kPer = (kMaxCtas + 255) / 256;
+  double ld[N][kPer];
+#pragma unroll
+  for (int k = 0; k < N; ++k)
+#pragma unroll
+    for (int i = 0; i < kPer; ++i) {
+      const int c = threadIdx.x + i * 256;
+      ld[k][i] = c < n_ctas ? __ldcg(ws + kPartials + k * kMaxCtas + c) : 0.0;  // L2: written by other CTAs
+    }
 #pragma unroll
   for (int k = 0; k < N; ++k) {
     double v = 0.0;
-    for (int c = threadIdx.x; c < n_ctas; c += blockDim.x) v += ws[kPartials + (size_t)c * N + k];
+#pragma unroll
+    for (int i = 0; i < kPer; ++i) v += ld[k][i];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     if (lane == 0) part[k][warp] = v;
@@ -65,6 +94,9 @@ __device__ __forceinline__ void gather_partials(const double* __restrict__ ws, i
   }
 }
 
+__device__ __forceinline__ void tv_finalize(const double* __restrict__ ws, float* __restrict__ loss, double n0, double n1,
+                                            double n2);
+
 // ---- total variation -------------------------------------------------------------------------------------------
 // grid [X,Y,Z,C], z fastest, channels innermost, taken as X*Y rows of Z*C contiguous floats.  Persistent launch: CTA b
 // owns the flat element span [b * chunk, (b+1) * chunk); its threads walk the span 256 elements at a time, so every load
@@ -77,7 +109,8 @@ __device__ __forceinline__ void gather_partials(const double* __restrict__ ws, i
 template <bool RELU, bool DO_SUM, bool DO_GRAD>
 __global__ void __launch_bounds__(256) tv_kernel(const float* __restrict__ g, float* __restrict__ grad, double* __restrict__ ws,
                                                  int X, int Y, int ZC, int C, int64_t sx, int64_t total, int64_t chunk,
-                                                 float cx, float cy, float cz, const float* __restrict__ upstream, int accumulate) {
+                                                 float cx, float cy, float cz, const float* __restrict__ upstream, int accumulate,
+                                                 float* __restrict__ loss, double n0, double n1, double n2) {
   const int64_t begin = (int64_t)blockIdx.x * chunk;
   const int64_t end = begin + chunk < total ? begin + chunk : total;
   int64_t idx = begin + threadIdx.x;
@@ -140,6 +173,7 @@ __global__ void __launch_bounds__(256) tv_kernel(const float* __restrict__ g, fl
   if (DO_SUM) {
     double v[3] = {(double)s0, (double)s1, (double)s2};
     block_store<3>(v, ws);
+    if (last_cta_done(ws)) tv_finalize(ws, loss, n0, n1, n2);
   }
 }
 
@@ -155,7 +189,7 @@ template <bool RELU, bool DO_SUM, bool DO_GRAD, int ZMODE>
 __global__ void __launch_bounds__(256) tv_vec_kernel(const float* __restrict__ g, float* __restrict__ grad, double* __restrict__ ws,
                                                      int X, int Y, int GR, int C, int64_t sxg, int64_t total_g, int64_t chunk,
                                                      float cx, float cy, float cz, const float* __restrict__ upstream,
-                                                     int accumulate) {
+                                                     int accumulate, float* __restrict__ loss, double n0, double n1, double n2) {
   const float4* g4 = reinterpret_cast<const float4*>(g);
   float4* grad4 = reinterpret_cast<float4*>(grad);
   const int64_t begin = (int64_t)blockIdx.x * chunk;
@@ -249,13 +283,15 @@ __global__ void __launch_bounds__(256) tv_vec_kernel(const float* __restrict__ g
   if (DO_SUM) {
     double v[3] = {(double)s0, (double)s1, (double)s2};
     block_store<3>(v, ws);
+    if (last_cta_done(ws)) tv_finalize(ws, loss, n0, n1, n2);
   }
 }
 
-__global__ void __launch_bounds__(256) tv_finalize_kernel(const double* __restrict__ ws, int n_ctas, float* __restrict__ loss,
-                                                          double n0, double n1, double n2) {
+// Last CTA of a TV launch: fold the partials into the loss.
+__device__ __forceinline__ void tv_finalize(const double* __restrict__ ws, float* __restrict__ loss, double n0, double n1,
+                                            double n2) {
   double tot[3];
-  gather_partials<3>(ws, n_ctas, tot);
+  gather_partials<3>(ws, gridDim.x, tot);
   if (threadIdx.x != 0) return;
   // mean over an empty difference tensor (an axis of extent 1) is NaN in torch; 0/0 reproduces that
   const float m0 = (float)(tot[0] / n0), m1 = (float)(tot[1] / n1), m2 = (float)(tot[2] / n2);
@@ -265,6 +301,24 @@ __global__ void __launch_bounds__(256) tv_finalize_kernel(const double* __restri
 // ---- density correlation / L2 / L1 between two grids --------------------------------------------------------------
 // workspace doubles: [5] mean_a, [6] mean_b, [7] var_a, [8] var_b, [9] cov, [10] sqrt(var_a*var_b); per-CTA partials from 16 on
 enum { kCorr = 0, kL2 = 1, kL1 = 2 };
+
+// Last CTA of a statistics launch: fold the partials into the loss and the statistics the gradient pass reads.
+__device__ __forceinline__ void pair_finalize(double* __restrict__ ws, float* __restrict__ loss, double n, int mode, float eps) {
+  double tot[5];
+  gather_partials<5>(ws, gridDim.x, tot);
+  if (threadIdx.x != 0) return;
+  if (mode != kCorr) {
+    *loss = (float)(tot[0] / n);
+    return;
+  }
+  const double ma = tot[0] / n, mb = tot[1] / n;
+  const double va = fmax(tot[2] / n - ma * ma, 0.0), vb = fmax(tot[3] / n - mb * mb, 0.0);
+  const double cov = tot[4] / n - ma * mb;
+  const double d = sqrt(va * vb);
+  ws[5] = ma; ws[6] = mb; ws[7] = va; ws[8] = vb; ws[9] = cov; ws[10] = d;
+  // 1 - mean(covariance_grid / (denominator + eps))                                   (sds_trainer.py:520-524)
+  *loss = 1.f - (float)(cov / (d + (double)eps));
+}
 
 template <int MODE>
 __device__ __forceinline__ void pair_accumulate(float xf, float yf, double (&acc)[5]) {
@@ -286,7 +340,7 @@ __device__ __forceinline__ void pair_accumulate(float xf, float yf, double (&acc
 // n4 = number of whole float4 groups the vector loop covers (0 when the pointers are not 16-byte aligned)
 template <int MODE>
 __global__ void __launch_bounds__(256) pair_stats_kernel(const float* __restrict__ a, const float* __restrict__ b, int64_t n,
-                                                         int64_t n4, double* __restrict__ sums) {
+                                                         int64_t n4, double* __restrict__ sums, float* __restrict__ loss, float eps) {
   double acc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
   const int64_t stride = (int64_t)gridDim.x * blockDim.x, t0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const float4* a4 = reinterpret_cast<const float4*>(a);
@@ -300,24 +354,7 @@ __global__ void __launch_bounds__(256) pair_stats_kernel(const float* __restrict
   }
   for (int64_t i = 4 * n4 + t0; i < n; i += stride) pair_accumulate<MODE>(__ldg(a + i), __ldg(b + i), acc);
   block_store<5>(acc, sums);
-}
-
-__global__ void __launch_bounds__(256) pair_finalize_kernel(double* __restrict__ ws, int n_ctas, float* __restrict__ loss, double n,
-                                                            int mode, float eps) {
-  double tot[5];
-  gather_partials<5>(ws, n_ctas, tot);
-  if (threadIdx.x != 0) return;
-  if (mode != kCorr) {
-    *loss = (float)(tot[0] / n);
-    return;
-  }
-  const double ma = tot[0] / n, mb = tot[1] / n;
-  const double va = fmax(tot[2] / n - ma * ma, 0.0), vb = fmax(tot[3] / n - mb * mb, 0.0);
-  const double cov = tot[4] / n - ma * mb;
-  const double d = sqrt(va * vb);
-  ws[5] = ma; ws[6] = mb; ws[7] = va; ws[8] = vb; ws[9] = cov; ws[10] = d;
-  // 1 - mean(covariance_grid / (denominator + eps))                                   (sds_trainer.py:520-524)
-  *loss = 1.f - (float)(cov / (d + (double)eps));
+  if (last_cta_done(sums)) pair_finalize(sums, loss, (double)n, MODE, eps);
 }
 
 // correlation_grid = (a - mean_a)(b - mean_b) / (denominator + eps): the second return value of the reference function
@@ -410,7 +447,7 @@ cudaError_t launch_tv(const float* grid, const int dims[3], int channels, bool r
     const int zmode = C <= 3 ? C : (C % 4 == 0 ? 4 : 0);
 #define VOXE_TV_VEC(R_, S_, G_, Z_)                                                                                          \
   tv_vec_kernel<R_, S_, G_, Z_><<<n_ctas, 256, 0, stream>>>(grid, grad, workspace, X, Y, ZC / 4, C, (int64_t)Y * (ZC / 4), units, \
-                                                            chunk, cx, cy, cz, upstream, acc)
+                                                            chunk, cx, cy, cz, upstream, acc, loss, n0, n1, n2)
 #define VOXE_TV_VEC_Z(R_, S_, G_)              \
   switch (zmode) {                             \
     case 1: VOXE_TV_VEC(R_, S_, G_, 1); break; \
@@ -429,7 +466,7 @@ cudaError_t launch_tv(const float* grid, const int dims[3], int channels, bool r
   } else {
 #define VOXE_TV_LAUNCH(R_, S_, G_)                                                                                       \
   tv_kernel<R_, S_, G_><<<n_ctas, 256, 0, stream>>>(grid, grad, workspace, X, Y, ZC, C, (int64_t)Y * ZC, total, chunk, cx, cy, \
-                                                    cz, upstream, acc)
+                                                    cz, upstream, acc, loss, n0, n1, n2)
     if (relu) {
       if (do_sum && do_grad) VOXE_TV_LAUNCH(true, true, true);
       else if (do_sum) VOXE_TV_LAUNCH(true, true, false);
@@ -444,11 +481,6 @@ cudaError_t launch_tv(const float* grid, const int dims[3], int channels, bool r
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   ++*launches;
-  if (loss) {
-    tv_finalize_kernel<<<1, 256, 0, stream>>>(workspace, n_ctas, loss, n0, n1, n2);
-    e = cudaGetLastError();
-    if (e == cudaSuccess) ++*launches;
-  }
   return e;
 }
 
@@ -458,13 +490,9 @@ cudaError_t launch_pair_loss(const float* a, const float* b, int64_t n, int mode
   cudaError_t e = cudaSuccess;
   const int64_t n4 = vec_groups(n, a, b, nullptr);
   const int blocks = stream_blocks(n4 ? n4 : n);
-  if (mode == kCorr) pair_stats_kernel<kCorr><<<blocks, 256, 0, stream>>>(a, b, n, n4, workspace);
-  else if (mode == kL2) pair_stats_kernel<kL2><<<blocks, 256, 0, stream>>>(a, b, n, n4, workspace);
-  else pair_stats_kernel<kL1><<<blocks, 256, 0, stream>>>(a, b, n, n4, workspace);
-  e = cudaGetLastError();
-  if (e != cudaSuccess) return e;
-  ++*launches;
-  pair_finalize_kernel<<<1, 256, 0, stream>>>(workspace, blocks, loss, (double)n, mode, eps);
+  if (mode == kCorr) pair_stats_kernel<kCorr><<<blocks, 256, 0, stream>>>(a, b, n, n4, workspace, loss, eps);
+  else if (mode == kL2) pair_stats_kernel<kL2><<<blocks, 256, 0, stream>>>(a, b, n, n4, workspace, loss, eps);
+  else pair_stats_kernel<kL1><<<blocks, 256, 0, stream>>>(a, b, n, n4, workspace, loss, eps);
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   ++*launches;

@@ -34,7 +34,7 @@ def _workspace(dev: torch.device) -> Tensor:
     key = (dev.index, torch.cuda.current_stream(dev).cuda_stream)
     ws = _workspaces.get(key)
     if ws is None:
-        ws = _workspaces[key] = torch.empty(nat.REG_WORKSPACE_DOUBLES, dtype=torch.float64, device=dev)
+        ws = _workspaces[key] = torch.zeros(nat.REG_WORKSPACE_DOUBLES, dtype=torch.float64, device=dev)
     return ws
 
 
@@ -143,7 +143,7 @@ class _PairLoss(torch.autograd.Function):
     @staticmethod
     def forward(ctx, sds_density: Tensor, regular_density: Tensor, mode: int, want_grid: bool):
         a, b = _pair_args(sds_density, regular_density)
-        ws = torch.empty(nat.REG_WORKSPACE_DOUBLES, dtype=torch.float64, device=a.device)  # its statistics are kept for the backward
+        ws = torch.zeros(nat.REG_WORKSPACE_DOUBLES, dtype=torch.float64, device=a.device)  # its statistics are kept for the backward
         loss, corr = _pair_forward(a, b, mode, want_grid, ws)
         ctx.save_for_backward(sds_density, regular_density, ws)
         ctx.mode = mode
