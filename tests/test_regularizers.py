@@ -142,10 +142,13 @@ def test_pair_kernels_match_reference_golden(case):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("dims,channels,relu", [((33, 17, 40), 1, True), ((16, 16, 16), 3, False), ((5, 9, 300), 12, False),
-                                                ((3, 1, 7), 2, False), ((1, 6, 6), 1, True), ((20, 20, 1), 4, False)])
+                                                ((3, 1, 7), 2, False), ((1, 6, 6), 1, True), ((20, 20, 1), 4, False),
+                                                ((6, 5, 8), 27, False), ((4, 7, 4), 5, True), ((9, 4, 6), 2, True),
+                                                ((7, 3, 5), 3, False), ((300, 2, 2), 48, False)])
 def test_tv_kernel_against_fp64_oracle(dims, channels, relu):
-    """Seeded grids; row lengths below / above one CTA, and axes of extent 1 (loss NaN as torch's empty mean, finite gradient
-    from the other axes)."""
+    """Seeded grids; every kernel variant (16-byte path with the z neighbours in the window C = 1, 2, 3, as aligned groups
+    C % 4 == 0, as scalars C = 5 / 27; scalar path when a row is not a multiple of 16 bytes), row lengths below / above one
+    CTA stride, and axes of extent 1 (loss NaN as torch's empty mean, finite gradient from the other axes)."""
     from voxe_b200 import regularizers as reg
 
     g = torch.Generator().manual_seed(sum(dims) + channels)
@@ -182,10 +185,10 @@ def test_headline_grid_properties():
         g1 = x.grad.clone()
         x.grad = None
         l2 = reg._tv_loss_on_grid((x.detach() * 4.0 + 1.5).requires_grad_(True))
-        assert abs(float(l2) - 4.0 * float(l1)) <= 1e-5 * float(l2)
+        assert abs(float(l2.detach()) - 4.0 * float(l1.detach())) <= 1e-5 * float(l2.detach())
         assert abs(float(g1.double().sum())) <= 1e-6
         # E|N(0,1) - N(0,1)| = 2 / sqrt(pi)
-        assert abs(float(l1) - 2.0 / np.pi ** 0.5) < 2e-3
+        assert abs(float(l1.detach()) - 2.0 / np.pi ** 0.5) < 2e-3
         ref = x.detach().clone().requires_grad_(True)  # torch's own ops on the GPU: same formula, independent kernels
         ((ref.diff(dim=0).abs().mean() + ref.diff(dim=1).abs().mean() + ref.diff(dim=2).abs().mean()) / 3).backward()
         _close_grad(g1, ref.grad, "tv 160^3")
@@ -207,6 +210,37 @@ def test_headline_grid_properties():
     da, db = ref - ref.mean(), base - base.mean()
     (1.0 - (da * db / (torch.sqrt((da ** 2).mean() * (db ** 2).mean()) + 1e-7)).mean()).backward()
     _close_grad(mixed.grad, ref.grad, "corr 160^3", tol=1e-4)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dims,channels", [((256, 256, 256), 4), ((512, 512, 512), 1)])
+def test_large_grids_against_torch_ops(dims, channels):
+    """BASELINE.json's larger grids (256^3 with 4 channels = the packed SH-0 voxel; 512^3 densities, 537 MB): 64-bit indexing
+    and the persistent spans at full size, checked against the same formula in torch ops on the GPU."""
+    from voxe_b200 import regularizers as reg
+
+    gen = torch.Generator(device="cuda").manual_seed(11)
+    x = torch.randn((*dims, channels), device="cuda", generator=gen)
+    x[:, ::5] = torch.round(x[:, ::5])
+    ours = x.clone().requires_grad_(True)
+    loss = reg._tv_loss_on_grid(ours, relu=True)
+    loss.backward()
+    ref = x.clone().requires_grad_(True)
+    h = torch.relu(ref)
+    want = (h.diff(dim=0).abs().mean() + h.diff(dim=1).abs().mean() + h.diff(dim=2).abs().mean()) / 3
+    want.backward()
+    _close_loss(loss, want.detach(), str(dims))
+    assert (ours.grad - ref.grad).abs().max().item() <= 1e-5 * ref.grad.abs().max().item()
+    del h, want
+    other = (0.5 * x + torch.randn_like(x)).requires_grad_(True)
+    l2, _ = reg.density_correlation_loss_fn(other, x, return_correlation_grid=False)
+    l2.backward()
+    o = other.detach().clone().requires_grad_(True)
+    da, db = o - o.mean(), x - x.mean()
+    w2 = 1.0 - (da * db / (torch.sqrt((da ** 2).mean() * (db ** 2).mean()) + 1e-7)).mean()
+    w2.backward()
+    _close_loss(l2, w2.detach(), str(dims))
+    assert (other.grad - o.grad).abs().max().item() <= 1e-4 * o.grad.abs().max().item()
 
 
 @pytest.mark.gpu
