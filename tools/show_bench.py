@@ -1,9 +1,23 @@
-"""Print the interesting fields of a bench.py JSON line read from stdin (helper for gpurun one-liners)."""
+"""Print the interesting fields of a bench.py JSON line (helper for gpurun one-liners).
+
+    python bench.py | python tools/show_bench.py [tag]        # from a pipe
+    python tools/show_bench.py gpurun_out/bench.json [tag]    # from a file
+
+Never waits on a terminal: with no file argument and an interactive stdin it exits with a usage message (a bare call once
+sat in a gpurun command line until the call's time limit ran out)."""
 import json
+import os
 import sys
 
-tag = sys.argv[1] if len(sys.argv) > 1 else ""
-d = json.loads(sys.stdin.read().strip().splitlines()[-1])
+args = sys.argv[1:]
+if args and os.path.isfile(args[0]):
+    text, args = open(args[0]).read(), args[1:]
+elif sys.stdin.isatty():
+    raise SystemExit(__doc__)
+else:
+    text = sys.stdin.read()
+tag = args[0] if args else ""
+d = json.loads(text.strip().splitlines()[-1])
 r = d.get("roofline") or {}
 e = d.get("e2e") or {}
 f = d.get("fused_step") or {}

@@ -45,10 +45,13 @@ void check(int rc, const char* what) {
 const float* cptr(const Tensor& t) { return t.defined() ? t.data_ptr<float>() : nullptr; }
 float* mptr(const Tensor& t) { return t.defined() ? t.data_ptr<float>() : nullptr; }
 
+// Checked, gradient-free, contiguous view of an input -- without creating tensor objects when it already is all that (the
+// common case: every dispatcher call costs about a microsecond of the ~40 a forward call takes on the host).
 Tensor prep(const Tensor& t, const c10::Device& dev, const char* name) {
   TORCH_CHECK(t.device() == dev, "all render inputs must live on one device (", name, " is on ", t.device(), ", expected ", dev, ")");
   TORCH_CHECK_TYPE(t.scalar_type() == at::kFloat, "the render path computes in fp32 (", name, " is ", t.scalar_type(), ")");
-  return t.contiguous();
+  if (!t.requires_grad() && t.is_contiguous()) return t;
+  return t.detach().contiguous();
 }
 
 voxe_stream_t stream_of(const c10::Device& dev) {
@@ -143,7 +146,8 @@ class RenderFn : public torch::autograd::Function<RenderFn> {
 
     Tensor g[4];
     for (int k = 0; k < 4; ++k)
-      if (grads[k].defined()) g[k] = grads[k].to(at::kFloat).contiguous();
+      if (grads[k].defined())
+        g[k] = (grads[k].scalar_type() == at::kFloat && grads[k].is_contiguous()) ? grads[k] : grads[k].to(at::kFloat).contiguous();
     if (!g[0].defined()) g[0] = at::zeros({R, (int64_t)rd.n_colour}, rays_o.options());
     if (!grad_volume.defined()) grad_volume = at::zeros_like(packed);  // no persistent volume attached: a fresh one
 
@@ -200,12 +204,12 @@ std::vector<Tensor> render(const Tensor& densities, const Tensor& features, cons
   Tensor rays_o, rays_d, jitter, noise;
   {
     at::NoGradGuard no_grad;
-    rays_o = prep(rays_o_in.detach(), dev, "ray origins");
-    rays_d = prep(rays_d_in.detach(), dev, "ray directions");
+    rays_o = prep(rays_o_in, dev, "ray origins");
+    rays_d = prep(rays_d_in, dev, "ray directions");
     const int64_t R = rays_o.size(0), S = rd.num_samples;
     if (rd.flags & VOXE_FLAG_PERTURB) {
       if (jitter_in.has_value() && jitter_in->defined()) {
-        jitter = prep(jitter_in->detach(), dev, "jitter");
+        jitter = prep(*jitter_in, dev, "jitter");
       } else if (strict_rng) {
         jitter = at::rand({R, S}, generator, rays_o.options());
       } else {  // in-kernel draws: take (seed, offset) from the generator and advance it
@@ -219,7 +223,7 @@ std::vector<Tensor> render(const Tensor& densities, const Tensor& features, cons
       TORCH_CHECK(!jitter.defined() || (jitter.dim() == 2 && jitter.size(0) == R && jitter.size(1) == S), "jitter must be [R, S]");
     }
     if (rd.noise_std != 0.f) {
-      noise = noise_in.has_value() && noise_in->defined() ? prep(noise_in->detach(), dev, "noise")
+      noise = noise_in.has_value() && noise_in->defined() ? prep(*noise_in, dev, "noise")
                                                           : at::randn({R, S}, generator, rays_o.options());
       TORCH_CHECK(noise.dim() == 2 && noise.size(0) == R && noise.size(1) == S, "noise must be [R, S]");
     } else if (strict_rng) {

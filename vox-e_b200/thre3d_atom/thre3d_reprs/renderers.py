@@ -137,7 +137,7 @@ def render_sh_voxel_grid(
         voxel_grid.fused_spec(), spec, densities, features, rays.origins, rays.directions, cache=voxel_grid.packed_cache(),
         grad_sink=voxel_grid.render_gradient_accumulator, grad_scratch=voxel_grid.render_gradient_scratch(),
     )
-    return RenderOut(colour=colour, depth=depth, extra={EXTRA_DISPARITY: disparity, EXTRA_ACCUMULATED_WEIGHTS: acc})
+    return RenderOut._trusted(colour, depth, {EXTRA_DISPARITY: disparity, EXTRA_ACCUMULATED_WEIGHTS: acc})
 
 
 def render_sh_voxel_grid_camera(voxel_grid: VoxelGrid, camera_intrinsics, camera_pose, render_config: SHVoxGridRenderConfig) -> RenderOut:
@@ -163,7 +163,7 @@ def render_sh_voxel_grid_camera(voxel_grid: VoxelGrid, camera_intrinsics, camera
             voxel_grid.fused_spec(), spec, densities.detach(), features.detach(), height, width, focal, camera_pose.rotation,
             camera_pose.translation, cache=voxel_grid.packed_cache(),
         )
-    return RenderOut(colour=colour, depth=depth, extra={EXTRA_DISPARITY: disparity, EXTRA_ACCUMULATED_WEIGHTS: acc})
+    return RenderOut._trusted(colour, depth, {EXTRA_DISPARITY: disparity, EXTRA_ACCUMULATED_WEIGHTS: acc})
 
 
 def render_sh_voxel_grid_attn(

@@ -296,13 +296,11 @@ def fused_render(
         _require_cuda(densities, features, rays_o, rays_d)  # raises the explanatory error
     if densities.dtype != torch.float32 or features.dtype != torch.float32:
         raise TypeError(f"the render path computes in fp32 (got {densities.dtype} / {features.dtype})")
-    rays_o, rays_d = _prep_rays(rays_o, rays_d)
-    R, S = rays_o.shape[0], rspec.num_samples
-    if jitter is not None and rspec.flags & nat.FLAG_PERTURB:
-        assert jitter.shape == (R, S)
-    if noise is not None and rspec.noise_std != 0.0:
-        assert noise.shape == (R, S)
-    ext = bridge()
+    if rays_o.dtype != torch.float32 or rays_d.dtype != torch.float32:
+        rays_o, rays_d = rays_o.float(), rays_d.float()
+    # ray / jitter / noise shapes are checked once, in the C++ entry point (same messages as _prep_rays)
+    R = rays_o.shape[0]
+    ext = _bridge_module or bridge()
     packed = (cache or PackedVolumeCache()).get(gspec, densities, features)
     if R == 0:
         z = torch.zeros((0, 1), dtype=torch.float32, device=dev)
