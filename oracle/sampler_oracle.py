@@ -5,6 +5,11 @@ the comparison is bit-exact), and what a selection means in the reference's term
 ``collate_rays([flatten_rays(cast_rays(intrinsics, pose_b)) for b ...])`` / ``images.permute(0,2,3,1).reshape(-1, C)``
 (thre3d_atom/modules/trainers.py:290-308; thre3d_atom/rendering/volumetric/utils/misc.py:12-50, 126-138).  The reference
 itself draws ``torch.randperm(N)[:k]``; its contract -- k distinct uniformly distributed rows -- is what the tests check.
+
+PARITY UNPINNED for the drawn numbers: no golden vector of the reference can pin them (they are ``torch.randperm``'s), so
+this file is pinned only in the other direction -- the kernel must equal it bit for bit, and it must be a permutation.  The
+meaning of an index (which ray, which pixel) is pinned against the reference's ``cast_rays`` through
+``tests/golden/cameras.npz`` (tests/test_abi_and_api.py) and tests/test_sampler.py.
 """
 from __future__ import annotations
 
