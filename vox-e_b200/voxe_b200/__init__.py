@@ -3,7 +3,8 @@
 Layout of the product tree (``vox-e_b200/`` is a path root, put it on ``sys.path``):
 
     csrc/          CUDA kernels + the C ABI declared in ``include/voxe.h``
-    voxe_b200/     this package: ctypes loader, autograd bridge, ray-shard data parallelism
+    voxe_b200/     this package: ctypes loader (_native), autograd bridge (render_function), fused optimiser step (optim),
+                   grid regularisers (regularizers), ray-batch sampler (sampling), ray-shard data parallelism (dist)
     thre3d_atom/   the reference-facing interface for the hot path (same module paths and names as Vox-E, so its
                    scripts, identity asserts and pickled checkpoints resolve to the fused implementation)
 
