@@ -253,3 +253,37 @@ def test_batchify_and_misc():
     assert batchify(abs, None, None) is abs
     assert compute_thre3d_grid_sizes((160, 160, 160), 4, 2.0) == [(20, 20, 20), (40, 40, 40), (80, 80, 80), (160, 160, 160)]
     assert check_power_of_2(64) and not check_power_of_2(48)
+
+
+def test_product_tree_never_touches_the_oracle_or_a_cpu_path():
+    """The oracle is test infrastructure: nothing under vox-e_b200/ may import it, and the only places outside tests/ that
+    do are the two the contract names (smoke() in __graft_entry__.py, the CPU legs of bench.py).  The product's native
+    sources must not contain host-side compute fallbacks either: every kernel entry point goes through a launch."""
+    import ast
+
+    offenders = []
+    for path in (ROOT / "vox-e_b200").rglob("*.py"):
+        tree = ast.parse(path.read_text())
+        for node in ast.walk(tree):
+            names = []
+            if isinstance(node, ast.Import):
+                names = [a.name for a in node.names]
+            elif isinstance(node, ast.ImportFrom):
+                names = [node.module or ""]
+            offenders += [f"{path.relative_to(ROOT)} imports {n}" for n in names if n.split(".")[0] == "oracle"]
+    assert not offenders, offenders
+    allowed = {"bench.py", "__graft_entry__.py"}
+    for path in ROOT.glob("*.py"):
+        if "oracle" in path.read_text() and path.name not in allowed:
+            offenders.append(path.name)
+    for path in (ROOT / "tools").glob("*.py"):
+        tree = ast.parse(path.read_text())
+        for node in ast.walk(tree):
+            if isinstance(node, ast.ImportFrom) and (node.module or "").split(".")[0] == "oracle":
+                offenders.append(f"tools/{path.name}")
+    assert not offenders, offenders
+    # a missing library is an error, not a detour
+    from voxe_b200 import _native as nat
+
+    src = (ROOT / "vox-e_b200" / "voxe_b200" / "_native.py").read_text()
+    assert "raise NativeLibraryError" in src and nat.NativeLibraryError.__mro__[1] is RuntimeError
