@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define VOXE_ABI_VERSION 10
+#define VOXE_ABI_VERSION 11
 
 #if defined(__GNUC__)
 #define VOXE_API __attribute__((visibility("default")))
@@ -277,6 +277,10 @@ VOXE_API int voxe_set_tuning(int samples_per_thread, int rays_per_cta, int regis
 
 /* Number of kernels this library has launched on the calling process since load (for bench accounting). */
 VOXE_API int64_t voxe_launch_count(void);
+
+/* Render launches that took a flag-specialised kernel variant (environment VOXE_SPECIALISED_KERNELS=1, read once at the
+ * first render call: same arithmetic as the generic kernels with the per-call switches resolved at compile time). */
+VOXE_API int64_t voxe_specialised_launch_count(void);
 
 #ifdef __cplusplus
 }

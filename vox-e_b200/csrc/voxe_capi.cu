@@ -4,6 +4,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "voxe.h"
@@ -13,8 +14,18 @@
 namespace {
 
 thread_local char g_error[512] = "";
-std::atomic<int64_t> g_launches{0};
+std::atomic<int64_t> g_launches{0}, g_specialised{0};
 std::atomic<int> g_tune_l{0}, g_tune_rpc{0}, g_tune_reg{0};
+
+// VOXE_SPECIALISED_KERNELS=1: take the flag-specialised kernel variants where they exist (same arithmetic, fewer
+// instructions per sample; opt-in until their parity run on a B200 is recorded -- see DESIGN.md section 8)
+bool specialised_kernels() {
+  static const bool on = [] {
+    const char* v = std::getenv("VOXE_SPECIALISED_KERNELS");
+    return v != nullptr && v[0] == '1';
+  }();
+  return on;
+}
 
 int fail(int code, const char* fmt, ...) {
   va_list ap;
@@ -134,6 +145,8 @@ int64_t voxe_packed_floats(const VoxeGridDesc* grid) {
 }
 
 int64_t voxe_launch_count(void) { return g_launches.load(); }
+
+int64_t voxe_specialised_launch_count(void) { return g_specialised.load(); }
 
 int voxe_set_tuning(int samples_per_thread, int rays_per_cta, int register_cap) {
   if (samples_per_thread < 0 || samples_per_thread > 64)
@@ -316,7 +329,10 @@ int voxe_render_fwd(const VoxeGridDesc* grid, const VoxeRenderDesc* render, cons
   p.depth = depth;
   p.acc = acc;
   p.disp = disparity;
-  cudaError_t e = voxe::launch_render(p, render->sh_degree, render->n_colour, regcap, false, (cudaStream_t)stream);
+  bool took_specialised = false;
+  cudaError_t e = voxe::launch_render(p, render->sh_degree, render->n_colour, regcap, false, specialised_kernels(), (cudaStream_t)stream,
+                                      &took_specialised);
+  if (took_specialised) g_specialised.fetch_add(1);
   if (e != cudaSuccess) return cuda_fail(e, "voxe_render_fwd launch");
   g_launches.fetch_add(1);
   return VOXE_OK;
@@ -412,7 +428,10 @@ int voxe_render_bwd(const VoxeGridDesc* grid, const VoxeRenderDesc* render, cons
   p.g_depth = g_depth;
   p.g_acc = g_acc;
   p.g_disp = g_disp;
-  cudaError_t e = voxe::launch_render(p, render->sh_degree, render->n_colour, regcap, true, (cudaStream_t)stream);
+  bool took_specialised = false;
+  cudaError_t e = voxe::launch_render(p, render->sh_degree, render->n_colour, regcap, true, specialised_kernels(), (cudaStream_t)stream,
+                                      &took_specialised);
+  if (took_specialised) g_specialised.fetch_add(1);
   if (e != cudaSuccess) return cuda_fail(e, "voxe_render_bwd launch");
   g_launches.fetch_add(1);
   return VOXE_OK;

@@ -9,7 +9,8 @@ struct KParams;
 struct CameraParams;
 
 // fused ray-marcher (voxe_render.cu)
-cudaError_t launch_render(const KParams& p, int sh_degree, int n_colour, int regcap, bool backward, cudaStream_t stream);
+cudaError_t launch_render(const KParams& p, int sh_degree, int n_colour, int regcap, bool backward, bool specialise,
+                          cudaStream_t stream, bool* took_specialised);
 cudaError_t launch_camera(const KParams& p, const CameraParams& cam, int sh_degree, int n_colour, cudaStream_t stream);
 int max_threads_per_cta(int regcap);
 cudaError_t launch_jitter_fill(int R, int S, unsigned long long seed, unsigned long long offset, float* out, cudaStream_t stream);

@@ -49,7 +49,7 @@ struct Layout {
 
 // One sample: gather the 8 corners, interpolate, SH-contract.  Returns the (pre-activated, interpolated) raw
 // density and writes raw colour logits.  `signs` gets one bit per corner: d pre(x)/dx < 0 (abs pre-activation).
-template <int DEG, int NCOL>
+template <int DEG, int NCOL, class SP = SpecDynamic>
 __device__ __forceinline__ float gather_sample(const KParams& p, const Corners& c, const float (&Y)[(DEG + 1) * (DEG + 1)],
                                                float (&raw)[NCOL], unsigned& signs) {
   using LT = Layout<DEG, NCOL>;
@@ -77,7 +77,7 @@ __device__ __forceinline__ float gather_sample(const KParams& p, const Corners& 
     }
   }
   // voxels.py:303-305: pre(density * scale) is applied at the voxels, then interpolated
-  if (p.preact == kPreAbs) {
+  if (SP::pre_abs(p.preact)) {
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
       const float dv = f4_get(v[q][LT::DCH], LT::DCO);
@@ -188,7 +188,7 @@ struct Bounds {
 // ---------------------------------------------------------------------------------------------------------
 // forward
 // ---------------------------------------------------------------------------------------------------------
-template <int DEG, int NCOL, int REGCAP>
+template <int DEG, int NCOL, int REGCAP, class SP>
 __global__ void __launch_bounds__(Bounds<REGCAP>::kThreads, Bounds<REGCAP>::kMinBlocks) render_fwd_kernel(const __grid_constant__ KParams p) {
   using LT = Layout<DEG, NCOL>;
   constexpr int NV = LT::NV;
@@ -214,8 +214,8 @@ __global__ void __launch_bounds__(Bounds<REGCAP>::kThreads, Bounds<REGCAP>::kMin
     u_row.init(p, ray);
     float4* samples = p.saved ? sample_slots(p, seg, ray) : nullptr;
     DepthWalker zw;
-    if (i0 < i1) zw.init(p, rc, u_row, i0);
-    const bool use_noise = (p.noise_std != 0.f);
+    if (i0 < i1) zw.init<SP>(p, rc, u_row, i0);
+    const bool use_noise = SP::noise(p.noise_std);
     float Y[LT::K];
     const float inv = 1.0f / rc.dnorm;
     sh_basis<DEG>(rc.d[0] * inv, rc.d[1] * inv, rc.d[2] * inv, (p.flags & kDiffuse) != 0, Y);
@@ -224,7 +224,7 @@ __global__ void __launch_bounds__(Bounds<REGCAP>::kThreads, Bounds<REGCAP>::kMin
     // samples interleave.  Samples outside the box are rare here (thread_samples) and are masked, not skipped: their
     // corner addresses are clamped into the volume and their sigma / colour are forced to 0 (process.py:80-91).
 #pragma unroll(kSampleUnroll)
-    for (int i = i0; i < i1; ++i, zw.advance(p, rc, u_row, i - 1)) {
+    for (int i = i0; i < i1; ++i, zw.advance<SP>(p, rc, u_row, i - 1)) {
       const float zi = zw.cur;
       const float px = __fadd_rn(rc.o[0], __fmul_rn(rc.d[0], zi));   // sample.py:67: o + d * z (mul, then add)
       const float py = __fadd_rn(rc.o[1], __fmul_rn(rc.d[1], zi));
@@ -234,8 +234,8 @@ __global__ void __launch_bounds__(Bounds<REGCAP>::kThreads, Bounds<REGCAP>::kMin
       make_corners(p, px, py, pz, c);
       float raw[NCOL], dpost, col[NCOL];
       unsigned signs;
-      const float sraw = gather_sample<DEG, NCOL>(p, c, Y, raw, signs);
-      float sigma = in ? post_act(p.postact, sraw, dpost) : 0.f;
+      const float sraw = gather_sample<DEG, NCOL, SP>(p, c, Y, raw, signs);
+      float sigma = in ? post_act(SP::postact(p.postact), sraw, dpost) : 0.f;
 #pragma unroll
       for (int k = 0; k < NCOL; ++k) col[k] = in ? sigmoid_fast(raw[k]) : 0.f;   // sigmoid(-1e10) == 0 outside the grid
       if (samples != nullptr) {  // what the backward needs of this sample: colour(s) and the raw density (every slot
@@ -317,7 +317,7 @@ __global__ void __launch_bounds__(Bounds<REGCAP>::kThreads, Bounds<REGCAP>::kMin
 // ---------------------------------------------------------------------------------------------------------
 // backward
 // ---------------------------------------------------------------------------------------------------------
-template <int DEG, int NCOL, int REGCAP>
+template <int DEG, int NCOL, int REGCAP, class SP>
 __global__ void __launch_bounds__(Bounds<REGCAP>::kThreads, Bounds<REGCAP>::kMinBlocks) render_bwd_kernel(const __grid_constant__ KParams p) {
   using LT = Layout<DEG, NCOL>;
   constexpr int NV = LT::NV;
@@ -423,8 +423,8 @@ __global__ void __launch_bounds__(Bounds<REGCAP>::kThreads, Bounds<REGCAP>::kMin
   u_row.init(p, ray);
   const float4* samples = sample_slots(p, seg, ray);
   DepthWalker zw;
-  zw.init(p, rc, u_row, i0);
-  const bool use_noise = (p.noise_std != 0.f);
+  zw.init<SP>(p, rc, u_row, i0);
+  const bool use_noise = SP::noise(p.noise_std);
   float Y[LT::K];
   const float inv = 1.0f / rc.dnorm;
   sh_basis<DEG>(rc.d[0] * inv, rc.d[1] * inv, rc.d[2] * inv, (p.flags & kDiffuse) != 0, Y);
@@ -433,7 +433,7 @@ __global__ void __launch_bounds__(Bounds<REGCAP>::kThreads, Bounds<REGCAP>::kMin
 
   float4 sv_next = __ldg(samples);  // the sample vectors are fetched one iteration ahead of their use
 #pragma unroll(kSampleUnroll)
-  for (int i = i0; i < i1; ++i, zw.advance(p, rc, u_row, i - 1)) {
+  for (int i = i0; i < i1; ++i, zw.advance<SP>(p, rc, u_row, i - 1)) {
     const float4 sv = sv_next;
     if (i + 1 < i1) sv_next = __ldg(samples + (size_t)(i + 1 - i0) * p.R);
     const float zi = zw.cur;
@@ -449,7 +449,7 @@ __global__ void __launch_bounds__(Bounds<REGCAP>::kThreads, Bounds<REGCAP>::kMin
       col[0] = sv.x;  // colour(s) + raw density stored by the forward
       if (NCOL > 1) col[1] = sv.y;
       if (NCOL > 2) col[2] = sv.z;
-      sigma = post_act(p.postact, sv.w, dpost);
+      sigma = post_act(SP::postact(p.postact), sv.w, dpost);
     }
     if (use_noise) sigma = fmaf(__ldg(p.noise + (size_t)ray * p.S + i), p.noise_std, sigma);
     const bool last = (i == p.S - 1);
@@ -477,7 +477,7 @@ __global__ void __launch_bounds__(Bounds<REGCAP>::kThreads, Bounds<REGCAP>::kMin
     if (!any) continue;
     Corners c;
     make_corners(p, px, py, pz, c);
-    const unsigned signs = (p.preact == kPreAbs) ? corner_signs<DEG, NCOL>(p, c) : 0u;
+    const unsigned signs = SP::pre_abs(p.preact) ? corner_signs<DEG, NCOL>(p, c) : 0u;
     float gfe[LT::CV * 4];
 #pragma unroll
     for (int k = 0; k < LT::CV * 4; ++k) gfe[k] = 0.f;
@@ -600,7 +600,7 @@ cudaError_t launch_camera_t(const KParams& p, const CameraParams& cam, cudaStrea
   return cudaGetLastError();
 }
 
-template <int DEG, int NCOL, int REGCAP>
+template <int DEG, int NCOL, int REGCAP, class SP = SpecDynamic>
 cudaError_t launch_pair(const KParams& p, bool backward, cudaStream_t stream) {
   using LT = Layout<DEG, NCOL>;
   const int threads = ((p.rpc * p.nseg + 31) / 32) * 32;
@@ -610,11 +610,11 @@ cudaError_t launch_pair(const KParams& p, bool backward, cudaStream_t stream) {
   if (backward && LT::CV > 1)
     smem = sizeof(float) * bwd_stage_offset_floats(LT::NV, p.nseg, p.rpc) + sizeof(float4) * 2 * (size_t)threads * BulkStage<LT::CV>::kSlot;
   if (backward) {
-    auto k = render_bwd_kernel<DEG, NCOL, REGCAP>;
+    auto k = render_bwd_kernel<DEG, NCOL, REGCAP, SP>;
     if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     k<<<blocks, threads, smem, stream>>>(p);
   } else {
-    auto k = render_fwd_kernel<DEG, NCOL, REGCAP>;
+    auto k = render_fwd_kernel<DEG, NCOL, REGCAP, SP>;
     if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     k<<<blocks, threads, smem, stream>>>(p);
   }
@@ -636,9 +636,39 @@ cudaError_t dispatch_deg(const KParams& p, int deg, int ncol, bool backward, cud
   return cudaErrorInvalidValue;
 }
 
+// Specialised variants (see Spec in voxe_device.cuh) exist for what the training loops actually run: RGB grids, the
+// default register budgets of pick_shape (80 / 96 at SH-0, 128 above), ReLU or Softplus post-activation, with or without
+// stratified jitter.  Everything else takes the generic kernels.
+template <int DEG, int REGCAP>
+cudaError_t dispatch_spec(const KParams& p, bool backward, cudaStream_t stream) {
+  const bool perturb = (p.flags & kPerturb) != 0;
+  if (p.postact == kPostRelu)
+    return perturb ? launch_pair<DEG, 3, REGCAP, Spec<1, kPostRelu, true>>(p, backward, stream)
+                   : launch_pair<DEG, 3, REGCAP, Spec<0, kPostRelu, true>>(p, backward, stream);
+  return perturb ? launch_pair<DEG, 3, REGCAP, Spec<1, kPostSoftplus, true>>(p, backward, stream)
+                 : launch_pair<DEG, 3, REGCAP, Spec<0, kPostSoftplus, true>>(p, backward, stream);
+}
+
+bool specialised_variant_exists(const KParams& p, int deg, int ncol, int regcap) {
+  if (ncol != 3 || (p.postact != kPostRelu && p.postact != kPostSoftplus)) return false;
+  const bool disparity = (p.flags & kDisparity) && !(p.flags & kAabb);
+  if (disparity || p.noise_std != 0.f || p.preact != kPreIdentity || p.jitter != nullptr) return false;
+  return deg == 0 ? (regcap == 80 || regcap == 96) : regcap == 128;
+}
+
 }  // namespace
 
-cudaError_t launch_render(const KParams& p, int deg, int ncol, int regcap, bool backward, cudaStream_t stream) {
+cudaError_t launch_render(const KParams& p, int deg, int ncol, int regcap, bool backward, bool specialise, cudaStream_t stream,
+                          bool* took_specialised) {
+  *took_specialised = specialise && specialised_variant_exists(p, deg, ncol, regcap);
+  if (*took_specialised) {
+    switch (deg) {
+      case 0: return regcap == 80 ? dispatch_spec<0, 80>(p, backward, stream) : dispatch_spec<0, 96>(p, backward, stream);
+      case 1: return dispatch_spec<1, 128>(p, backward, stream);
+      case 2: return dispatch_spec<2, 128>(p, backward, stream);
+      case 3: return dispatch_spec<3, 128>(p, backward, stream);
+    }
+  }
   if (regcap <= 64) return dispatch_deg<64>(p, deg, ncol, backward, stream);
   if (regcap == 80) return dispatch_deg<80>(p, deg, ncol, backward, stream);
   if (regcap == 96) return dispatch_deg<96>(p, deg, ncol, backward, stream);

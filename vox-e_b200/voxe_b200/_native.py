@@ -16,7 +16,7 @@ _lock = threading.Lock()
 _lib: Optional[ctypes.CDLL] = None
 
 # ---- enums of include/voxe.h -------------------------------------------------------------------------------
-ABI_VERSION = 10
+ABI_VERSION = 11
 PREACT_IDENTITY, PREACT_ABS = 0, 1
 POSTACT_IDENTITY, POSTACT_RELU, POSTACT_SOFTPLUS = 0, 1, 2
 FLAG_PERTURB, FLAG_AABB_SAMPLING, FLAG_DISPARITY_SAMPLING = 1, 2, 4
@@ -99,6 +99,7 @@ EXPORTS = {
     "voxe_sample_rays": (ctypes.c_int, [ctypes.POINTER(VoxeSamplerDesc), _P, _P, _P, _P, _P, ctypes.c_int64, _P, _P, _P, _P, _P]),
     "voxe_set_tuning": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int]),
     "voxe_launch_count": (ctypes.c_int64, []),
+    "voxe_specialised_launch_count": (ctypes.c_int64, []),
 }
 
 
