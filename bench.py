@@ -9,19 +9,30 @@ background; every frame is rendered as 40 consecutive flat-index batches of <= 4
 
 A *step* is one frame = 160 000 rays = 40 x (forward kernel, backward kernel accumulating into the packed gradient
 volume; the stratified jitter is generated inside both kernels, ``--jitter buffer`` draws it with torch.rand instead)
-+ one gradient zero-fill + one unpack of the packed gradient into d_densities / d_features (+ one NCCL all-reduce of
-the packed gradient when N > 1: each rank renders its own pose -- weak scaling).
++ one gradient zero-fill + one unpack of the packed gradient into d_densities / d_features (+ ONE all-reduce of the packed
+gradient when N > 1: each rank renders its own pose -- weak scaling; the library's own peer-memory kernel
+``voxe_allreduce_grads_peer``, ``--collective nccl`` for ncclAllReduce through torch.distributed).
 
   value     device-resident throughput: the step above replayed as a CUDA graph over C-ABI launches, inputs in HBM;
             three batches are in flight on three streams (--lanes 3; the strictly serialised number is reported as
-            ``serialized``)
-  e2e       the same frame through the public API (``VolumetricModel.render_rays`` + ``.backward()`` per 4096-ray batch)
-            with rays and upstream gradients starting in pinned HOST memory and loss + colour read back every step
-  roofline  the backward kernel (dominant) timed alone with CUDA events: algorithmic bytes / duration vs measured HBM peak
-  cpu_baseline  the oracle port (PyTorch fp32, all host threads) on a bounded sample of the same batches
+            ``serialized``); ``value_softplus`` is the same frame on a Softplus field (every in-grid sample scatters)
+  parity    the timed leg's own outputs (colours and voxel gradients of the last timed frame) against the oracle run in
+            fp32 on the same GPU with the very jitter the kernels drew (voxe_jitter_fill)
+  e2e       the same frame through the public API (``VolumetricModel.render_rays`` + ``.backward()`` per 4096-ray batch,
+            torch's default autograd engine) with rays and upstream gradients starting in pinned HOST memory and loss +
+            colour read back every step; variants (CUDA-graph capture of the same calls, calling-thread engine, deferred
+            gradients, one call per frame) beside it
+  roofline  the backward kernel (dominant) timed alone with CUDA events: the bytes it moves (counted by the kernel
+            itself: saved-vector reloads + the scatters it really issues) / duration vs measured HBM peak; the SURVEY 8d
+            contract model beside it as ``model_frac``; L2-side figure from the committed ncu capture
+  gpu_baseline  the same batch through stock ATen ops on the same GPU (the oracle, or the reference itself when
+            ``oracle/_ref`` was built), CUDA events
+  cpu_baseline  the reference (``oracle/_ref``) or its oracle port (PyTorch fp32, all host threads) on a bounded sample
 
-``--impl reference`` times only the CPU leg (the reference is pure Python/PyTorch and does not travel to the GPU box;
-``oracle/voxe_oracle.py`` is its pinned restatement), one 4096-ray batch forward+backward per step.
+``--impl reference`` times only the CPU leg, one 4096-ray batch forward+backward per step.
+``--check`` (any N): ranks render disjoint ray shards, all-reduce with each collective, compare with the unsharded gradient.
+``--workload cfg4|cfg5 [--gpus N]``: the other BASELINE.json configurations as stated there (cfg 4: 100 ``get_random_pose``
+views dealt round-robin over the ranks, one all-reduce per step).
 """
 import argparse
 import json
@@ -50,30 +61,46 @@ WL = dict(
     height=400, width=400, focal=555.5, radius=4.0311, pitch=60.0, num_poses=9, S=256, near=1.8, far=6.6,
     batch=4096, perturb=True, white_bkgd=True, seed=42,
 )
-BYTES_PER_SAMPLE_FWD = 8 * 4 * 4          # 8 corners x (F+1)=4 channels x 4 B: the forward gather
-BYTES_PER_SAMPLE_BWD = 2 * 8 * 4 * 4      # backward re-gather + scatter-add payload
-BYTES_PER_RAY_FWD = 24 + 24               # ray read + outputs
-BYTES_PER_RAY_BWD = 24 + 24               # ray read + upstream gradients
+# Bytes per in-grid sample.  MODEL_* is the SURVEY.md 8d contract (three cache-less corner sweeps: forward gather, backward
+# re-gather, scatter payload) kept as ``model_frac``; MOVED_* is what the kernels really move: the forward gathers 8 corners
+# and saves one 16-byte vector, the backward reloads that vector and scatters 8 corners only for the samples whose
+# gradient is non-zero (the fraction is counted by the kernel itself, VoxeRenderDesc.stats).
+MODEL_BYTES_PER_SAMPLE_FWD = 8 * 4 * 4
+MODEL_BYTES_PER_SAMPLE_BWD = 2 * 8 * 4 * 4
+MODEL_BYTES_PER_RAY = 24 + 24
+MOVED_GATHER = 8 * 4 * 4                  # 8 corners x roundup4(F+1) channels x 4 B
+MOVED_SAVED_VECTOR = 16
+N_SEGMENTS = 16                           # depth segments per ray at S >= 128 (pick_shape in csrc/voxe_capi.cu)
+
+
+def moved_bytes_per_ray(direction):
+    """Per-ray traffic outside the sample loop: rays, outputs / upstream gradients, segment summaries ((n_colour + 3) floats
+    per ray and depth segment, written by the forward and read by the backward)."""
+    summaries = (3 + 3) * N_SEGMENTS * 4
+    return 24 + (12 + 4 + 4 + 4 if direction == "fwd" else 12) + summaries
+
 
 # The other BASELINE.json configurations (parity cases in tests/test_baseline_configs.py); `--workload cfgN` times their
 # device-resident leg for the record (DESIGN.md section 6) -- the bench line the driver reads is always cfg 2.
 OTHER_WORKLOADS = {
     "cfg3": dict(name="cfg3: 160^3 SH-2 grid, 512x512 render, one 262144-ray differentiable batch, S=256", sh_degree=2,
                  postact="softplus", height=512, width=512, focal=711.1, batch=512 * 512),
-    "cfg4": dict(name="cfg4: 256^3 SH-0 grid, 800x800 views, one view per launch, S=256", dims=(256, 256, 256), postact="softplus",
-                 height=800, width=800, focal=1111.1, batch=800 * 800),
+    "cfg4": dict(name="cfg4: 256^3 SH-0 grid, 100 random 800x800 views sharded over the ranks, one view per launch, S=256", dims=(256, 256, 256),
+                 postact="softplus", height=800, width=800, focal=1111.1, batch=800 * 800, random_views=100, grid_copies=1),
     "cfg5": dict(name="cfg5: 512^3 SH-2 grid (15 GB), 1024x1024 render, S=512, 65536-ray batches", dims=(512, 512, 512), sh_degree=2,
                  postact="softplus", height=1024, width=1024, focal=1422.2, S=512, batch=65536, grid_copies=1),
 }
 
 
 def select_workload(name):
-    global BYTES_PER_SAMPLE_FWD, BYTES_PER_SAMPLE_BWD
+    global MODEL_BYTES_PER_SAMPLE_FWD, MODEL_BYTES_PER_SAMPLE_BWD, MOVED_GATHER, N_SEGMENTS
     if name != "cfg2":
         WL.update(OTHER_WORKLOADS[name])
     ch = 3 * (WL["sh_degree"] + 1) ** 2 + 1
-    BYTES_PER_SAMPLE_FWD = 8 * ch * 4
-    BYTES_PER_SAMPLE_BWD = 2 * 8 * ch * 4
+    MODEL_BYTES_PER_SAMPLE_FWD = 8 * ch * 4
+    MODEL_BYTES_PER_SAMPLE_BWD = 2 * 8 * ch * 4
+    MOVED_GATHER = 8 * ((ch + 3) // 4) * 16
+    N_SEGMENTS = (WL["S"] + 15) // 16
 
 
 def measured_hbm_peak():
@@ -220,19 +247,67 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------------------
-# CPU leg: the oracle port, PyTorch fp32 on the host cores
+# reference arm: the reference itself (oracle/_ref, staged by oracle/build_ref.py) or its oracle port, stock ATen ops
 # ---------------------------------------------------------------------------------------------------------
-def cpu_leg(steps, warmup, budget_s=None):
-    """One step = one 4096-ray batch of pose 0 forward+backward through the oracle in fp32.  Returns rays/s etc."""
-    from oracle.voxe_oracle import OracleConfig, OracleGrid, render_oracle_with_grads
+def reference_kind():
+    from oracle import build_ref
 
+    return "reference" if build_ref.available() else "port"
+
+
+def use_staged_reference():
+    """Make ``thre3d_atom`` resolve to the staged reference instead of this repository's mirror (reference arm only: the
+    two packages share their import paths, so one process can hold only one of them)."""
+    from oracle import build_ref
+
+    product = str(ROOT / "vox-e_b200")
+    sys.path[:] = [q for q in sys.path if q != product]
+    for q in reversed(build_ref.ref_paths()):
+        sys.path.insert(0, q)
+    for name in [m for m in sys.modules if m == "thre3d_atom" or m.startswith("thre3d_atom.")]:
+        del sys.modules[name]
+
+
+def reference_leg(device, steps, warmup, budget_s=None):
+    """One step = one 4096-ray batch of pose 0 forward+backward, fp32, through the reference's own render procedure
+    (``render_sh_voxel_grid`` of the staged reference; kind "reference") or, when ``oracle/_ref`` was not built, through
+    the oracle port (kind "port").  ``device`` cpu: all host threads, perf_counter; cuda: CUDA events."""
+    kind = reference_kind()
+    on_gpu = device.type == "cuda"
     threads = os.cpu_count() or 1
-    torch.set_num_threads(threads)
-    dens, feat = make_grid_tensors("cpu")
-    rays_o, rays_d = frame_rays(make_poses()[0], torch.device("cpu"))
-    grid = OracleGrid(tuple(w / d for w, d in zip(WL["world"], WL["dims"])), density_scale=WL["density_scale"],
-                      preact=WL["preact"], postact=WL["postact"])
-    cfg = OracleConfig(num_samples=WL["S"], near=WL["near"], far=WL["far"], perturb=True, white_bkgd=True)
+    if not on_gpu:
+        torch.set_num_threads(threads)
+    if kind == "reference":
+        use_staged_reference()
+    dens, feat = make_grid_tensors(device)
+    rays_o, rays_d = frame_rays(make_poses()[0], device)
+    voxel = tuple(w / d for w, d in zip(WL["world"], WL["dims"]))
+    if kind == "reference":
+        from thre3d_atom.rendering.volumetric.render_interface import Rays
+        from thre3d_atom.thre3d_reprs.renderers import SHVoxGridRenderConfig, render_sh_voxel_grid
+        from thre3d_atom.thre3d_reprs.voxels import VoxelGrid, VoxelSize
+        from thre3d_atom.utils.imaging_utils import CameraBounds
+
+        post = torch.nn.ReLU() if WL["postact"] == "relu" else torch.nn.Softplus()
+        grid = VoxelGrid(dens, feat, VoxelSize(*voxel), density_preactivation=torch.nn.Identity(), density_postactivation=post,
+                         expected_density_scale=WL["density_scale"], tunable=True)
+        cfg = SHVoxGridRenderConfig(num_samples_per_ray=WL["S"], camera_bounds=CameraBounds(WL["near"], WL["far"]), white_bkgd=True,
+                                    perturb_sampled_points=True)
+
+        def one(o, d, gcol):
+            grid.densities.grad = None
+            grid.features.grad = None
+            render_sh_voxel_grid(grid, Rays(o, d), cfg).colour.backward(gcol)
+    else:
+        from oracle.voxe_oracle import OracleConfig, OracleGrid, render_oracle_with_grads
+
+        ogrid = OracleGrid(voxel, density_scale=WL["density_scale"], preact=WL["preact"], postact=WL["postact"])
+        ocfg = OracleConfig(num_samples=WL["S"], near=WL["near"], far=WL["far"], perturb=True, white_bkgd=True)
+
+        def one(o, d, gcol):
+            jitter = torch.rand(o.shape[0], WL["S"], device=device)
+            render_oracle_with_grads(dens, feat, ogrid, o, d, ocfg, gcol, jitter=jitter, dtype=torch.float32)
+
     g = torch.Generator().manual_seed(1)
     B = WL["batch"]
     n_batches = rays_o.shape[0] // B
@@ -241,35 +316,64 @@ def cpu_leg(steps, warmup, budget_s=None):
     for k in range(warmup + steps):
         b = (17 + k) % n_batches  # start mid-frame so the batches cross the object
         o, d = rays_o[b * B : (b + 1) * B], rays_d[b * B : (b + 1) * B]
-        gcol = torch.randn(B, 3, generator=g)
-        t0 = time.perf_counter()
-        jitter = torch.rand(B, WL["S"], generator=g)
-        render_oracle_with_grads(dens, feat, grid, o, d, cfg, gcol, jitter=jitter, dtype=torch.float32)
-        dt = time.perf_counter() - t0
+        gcol = torch.randn(B, 3, generator=g).to(device)
+        if on_gpu:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize(device)
+            e0.record()
+            one(o, d, gcol)
+            e1.record()
+            torch.cuda.synchronize(device)
+            dt = e0.elapsed_time(e1) * 1e-3
+        else:
+            t0 = time.perf_counter()
+            one(o, d, gcol)
+            dt = time.perf_counter() - t0
         if k >= warmup:
             times.append(dt)
         if budget_s is not None and k >= warmup and time.perf_counter() - t_begin > budget_s:
             break
     total = sum(times)
-    return {"rays_per_s": B * len(times) / total, "ms_per_step": 1e3 * total / len(times), "steps": len(times), "cores": threads,
-            "sample": f"{len(times)} batches of {B} rays (pose 0, batches 17..) fwd+bwd, fp32, after {warmup} warm-up"}
+    what = "the reference's render_sh_voxel_grid + backward (oracle/_ref)" if kind == "reference" else "the oracle port of the reference"
+    return {"rays_per_s": B * len(times) / total, "ms_per_step": 1e3 * total / len(times), "steps": len(times),
+            "cores": 0 if on_gpu else threads, "kind": kind, "device": str(device),
+            "sample": f"{len(times)} batches of {B} rays (pose 0, batches 17..) fwd+bwd through {what}, fp32, stock ATen ops, "
+                      f"after {warmup} warm-up" + (", CUDA events" if on_gpu else f", {threads} host threads")}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    r = cpu_leg(args.steps, args.warmup)
+    device = torch.device(args.ref_device)
+    r = reference_leg(device, args.steps, args.warmup, budget_s=150.0)  # K steps, or as many as fit into 2.5 minutes
     line = {
         "impl": "reference", "metric": "rays/s fwd+bwd, 160^3 SH-0 grid, 400x400 render", "value": r["rays_per_s"], "unit": "rays/s",
         "n_gpus": args.gpus, "steps": r["steps"], "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WL["name"], "step": "one 4096-ray batch fwd+bwd on the host CPU (bounded sample of the frame)"},
-        "cpu_baseline": {"value": r["rays_per_s"], "unit": "rays/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]},
+        "config": {"workload": WL["name"], "step": f"one 4096-ray batch fwd+bwd on {'the GPU, stock ATen ops' if device.type == 'cuda' else 'the host CPU'} "
+                                                   "(bounded sample of the frame)"},
+        "cpu_baseline": {"value": r["rays_per_s"], "unit": "rays/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]},
         "e2e": {"value": r["rays_per_s"], "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+def reference_subprocess(device, steps, warmup, timeout_s=240):
+    """Run the reference arm in a child process (the staged reference and this repository's mirror cannot share one
+    interpreter) and return its JSON line, or a dict with "error"."""
+    cmd = [sys.executable, str(Path(__file__).resolve()), "--impl", "reference", "--ref-device", device, "--steps", str(steps),
+           "--warmup", str(warmup)]
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")}
+    try:
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout_s, env=env, cwd=str(ROOT))
+        lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+        if r.returncode != 0 or not lines:
+            return {"error": (r.stderr or r.stdout)[-400:]}
+        return json.loads(lines[-1])
+    except Exception as exc:  # noqa: BLE001
+        return {"error": str(exc)[:400]}
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -280,31 +384,52 @@ class DeviceBench:
 
     N_GRID_COPIES = 3  # rotating copies: 3 x 65.5 MB of grid + 65.5 MB of gradients >> 126 MB L2
 
-    def __init__(self, device, rank, world, count_s_in=True, n_lanes=1, kernel_jitter=True):
+    def __init__(self, device, rank, world, count_s_in=True, n_lanes=1, kernel_jitter=True, postact=None, peer_volume=None,
+                 share=None):
         from voxe_b200 import _native as nat
         from voxe_b200.render_function import FusedGridSpec, FusedRenderSpec, pack_volume
 
         self.nat, self.lib = nat, nat.load_library()
         self.device, self.rank, self.world = device, rank, world
-        dens, feat = make_grid_tensors(device)
+        self.postact = postact or WL["postact"]
+        dens, feat = (share.dens, share.feat) if share is not None else make_grid_tensors(device)
         half = [w / 2 for w in WL["world"]]
         self.N_GRID_COPIES = WL.get("grid_copies", self.N_GRID_COPIES)
         self.gspec = FusedGridSpec(dims=WL["dims"], n_features=feat.shape[-1], aabb=tuple((-h, h) for h in half),
                                    density_scale=WL["density_scale"], preact=nat.PREACT_IDENTITY,
-                                   postact=nat.POSTACT_RELU if WL["postact"] == "relu" else nat.POSTACT_SOFTPLUS)
+                                   postact=nat.POSTACT_RELU if self.postact == "relu" else nat.POSTACT_SOFTPLUS)
         flags = nat.FLAG_WHITE_BKGD | (nat.FLAG_PERTURB if WL["perturb"] else 0)
         self.rspec = FusedRenderSpec(num_samples=WL["S"], near=WL["near"], far=WL["far"], flags=flags, sh_degree=WL["sh_degree"], n_colour=3)
         self.gd = self.gspec.to_native()
         self.rd = nat.VoxeRenderDesc.from_buffer_copy(self.rspec.native_bytes())  # private copy: rng_offset changes per launch
         self.kernel_jitter = kernel_jitter and WL["perturb"]
         self.dens, self.feat = dens, feat
-        self.packed = [pack_volume(self.gspec, dens, feat) for _ in range(self.N_GRID_COPIES)]
-        self.packed_grad = torch.zeros_like(self.packed[0])
-        self.d_dens, self.d_feat = torch.empty_like(dens), torch.empty_like(feat)
-        self.poses = make_poses()
+        # a second bench on the same values (the Softplus twin) shares volumes, rays and outputs with the first
+        self.packed = share.packed if share is not None else [pack_volume(self.gspec, dens, feat) for _ in range(self.N_GRID_COPIES)]
+        if share is not None:
+            self.packed_grad, self.peer_volume = share.packed_grad, share.peer_volume
+        elif peer_volume is not None:  # N > 1: the gradient volume lives in peer-mapped memory (voxe_allreduce_grads_peer)
+            self.peer_volume = peer_volume(self.packed[0].numel())
+            self.packed_grad = self.peer_volume.buffer
+        else:
+            self.peer_volume = None
+            self.packed_grad = torch.zeros_like(self.packed[0])
+        self.d_dens, self.d_feat = (share.d_dens, share.d_feat) if share is not None else (torch.empty_like(dens), torch.empty_like(feat))
+        if WL.get("random_views"):
+            # cfg 4 as BASELINE.json states it: `random_views` poses from get_random_pose after np.random.seed(42)
+            # (utils/imaging_utils.py:197-215 upstream), dealt round-robin over the ranks
+            from thre3d_atom.utils.imaging_utils import get_random_pose
+            from voxe_b200.dist import shard_views
+
+            np.random.seed(WL["seed"])
+            every = [get_random_pose(WL["radius"])[0] for _ in range(WL["random_views"])]
+            self.poses = [every[i] for i in shard_views(len(every), rank, world)]
+            self.total_views = len(every)
+        else:
+            self.poses = make_poses()
         if WL["batch"] < WL["height"] * WL["width"] and WL["name"].startswith("cfg5"):
             self.poses = self.poses[:3]
-        self.rays = [frame_rays(p, device) for p in self.poses]
+        self.rays = share.rays if share is not None else [frame_rays(p, device) for p in self.poses]
         if WL["name"].startswith("cfg5"):  # one 65536-ray batch through the middle of each frame
             lo = (WL["height"] // 2 - 32) * WL["width"]
             self.rays = [(o[lo:lo + WL["batch"]].contiguous(), d[lo:lo + WL["batch"]].contiguous()) for o, d in self.rays]
@@ -353,13 +478,29 @@ class DeviceBench:
         self.nat.check(self.lib.voxe_render_bwd(
             self.gd, self.rd, self.packed[copy].data_ptr(), o[b0:b1].data_ptr(), d[b0:b1].data_ptr(),
             self._jitter_arg(pose, b0), None, saved.data_ptr(), self.G[b0:b1].data_ptr(), None, None, None,
-            self.packed_grad.data_ptr(), b1 - b0, self._stream()), "voxe_render_bwd")
+            self.packed_grad.data_ptr(), None, 0, b1 - b0, self._stream()), "voxe_render_bwd")
+
+    def scatter_stats(self, pose=0):
+        """(in-grid samples the backward processed, samples whose 8-corner scatter it issued) for one frame, counted by the
+        kernel itself (VoxeRenderDesc.stats); run once, eagerly, outside every timed region."""
+        counters = torch.zeros(2, dtype=torch.int64, device=self.device)
+        self.rd.stats = counters.data_ptr()
+        try:
+            for b0, b1 in self.batches:
+                self._fwd(pose, 0, b0, b1, self.saved)
+                self._bwd(pose, 0, b0, b1, self.saved)
+            torch.cuda.synchronize(self.device)
+        finally:
+            self.rd.stats = None
+        self.packed_grad.zero_()
+        n_in, n_scatter = (int(v) for v in counters.tolist())
+        return n_in, n_scatter
 
     def unpack(self):
         self.nat.check(self.lib.voxe_unpack_grad(self.gd, self.packed_grad.data_ptr(), self.d_dens.data_ptr(), self.d_feat.data_ptr(), 0,
                                                  self._stream()), "voxe_unpack_grad")
 
-    def frame_body(self, pose, copy, what="both", saved_set=None, refresh_jitter=True):
+    def frame_body(self, pose, copy, what="both", saved_set=None, refresh_jitter=True, zero=True):
         """One frame.  ``saved_set``: per-batch workspaces (needed when fwd and bwd of a batch are not adjacent).
 
         Stream structure of the whole-frame step: the jitter draw of a later batch (torch.rand, sample.py:63) runs on a side
@@ -377,7 +518,8 @@ class DeviceBench:
                     self._bwd(pose, copy, b0, b1, saved)
             return
         draw = WL["perturb"] and refresh_jitter and not self.kernel_jitter
-        self.packed_grad.zero_()
+        if zero:  # one zero-fill per optimiser step (cfg 4 accumulates all of a rank's views before its one all-reduce)
+            self.packed_grad.zero_()
         n = self.n_lanes
         lanes = [main] + self.lane_streams[: n - 1]
         for lane in lanes[1:]:
@@ -419,11 +561,12 @@ class DeviceBench:
             if what != "both":  # isolated kernels: fixed jitter, per-batch workspaces filled by a full pass first
                 saved_set = [torch.empty_like(self.saved) for _ in self.batches]
                 self.frame_body(pose, copy, "both", saved_set, refresh_jitter=False)
-            self.frame_body(pose, copy, what, saved_set)  # warm (lazy module load, allocator)
+            zero = n == 0 or not WL.get("random_views")
+            self.frame_body(pose, copy, what, saved_set, zero=zero)  # warm (lazy module load, allocator)
             torch.cuda.synchronize(self.device)
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
-                self.frame_body(pose, copy, what, saved_set)
+                self.frame_body(pose, copy, what, saved_set, zero=zero)
             graphs.append(g)
             self._keep = getattr(self, "_keep", []) + [saved_set]
         return graphs
@@ -450,14 +593,25 @@ class DeviceBench:
         return start.elapsed_time(stop)  # ms
 
 
-def e2e_leg(device, rank, world, steps, warmup, dist, deferred=False, engine_threads=False, whole_frame=False):
-    """The frame through the public API, inputs starting in pinned host memory.  ``deferred``: the opt-in gradient
-    accumulation mode (VoxelGrid.accumulate_render_gradients) with one materialisation per frame."""
+def e2e_leg(device, rank, world, steps, warmup, dist, deferred=False, engine_threads=True, whole_frame=False, graph=False,
+            peer_volume=None):
+    """The frame through the public API, inputs starting in pinned host memory.
+
+    engine_threads  True: torch's default autograd engine (a device worker thread runs every backward()); False: the stock
+                    caller-side switch torch.autograd.set_multithreading_enabled(False) (backward on the calling thread)
+    graph           the same API calls of one frame captured ONCE with torch.cuda.graph (stock torch; the render path is
+                    capturable: in-kernel jitter reads the graph-registered generator state, so every replay draws fresh
+                    jitter) and replayed per frame on static device buffers that the per-frame host->device copies fill
+    deferred        the opt-in gradient accumulation mode (VoxelGrid.accumulate_render_gradients), one materialisation per frame
+    whole_frame     one render_rays + one backward per frame instead of 4096-ray batches
+    N > 1: one collective per frame -- on the packed sink volume (deferred; the library's peer kernel when the volume is
+    peer-mapped) or on ONE flat buffer holding both dense gradients (VoxelGradAllReducer)."""
     from thre3d_atom.modules.volumetric_model import VolumetricModel
     from thre3d_atom.rendering.volumetric.render_interface import Rays
     from thre3d_atom.thre3d_reprs.renderers import SHVoxGridRenderConfig, render_sh_voxel_grid
     from thre3d_atom.thre3d_reprs.voxels import VoxelGrid, VoxelSize
     from thre3d_atom.utils.imaging_utils import CameraBounds
+    from voxe_b200.dist import VoxelGradAllReducer
 
     dens, feat = make_grid_tensors(device)
     grid = VoxelGrid(dens, feat, VoxelSize(*(w / d for w, d in zip(WL["world"], WL["dims"]))), density_preactivation=torch.nn.Identity(),
@@ -465,8 +619,15 @@ def e2e_leg(device, rank, world, steps, warmup, dist, deferred=False, engine_thr
     vm = VolumetricModel(grid, render_sh_voxel_grid,
                          SHVoxGridRenderConfig(num_samples_per_ray=WL["S"], camera_bounds=CameraBounds(WL["near"], WL["far"]),
                                                white_bkgd=True, perturb_sampled_points=WL["perturb"]), device=device)
+    volume = None
     if deferred:
         grid.accumulate_render_gradients()
+        if world > 1 and peer_volume is not None:
+            spec = grid.fused_spec()
+            packed = grid.packed_cache().get(spec, grid.densities, grid.features)
+            volume = peer_volume(packed.numel())
+            volume.adopt(grid.render_gradient_accumulator)
+    reducer = VoxelGradAllReducer([grid.densities, grid.features]) if world > 1 else None
     poses = make_poses()
     host = []
     g = torch.Generator().manual_seed(7)
@@ -480,14 +641,8 @@ def e2e_leg(device, rank, world, steps, warmup, dist, deferred=False, engine_thr
     h2d = R * (12 + 12 + 12)
     d2h = R * 12 + 4
 
-    def one_frame(idx):
-        o_h, d_h, g_h = host[idx % len(host)]
-        grid.densities.grad = None
-        grid.features.grad = None
-        # the step's inputs: rays and upstream gradients of the whole frame, pinned host memory -> device
-        o = o_h.to(device, non_blocking=True)
-        d = d_h.to(device, non_blocking=True)
-        gc = g_h.to(device, non_blocking=True)
+    def render_frame(o, d, gc):
+        """The API calls of one frame on device-resident inputs: per batch render_rays -> backward."""
         colours = []
         for o_b, d_b, g_b in zip(o.split(B), d.split(B), gc.split(B)):  # 4096-ray batches (views, no copies)
             out = vm.render_rays(Rays(o_b, d_b))
@@ -496,20 +651,60 @@ def e2e_leg(device, rank, world, steps, warmup, dist, deferred=False, engine_thr
             out.colour.backward(g_b)
             colours.append(out.colour.detach())
         colour = torch.cat(colours)
-        loss_total = (colour * gc).sum()
+        return colour, (colour * gc).sum()
+
+    def finish(colour, loss_total):
         colour_host.copy_(colour, non_blocking=True)  # the step's result: the rendered frame and the loss
         if deferred:
-            if world > 1:
-                dist.all_reduce(grid.render_gradient_accumulator.buffer)  # ONE collective on the packed volume
+            if volume is not None:
+                volume.allreduce()  # ONE collective on the packed volume: the library's own peer-memory kernel
+                grid.render_gradient_accumulator.dirty = True
+            elif world > 1:
+                dist.all_reduce(grid.render_gradient_accumulator.buffer)
             grid.materialize_render_gradients()
         elif world > 1:
-            dist.all_reduce(grid.densities.grad)
-            dist.all_reduce(grid.features.grad)
+            reducer()  # ONE collective: both dense gradients through one flat buffer
         return float(loss_total.item())  # D2H of the step's result; also orders the colour copy
 
-    # torch's autograd engine normally hands every backward() to a per-device worker thread and blocks the caller on it
-    # (two thread hops, ~25 us per call on these hosts, more than the kernels of a 4096-ray batch); the stock switch
-    # below runs the backward on the calling thread instead.  It is a caller-side setting, not part of the library.
+    static = None
+    if graph:
+        static = [torch.empty(R, 3, device=device) for _ in range(3)]
+        for t, h in zip(static, host[0]):
+            t.copy_(h)
+        grid.densities.grad = None
+        grid.features.grad = None
+        side = torch.cuda.Stream(device)
+        side.wait_stream(torch.cuda.current_stream(device))
+        with torch.cuda.stream(side):  # warm-up on a side stream, as torch's CUDA-graph recipe asks
+            for _ in range(2):
+                grid.densities.grad = None
+                grid.features.grad = None
+                render_frame(*static)
+        torch.cuda.current_stream(device).wait_stream(side)
+        torch.cuda.synchronize(device)
+        grid.densities.grad = None
+        grid.features.grad = None
+        cuda_graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(cuda_graph):
+            static_colour, static_loss = render_frame(*static)
+
+    def one_frame(idx):
+        o_h, d_h, g_h = host[idx % len(host)]
+        if graph:
+            # the step's inputs land in the graph's static buffers; .grad is re-zeroed by the graph itself (the first
+            # backward of the captured frame created it with a zero-fill that is part of the graph)
+            for t, h in zip(static, (o_h, d_h, g_h)):
+                t.copy_(h, non_blocking=True)
+            cuda_graph.replay()
+            return finish(static_colour, static_loss)
+        grid.densities.grad = None
+        grid.features.grad = None
+        # the step's inputs: rays and upstream gradients of the whole frame, pinned host memory -> device
+        o = o_h.to(device, non_blocking=True)
+        d = d_h.to(device, non_blocking=True)
+        gc = g_h.to(device, non_blocking=True)
+        return finish(*render_frame(o, d, gc))
+
     with torch.autograd.set_multithreading_enabled(engine_threads):
         for k in range(warmup):
             one_frame(k * world + rank)
@@ -525,11 +720,14 @@ def e2e_leg(device, rank, world, steps, warmup, dist, deferred=False, engine_thr
         t = torch.tensor([elapsed], device=device)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         elapsed = float(t.item())
+    api = ("per 4096-ray batch: VolumetricModel.render_rays(Rays) -> out.colour.backward(dL/dcolour); per frame: one pinned H2D copy "
+           "of rays + upstream gradients, one D2H copy of the rendered colours and the loss")
+    if graph:
+        api += "; the frame's API calls captured once with torch.cuda.graph and replayed per frame on static input buffers"
     return {"value": world * R * steps / elapsed, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
             "ms_per_step": 1e3 * elapsed / steps, "steps": steps,
             "autograd_engine": "worker threads (torch default)" if engine_threads else "calling thread (torch.autograd.set_multithreading_enabled(False))",
-            "api": "per 4096-ray batch: VolumetricModel.render_rays(Rays) -> out.colour.backward(dL/dcolour); per frame: "
-            "one pinned H2D copy of rays + upstream gradients, one D2H copy of the rendered colours and the loss"}
+            "api": api}
 
 
 def inference_leg(device, frames=24):
@@ -740,6 +938,229 @@ def sampler_leg(device):
                     f"{n * 24 / 1e6:.0f} MB"}
 
 
+def oracle_frame(bench, pose, want_grads=True, ray_stride=1):
+    """The oracle (stock ATen ops, fp32) on the bench's own GPU for frame ``pose`` with the very jitter the kernels drew
+    (voxe_jitter_fill with the per-batch (seed, offset) of DeviceBench._jitter_arg).  Test infrastructure used as the
+    checker of the timed leg, never timed as the product.  Returns colour [R,3] (NaN rows where ray_stride skipped) and,
+    with want_grads, the frame's dense voxel gradients."""
+    from oracle.voxe_oracle import OracleConfig, OracleGrid, render_oracle, render_oracle_with_grads
+
+    o, d = bench.rays[pose]
+    voxel = tuple(w / n for w, n in zip(WL["world"], WL["dims"]))
+    ogrid = OracleGrid(voxel, density_scale=WL["density_scale"], preact=WL["preact"], postact=bench.postact)
+    ocfg = OracleConfig(num_samples=WL["S"], near=WL["near"], far=WL["far"], perturb=bool(WL["perturb"]), white_bkgd=True)
+    colour = torch.full((bench.R, 3), float("nan"), device=bench.device)
+    gd = torch.zeros_like(bench.dens) if want_grads else None
+    gf = torch.zeros_like(bench.feat) if want_grads else None
+    rd = bench.nat.VoxeRenderDesc.from_buffer_copy(bench.rspec.native_bytes())
+    chunk = 8192
+    for b0, b1 in bench.batches:
+        jit = None
+        if WL["perturb"]:
+            if bench.kernel_jitter:
+                rd.rng_seed, rd.rng_offset = WL["seed"], (pose << 20) | b0
+                jit = torch.empty(b1 - b0, WL["S"], device=bench.device)
+                bench.nat.check(bench.lib.voxe_jitter_fill(rd, jit.data_ptr(), b1 - b0, bench._stream()), "voxe_jitter_fill")
+            else:
+                jit = bench.jitter
+        for c0 in range(b0, b1, chunk):
+            c1 = min(c0 + chunk, b1)
+            sel = torch.arange(c0, c1, ray_stride, device=bench.device)
+            j = None if jit is None else jit[sel - b0]
+            if want_grads:
+                res = render_oracle_with_grads(bench.dens, bench.feat, ogrid, o[sel], d[sel], ocfg, bench.G[sel], jitter=j, dtype=torch.float32)
+                gd += res["d_densities"]
+                gf += res["d_features"]
+            else:
+                with torch.no_grad():
+                    res = render_oracle(bench.dens, bench.feat, ogrid, o[sel], d[sel], ocfg, jitter=j, dtype=torch.float32)
+            colour[sel] = res["colour"]
+    return colour, gd, gf
+
+
+def parity_of_timed_leg(bench, pose, copy, world):
+    """"the timed run is the same run that is parity-checked".  Called right after the timed loop: the
+    bench's output buffers still hold the colours of the last timed frame (``pose``) and -- at N = 1 -- d_densities /
+    d_features hold its unpacked voxel gradients.  Both are compared with the oracle on the same GPU (fp32, same jitter)."""
+    colour_timed = bench.colour.clone()
+    want_grads = world == 1
+    got_d, got_f = (bench.d_dens.clone(), bench.d_feat.clone()) if want_grads else (None, None)
+    colour, gd, gf = oracle_frame(bench, pose, want_grads=want_grads)
+    out = {"frame": f"last timed frame (pose {pose}, packed-volume copy {copy}), all {bench.R} rays",
+           "oracle": "oracle/voxe_oracle.py, fp32 ATen ops on the same GPU, jitter = voxe_jitter_fill of the launches' (seed, offset)",
+           "colour_max_abs": float((colour_timed - colour).abs().max()), "colour_tol": 1e-4}
+    ok = out["colour_max_abs"] <= out["colour_tol"]
+    if want_grads:
+        # ReLU: a sample whose interpolated density is within rounding of 0 flips its derivative between two fp32
+        # evaluation orders (SURVEY.md 8c: floor 3.5e-4 of ||g||inf at 160^3); Softplus has no kink
+        tol = 2e-3 if bench.postact == "relu" else 2e-4
+        for name, got, want in (("d_densities", got_d, gd), ("d_features", got_f, gf)):
+            diff = (got - want)
+            out[name] = {"rel_l2": float(diff.norm() / want.norm().clamp_min(1e-30)),
+                         "max_abs_over_inf": float(diff.abs().max() / want.abs().max().clamp_min(1e-30))}
+            ok = ok and out[name]["rel_l2"] <= tol and out[name]["max_abs_over_inf"] <= tol
+        out["grad_tol"] = tol
+    else:
+        out["gradients"] = "N > 1: the unpacked volume is the sum over ranks; the rank-sum check is `bench.py --check`"
+    out["ok"] = bool(ok)
+    return out
+
+
+def l2_probe(device):
+    """Measured L2 bandwidth: device-to-device copy between two 24 MB buffers (both resident in the 126 MB L2), read +
+    write bytes, best of 20, CUDA events -- the same recipe MEASURED_PEAKS.json uses for HBM, at an L2-resident size."""
+    n = 6 * 2**20
+    a, b = torch.empty(n, device=device), torch.empty(n, device=device)
+    for _ in range(5):
+        b.copy_(a)
+    best = float("inf")
+    for _ in range(20):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            b.copy_(a)
+        e1.record()
+        torch.cuda.synchronize(device)
+        best = min(best, e0.elapsed_time(e1) / 10)
+    return 2 * n * 4 / (best * 1e-3) / 1e9
+
+
+def ncu_capture(kernel_substring):
+    """Counters of a kernel from the committed ncu capture (profiles/r2_ncu_kernels.json, written by tools/ncu_extract.py
+    from an `ncu --set full` run of `bench.py --ncu`; keyed by the git revision it was taken on)."""
+    path = ROOT / "profiles" / "r2_ncu_kernels.json"
+    if not path.exists():
+        return None, None
+    data = json.loads(path.read_text())
+    for name, rec in data.get("kernels", {}).items():
+        if kernel_substring in name:
+            return rec, {"file": "profiles/r2_ncu_kernels.json", "git": data.get("git"), "command": data.get("command")}
+    return None, None
+
+
+def make_peer_volume_factory(device, world, collective):
+    """N > 1: gradient volumes come from torch's symmetric-memory allocator (plumbing) so that the library's own all-reduce
+    kernel can reach every rank's copy; None selects ncclAllReduce through torch.distributed."""
+    if world == 1 or collective == "nccl":
+        return None
+    from voxe_b200.dist import PeerGradVolume
+
+    return lambda n_floats: PeerGradVolume(n_floats, device, multicast=(collective != "peer-p2p"))
+
+
+def run_check(args):
+    """`--check`: the CUDA path's gradients under data parallelism.  Every rank renders a disjoint, round-robin share of the
+    4096-ray batches of one frame; the packed gradient volumes are summed with (a) the library's peer-memory kernel
+    (multicast and plain peer loads), (b) ncclAllReduce through the C ABI on a communicator built with the voxe_nccl_*
+    helpers, (c) torch.distributed; each sum is compared, on every rank, with the volume of an unsharded render of the
+    whole frame on that rank (<= 1e-5 ||g||inf: float atomics order).  Prints one JSON line (rank 0)."""
+    import torch.distributed as dist
+
+    rank, world, local = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+    device = torch.device(f"cuda:{local}")
+    torch.cuda.set_device(device)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    WL["perturb"] = True
+    bench = DeviceBench(device, rank, world, count_s_in=False, n_lanes=1, kernel_jitter=True)
+    pose = 2
+
+    def render(batches):
+        bench.packed_grad.zero_()
+        for b0, b1 in batches:
+            bench._fwd(pose, 0, b0, b1, bench.saved)
+            bench._bwd(pose, 0, b0, b1, bench.saved)
+        torch.cuda.synchronize(device)
+        return bench.packed_grad.clone()
+
+    full = render(bench.batches)
+    share = render(bench.batches[rank::world])
+    scale = float(full.abs().max())
+    results = {}
+
+    def record(name, summed):
+        err = float((summed - full).abs().max()) / scale
+        t = torch.tensor([err], device=device)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        results[name] = {"max_abs_over_inf": float(t.item()), "ok": float(t.item()) <= 1e-5}
+
+    from voxe_b200 import _native as nat
+    from voxe_b200.dist import PeerGradVolume
+
+    lib = nat.load_library()
+    if world > 1:
+        for name, multicast in (("voxe_allreduce_grads_peer (multimem)", True), ("voxe_allreduce_grads_peer (peer loads/stores)", False)):
+            try:
+                vol = PeerGradVolume(full.numel(), device, multicast=multicast)
+                if multicast and not vol.multicast:
+                    results[name] = {"skipped": "no multicast mapping on this box"}
+                    continue
+                for _ in range(3):  # repeated use of the same signal pads
+                    vol.buffer.copy_(share)
+                    torch.cuda.synchronize(device)
+                    dist.barrier()
+                    vol.allreduce()
+                    torch.cuda.synchronize(device)
+                assert not vol.failed(), "a peer did not arrive"
+                record(name, vol.buffer)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                dist.barrier()
+                torch.cuda.synchronize(device)
+                e0.record()
+                for _ in range(10):
+                    vol.allreduce()
+                e1.record()
+                torch.cuda.synchronize(device)
+                results[name]["us"] = round(1e3 * e0.elapsed_time(e1) / 10, 1)
+                results[name]["bytes"] = full.numel() * 4
+                del vol
+            except Exception as exc:  # noqa: BLE001
+                results[name] = {"error": str(exc)[:300]}
+        # (b) the C ABI's NCCL entry point on its own communicator
+        try:
+            import ctypes
+
+            uid = torch.zeros(nat.NCCL_UNIQUE_ID_BYTES, dtype=torch.uint8)
+            if rank == 0:
+                nat.check(lib.voxe_nccl_unique_id(uid.data_ptr()), "voxe_nccl_unique_id")
+            uid_dev = uid.to(device)
+            dist.broadcast(uid_dev, 0)
+            uid = uid_dev.cpu()
+            comm = ctypes.c_void_p()
+            nat.check(lib.voxe_nccl_comm_create(ctypes.byref(comm), world, rank, uid.data_ptr()), "voxe_nccl_comm_create")
+            buf = share.clone()
+            stream = torch.cuda.current_stream(device).cuda_stream
+            nat.check(lib.voxe_allreduce_grads(comm, buf.data_ptr(), buf.numel(), stream), "voxe_allreduce_grads")
+            torch.cuda.synchronize(device)
+            record("voxe_allreduce_grads (ncclAllReduce, own communicator)", buf)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            dist.barrier()
+            torch.cuda.synchronize(device)
+            e0.record()
+            for _ in range(10):
+                lib.voxe_allreduce_grads(comm, buf.data_ptr(), buf.numel(), stream)
+            e1.record()
+            torch.cuda.synchronize(device)
+            results["voxe_allreduce_grads (ncclAllReduce, own communicator)"]["us"] = round(1e3 * e0.elapsed_time(e1) / 10, 1)
+            nat.check(lib.voxe_nccl_comm_destroy(comm), "voxe_nccl_comm_destroy")
+        except Exception as exc:  # noqa: BLE001
+            results["voxe_allreduce_grads (ncclAllReduce, own communicator)"] = {"error": str(exc)[:300]}
+        buf = share.clone()
+        dist.all_reduce(buf)
+        record("torch.distributed.all_reduce (NCCL)", buf)
+    else:
+        record("single rank (no collective)", share)
+    # the API path: render_rays + backward on each rank's share, one collective, compared with the unsharded dense gradients
+    if rank == 0:
+        ok = all(r.get("ok", True) and "error" not in r for r in results.values())
+        print(json.dumps({"check": "rank-sum of render_bwd_kernel gradients", "n_gpus": world, "frame": f"pose {pose}, {len(bench.batches)} batches dealt round-robin",
+                          "grad_inf_norm": scale, "collectives": results, "ok": ok}), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def run_ours(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -765,8 +1186,25 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=device)
     torch.manual_seed(WL["seed"] + rank)
 
+    headline = args.workload == "cfg2"
+    collective = args.collective
+    peer_factory = None
+    if world > 1 and collective != "nccl":
+        try:
+            peer_factory = make_peer_volume_factory(device, world, collective)
+            probe = peer_factory(1024)  # fails here, on every rank alike, when the box cannot map peer memory
+            collective = "voxe_allreduce_grads_peer (" + ("multimem.ld_reduce / multimem.st through the NVSwitch" if probe.multicast
+                                                          else "peer loads / stores over NVLink") + ")"
+            del probe
+        except Exception as exc:  # noqa: BLE001
+            if rank == 0:
+                print(f"[bench] peer-mapped gradient volume unavailable ({str(exc)[:200]}); using ncclAllReduce", file=sys.stderr)
+            peer_factory, collective = None, "nccl"
+    if world > 1 and peer_factory is None:
+        collective = "ncclAllReduce via torch.distributed"
+
     bench = DeviceBench(device, rank, world, count_s_in=not (args.ncu or args.sweep), n_lanes=args.lanes,
-                        kernel_jitter=args.jitter == "kernel")
+                        kernel_jitter=args.jitter == "kernel", peer_volume=peer_factory)
     barrier = (lambda: dist.barrier()) if world > 1 else None
 
     if args.ncu:  # profiler mode: eager launches of whole frames, nothing else (numbers printed here are NOT bench values)
@@ -781,9 +1219,15 @@ def run_ours(args):
         print(json.dumps({"ncu_mode": True, "frames": args.steps, "kernels_per_frame": bench.kernels_per_step}))
         return
 
-    def after_replay():
+    def allreduce():
         if world > 1:
-            dist.all_reduce(bench.packed_grad)  # ONE all-reduce of the packed voxel gradients per step
+            if bench.peer_volume is not None:
+                bench.peer_volume.allreduce()   # ONE all-reduce of the packed voxel gradients per step: the library's kernel
+            else:
+                dist.all_reduce(bench.packed_grad)
+
+    def after_replay():
+        allreduce()
         bench.unpack()
 
     if args.sweep:  # tuning mode: (L, rays per CTA, register cap) grid, isolated kernels + whole frame; not a bench line
@@ -807,18 +1251,46 @@ def run_ours(args):
                 print(json.dumps({"sweep": cfg, "error": str(exc)[:200]}), flush=True)
         return
 
+    random_views = bool(WL.get("random_views"))
+
+    def timed(b, graphs, steps, warmup):
+        """ms per step, max over ranks.  Weak-scaling workloads replay one graph (one frame) per step, rotating poses and
+        packed-volume copies; cfg 4 (random_views) replays ALL of this rank's views per step before the one all-reduce."""
+        if random_views:
+            def step_all():
+                for g in graphs:
+                    g.replay()
+                after_replay()
+            for _ in range(warmup):
+                step_all()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            if barrier:
+                barrier()
+            torch.cuda.synchronize(device)
+            e0.record()
+            for _ in range(steps):
+                step_all()
+            e1.record()
+            torch.cuda.synchronize(device)
+            if barrier:
+                barrier()
+            ms = e0.elapsed_time(e1)
+        else:
+            ms = b.time_graphs(graphs, steps, warmup, after_replay=after_replay, barrier=barrier)
+        if world > 1:
+            t = torch.tensor([ms], device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms / steps
+
     # strictly serialised variant first (one batch in flight), reported beside the headline
     serialized = None
-    if bench.n_lanes > 1:
+    if bench.n_lanes > 1 and headline:
         lanes = bench.n_lanes
         bench.n_lanes = 1
         g1 = bench.capture("both")
-        ms1 = bench.time_graphs(g1, args.steps, args.warmup, after_replay=after_replay, barrier=barrier)
-        if world > 1:
-            t = torch.tensor([ms1], device=device)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms1 = float(t.item())
-        serialized = {"value": world * bench.R / (ms1 / args.steps * 1e-3), "ms_per_step": ms1 / args.steps,
+        ms1 = timed(bench, g1, args.steps, args.warmup)
+        serialized = {"value": world * bench.R / (ms1 * 1e-3), "ms_per_step": ms1,
                       "note": "one batch in flight: fwd(k) -> bwd(k) -> fwd(k+1) ... on a single stream"}
         del g1
         bench.n_lanes = lanes
@@ -827,97 +1299,192 @@ def run_ours(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    ms = bench.time_graphs(graphs, args.steps, args.warmup, after_replay=after_replay, barrier=barrier)
+    ms_per_step = timed(bench, graphs, args.steps, args.warmup)
     clocks = sampler.stop() if rank == 0 else None
+    rays_per_step = (bench.total_views * bench.R) if random_views else world * bench.R
+    rays_per_s = rays_per_step / (ms_per_step * 1e-3)
+    last = ((args.warmup + args.steps - 1) * world + rank) % len(graphs)  # graph index = pose of the last timed frame
+    parity = None
+    if rank == 0 and (headline or args.parity) and not random_views:
+        parity = parity_of_timed_leg(bench, last, last % bench.N_GRID_COPIES, world)
     if world > 1:
-        t = torch.tensor([ms], device=device)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-    ms_per_step = ms / args.steps
-    rays_per_s = world * bench.R / (ms_per_step * 1e-3)
+        dist.barrier()
 
-    # dominant kernel alone (rank 0, N=1 semantics; other ranks idle-wait at the barrier below)
+    # the same frame on a Softplus field (the reference scripts' default): every in-grid sample scatters
+    softplus = None
+    if headline:
+        twin = DeviceBench(device, rank, world, count_s_in=False, n_lanes=args.lanes, kernel_jitter=args.jitter == "kernel",
+                           postact="softplus", share=bench)
+        tg = twin.capture("both")
+        tms = timed(twin, tg, max(10, args.steps // 4), 3)
+        softplus = {"value": world * bench.R / (tms * 1e-3), "ms_per_step": tms, "postact": "softplus"}
+        if rank == 0:
+            last_t = ((3 + max(10, args.steps // 4) - 1) * world + rank) % len(tg)
+            softplus["parity"] = parity_of_timed_leg(twin, last_t, last_t % bench.N_GRID_COPIES, world)
+        if world > 1:
+            dist.barrier()
+
+    # dominant kernel alone (rank 0; other ranks idle-wait at the barrier below)
     peak, peak_note = measured_hbm_peak()
     roof = None
     if rank == 0:
         s_in_mean = sum(t for t, _ in bench.s_in) / len(bench.s_in)
-        out = {}
-        for what, bps, bpr in (("bwd", BYTES_PER_SAMPLE_BWD, BYTES_PER_RAY_BWD), ("fwd", BYTES_PER_SAMPLE_FWD, BYTES_PER_RAY_FWD)):
-            gs = bench.capture(what, poses=sorted({0, 3 % len(bench.poses), 5 % len(bench.poses)}))
-            bench.world, saved = 1, bench.world
-            t_ms = bench.time_graphs(gs, max(8, args.steps), 3)
-            bench.world = saved
-            per_launch_us = 1e3 * t_ms / (max(8, args.steps) * len(bench.batches))
-            bytes_per_launch = (s_in_mean * bps + bench.R * bpr) / len(bench.batches)
-            out[what] = (per_launch_us, bytes_per_launch)
-        bwd_us, bwd_bytes = out["bwd"]
-        fwd_us, fwd_bytes = out["fwd"]
-        achieved = bwd_bytes / (bwd_us * 1e-6) / 1e9
-        step_bytes = s_in_mean * (BYTES_PER_SAMPLE_FWD + BYTES_PER_SAMPLE_BWD) + bench.R * 96
-        step_gbs = step_bytes / (ms_per_step * 1e-3) / 1e9
+        n_b = len(bench.batches)
+
+        def kernel_us(b, what):
+            gs = b.capture(what, poses=sorted({0, 3 % len(b.poses), 5 % len(b.poses)}))
+            b.world, saved = 1, b.world
+            t_ms = b.time_graphs(gs, max(8, args.steps), 3)
+            b.world = saved
+            return 1e3 * t_ms / (max(8, args.steps) * n_b)
+
+        def moved(b, what, us):
+            """Bytes one launch of the kernel moves (frame average), per the kernel's own counters."""
+            n_in, n_scatter = b.scatter_stats(pose=0)
+            s_in_pose0 = b.s_in[0][0] if b.s_in else bench.s_in[0][0]
+            if what == "fwd":  # every in-grid sample: 8-corner gather + one saved vector
+                per_frame = s_in_mean * (MOVED_GATHER + MOVED_SAVED_VECTOR) + bench.R * moved_bytes_per_ray("fwd")
+                frac_scatter = None
+            else:              # processed samples reload one vector; only samples with a non-zero gradient scatter
+                frac_processed, frac_scatter = n_in / s_in_pose0, n_scatter / s_in_pose0
+                per_frame = s_in_mean * (frac_processed * MOVED_SAVED_VECTOR + frac_scatter * MOVED_GATHER) + bench.R * moved_bytes_per_ray("bwd")
+            return per_frame / n_b, frac_scatter
+
+        bwd_us, fwd_us = kernel_us(bench, "bwd"), kernel_us(bench, "fwd")
+        bwd_bytes, frac_scatter = moved(bench, "bwd", bwd_us)
+        fwd_bytes, _ = moved(bench, "fwd", fwd_us)
+        model_bwd = (s_in_mean * MODEL_BYTES_PER_SAMPLE_BWD + bench.R * MODEL_BYTES_PER_RAY) / n_b
+        model_fwd = (s_in_mean * MODEL_BYTES_PER_SAMPLE_FWD + bench.R * MODEL_BYTES_PER_RAY) / n_b
+        model_step = s_in_mean * (MODEL_BYTES_PER_SAMPLE_FWD + MODEL_BYTES_PER_SAMPLE_BWD) + bench.R * 96
+        moved_step = (bwd_bytes + fwd_bytes) * n_b
+        gbs = lambda nbytes, us: nbytes / (us * 1e-6) / 1e9  # noqa: E731
+        l2_peak = l2_probe(device)
+        cap, cap_src = ncu_capture("render_bwd_kernel") if args.workload == "cfg2" else (None, None)
+        cap_f, _ = ncu_capture("render_fwd_kernel") if args.workload == "cfg2" else (None, None)
+        step_us = ms_per_step * 1e3 / (len(graphs) if random_views else 1)
         roof = {
-            "bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
-            # dram__bytes_read.sum + dram__bytes_write.sum per backward launch from the committed ncu --set full capture
-            # (profiles/r1b_bwd_kernel_metrics.txt); the grid is L2-resident at 160^3, hence far below the algorithmic bytes
-            "traffic": 14.2e6 if args.workload == "cfg2" else None,
-            "peak_source": peak_note, "kernel": "render_bwd_kernel<DEG=0,NCOL=3>", "us_per_launch": round(bwd_us, 2),
-            "algorithmic_bytes_per_launch": round(bwd_bytes), "fwd_kernel": {"us_per_launch": round(fwd_us, 2),
-            "achieved": round(fwd_bytes / (fwd_us * 1e-6) / 1e9, 1), "frac": round(fwd_bytes / (fwd_us * 1e-6) / 1e9 / peak, 4)},
-            "step": {"achieved": round(step_gbs, 1), "frac": round(step_gbs / peak, 4),  # per GPU (each rank renders its own frame)
-                     "bytes_per_ray": round(step_bytes / bench.R, 1), "s_in_per_ray": round(s_in_mean / bench.R, 2)},
+            "bound": "hbm", "achieved": round(gbs(bwd_bytes, bwd_us), 1), "peak": peak, "unit": "GB/s",
+            "frac": round(gbs(bwd_bytes, bwd_us) / peak, 4), "peak_source": peak_note,
+            "kernel": f"render_bwd_kernel<DEG={WL['sh_degree']},NCOL=3> ({bench.postact})", "us_per_launch": round(bwd_us, 2),
+            "algorithmic_bytes_per_launch": round(bwd_bytes),
+            "bytes_billed": "per in-grid sample the kernel processed: 16 B saved-vector reload + (fraction that scatters) x 8 corners x "
+                            f"{MOVED_GATHER // 8} B RED payload; per ray: rays + dL/dcolour + segment summaries; fractions counted by the kernel "
+                            "(VoxeRenderDesc.stats)",
+            "scatter_fraction": None if frac_scatter is None else round(frac_scatter, 4),
+            # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture (the grid is
+            # L2-resident at 160^3, hence far below the algorithmic bytes)
+            "traffic": None if not cap else cap.get("dram_bytes"),
+            "traffic_source": cap_src,
+            "model_frac": round(gbs(model_bwd, bwd_us) / peak, 4),
+            "model_note": "SURVEY.md 8d contract (backward billed 2 x 8 corners x (F+1) x 4 B per in-AABB sample: a re-gather the kernel "
+                          "replaced by the 16-byte reload, and a scatter for every sample) -- kept for continuity, not a ceiling",
+            "l2": {"peak_measured": round(l2_peak, 1), "unit": "GB/s", "how": "torch copy between two 24 MB (L2-resident) buffers, read+write bytes, best of 20",
+                   "lts_bytes_per_launch": None if not cap else cap.get("lts_bytes"),
+                   "achieved": None if not cap or not cap.get("lts_bytes") else round(gbs(cap["lts_bytes"], bwd_us), 1),
+                   "frac": None if not cap or not cap.get("lts_bytes") else round(gbs(cap["lts_bytes"], bwd_us) / l2_peak, 4)},
+            "fwd_kernel": {"us_per_launch": round(fwd_us, 2), "algorithmic_bytes_per_launch": round(fwd_bytes),
+                           "achieved": round(gbs(fwd_bytes, fwd_us), 1), "frac": round(gbs(fwd_bytes, fwd_us) / peak, 4),
+                           "model_frac": round(gbs(model_fwd, fwd_us) / peak, 4),
+                           "traffic": None if not cap_f else cap_f.get("dram_bytes"),
+                           "l2_frac": None if not cap_f or not cap_f.get("lts_bytes") else round(gbs(cap_f["lts_bytes"], fwd_us) / l2_peak, 4)},
+            "step": {"achieved": round(gbs(moved_step, step_us), 1), "frac": round(gbs(moved_step, step_us) / peak, 4),  # per GPU
+                     "model_frac": round(gbs(model_step, step_us) / peak, 4),
+                     "bytes_per_ray": round(moved_step / bench.R, 1), "s_in_per_ray": round(s_in_mean / bench.R, 2)},
         }
+        if softplus is not None:
+            t_bwd, t_fwd = kernel_us(twin, "bwd"), kernel_us(twin, "fwd")
+            t_bytes, t_frac = moved(twin, "bwd", t_bwd)
+            softplus["bwd_kernel"] = {"us_per_launch": round(t_bwd, 2), "scatter_fraction": round(t_frac, 4), "algorithmic_bytes_per_launch": round(t_bytes),
+                                      "achieved": round(gbs(t_bytes, t_bwd), 1), "frac": round(gbs(t_bytes, t_bwd) / peak, 4)}
+            softplus["fwd_kernel"] = {"us_per_launch": round(t_fwd, 2)}
     if world > 1:
         dist.barrier()
 
     e2e = None
-    if args.workload == "cfg2":
-        e2e = e2e_leg(device, rank, world, max(2, min(args.steps, args.e2e_steps)), min(args.warmup, 3), dist)
-        e2e_deferred = e2e_leg(device, rank, world, max(2, min(args.steps, args.e2e_steps)), min(args.warmup, 3), dist, deferred=True)
-        e2e["deferred_grads"] = {"value": e2e_deferred["value"], "ms_per_step": e2e_deferred["ms_per_step"],
-                                 "note": "same loop with VoxelGrid.accumulate_render_gradients(): gradients materialised once per frame"}
-        e2e_frame = e2e_leg(device, rank, world, max(2, min(args.steps, args.e2e_steps)), min(args.warmup, 3), dist, whole_frame=True)
-        e2e["whole_frame_call"] = {"value": e2e_frame["value"], "ms_per_step": e2e_frame["ms_per_step"],
-                                   "note": "not the headline workload: the same frame as ONE render_rays(160000 rays) + ONE backward() "
-                                           "(the SDS edit loop's calling pattern) -- what the API delivers when the caller does not split into 4096-ray batches"}
-        e2e_threads = e2e_leg(device, rank, world, max(2, min(args.steps, args.e2e_steps)), min(args.warmup, 3), dist, engine_threads=True)
-        e2e["default_engine_threads"] = {"value": e2e_threads["value"], "ms_per_step": e2e_threads["ms_per_step"],
-                                         "note": "same loop with torch's default multi-threaded autograd engine (host-bound: ~50 us of engine overhead per backward())"}
+    if headline:
+        n_e2e, w_e2e = max(2, min(args.steps, args.e2e_steps)), min(args.warmup, 3)
+        e2e = e2e_leg(device, rank, world, n_e2e, w_e2e, dist)
+        variants = {
+            "cuda_graph": (dict(graph=True), "the same API calls of a frame captured once with torch.cuda.graph and replayed (stock torch; "
+                                             "H2D of the frame's inputs and D2H of its results stay in the timed region)"),
+            "calling_thread_engine": (dict(engine_threads=False), "same loop under torch.autograd.set_multithreading_enabled(False): backward() "
+                                                                  "runs on the calling thread (a caller-side switch)"),
+            "deferred_grads": (dict(deferred=True, peer_volume=peer_factory), "same loop with VoxelGrid.accumulate_render_gradients(): gradients "
+                                                                              "materialised once per frame"),
+            "whole_frame_call": (dict(whole_frame=True), "not the headline workload: the same frame as ONE render_rays(160000 rays) + ONE backward() "
+                                                         "(the SDS edit loop's calling pattern)"),
+        }
+        for name, (kw, note) in variants.items():
+            try:
+                r = e2e_leg(device, rank, world, n_e2e, w_e2e, dist, **kw)
+                e2e[name] = {"value": r["value"], "ms_per_step": r["ms_per_step"], "note": note}
+            except Exception as exc:  # noqa: BLE001 -- a variant that cannot run is reported, the headline stands
+                e2e[name] = {"error": str(exc)[:300], "note": note}
+        e2e["collective"] = None if world == 1 else "one per frame: VoxelGradAllReducer (flat buffer of both dense gradients, ncclAllReduce)"
 
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu and args.workload == "cfg2":
-        r = cpu_leg(steps=6, warmup=1, budget_s=25.0)
-        cpu = {"value": r["rays_per_s"], "unit": "rays/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]}
+    cpu = gpu_baseline = None
+    if rank == 0 and world == 1 and headline:
+        if not args.no_cpu:
+            r = reference_subprocess("cpu", 8, 1)
+            if "error" in r:
+                cpu = {"error": r["error"]}
+            else:
+                cpu = dict(r["cpu_baseline"])
+        r = reference_subprocess("cuda", 10, 3)
+        if "error" in r:
+            gpu_baseline = {"error": r["error"]}
+        else:
+            gpu_baseline = {"value": r["value"], "unit": "rays/s", "ms_per_batch": r["ms_per_step"], "kind": r["cpu_baseline"]["kind"],
+                            "what": "the same 4096-ray batches fwd+bwd through stock ATen ops on this GPU (BASELINE.md: the bar the kernels have to beat)",
+                            "sample": r["cpu_baseline"]["sample"],
+                            "ours_serialized_over_baseline": None if not serialized else round(serialized["value"] / r["value"], 1)}
 
     fused_step = None
-    if rank == 0 and world == 1 and args.workload == "cfg2":
+    if rank == 0 and world == 1 and headline:
         fused_step = fused_step_leg(device, peak)
 
     inference = None
-    if rank == 0 and world == 1 and args.workload == "cfg2":
+    if rank == 0 and world == 1 and headline:
         inference = inference_leg(device)
 
     regularizers = sampler = None
-    if rank == 0 and world == 1 and args.workload == "cfg2":
+    if rank == 0 and world == 1 and headline:
         regularizers = regularizers_leg(device, peak)
         sampler = sampler_leg(device)
 
     if rank == 0:
+        if random_views:
+            step = (f"{bench.total_views} get_random_pose views of {WL['height']}x{WL['width']} dealt round-robin over {world} rank(s), each view one "
+                    f"launch pair (fwd, bwd) accumulating into the packed gradient volume, then ONE all-reduce ({bench.packed_grad.numel() * 4 / 1e6:.0f} MB) "
+                    "+ unpack; total work fixed as N grows")
+        else:
+            step = (f"one {WL['height']}x{WL['width']} frame = {len(bench.batches)} batches x (fwd, bwd; jitter "
+                    f"{'generated in-kernel' if bench.kernel_jitter else 'drawn by torch.rand'}) + grad zero-fill + unpack"
+                    + (f" + 1 all-reduce of the packed voxel grads ({bench.packed_grad.numel() * 4 / 1e6:.0f} MB)" if world > 1 else ""))
         line = {
             "metric": "rays/s fwd+bwd, 160^3 SH-0 grid, 400x400 render", "value": rays_per_s, "unit": "rays/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "strong" if random_views else "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WL["name"], "step": f"one {WL['height']}x{WL['width']} frame = {len(bench.batches)} batches x (fwd, bwd; jitter {'generated in-kernel' if bench.kernel_jitter else 'drawn by torch.rand'}) + grad zero-fill + unpack"
-                       + (" + 1 NCCL all-reduce of packed voxel grads" if world > 1 else ""),
-                       "batches_in_flight": f"{bench.n_lanes} (each launch is one <=4096-ray batch with its own workspace; gradients accumulate "
+            "config": {"workload": WL["name"], "step": step,
+                       "batches_in_flight": f"{bench.n_lanes} (each launch is one <={WL['batch']}-ray batch with its own workspace; gradients accumulate "
                                             "over the frame, so batch k+1's forward does not wait for batch k's backward)",
                        "l2": f"{bench.N_GRID_COPIES} rotating packed-volume copies ({bench.N_GRID_COPIES * bench.packed[0].numel() * 4 / 1e6:.0f} MB) + "
                              f"{bench.packed_grad.numel() * 4 / 1e6:.0f} MB gradient volume + per-batch workspaces > 126 MB L2; {len(bench.poses)} poses rotate",
                        "parallelism": f"ray/view data parallel x{world}", "timing": "CUDA events around K graph replays, max over ranks",
+                       "collective": None if world == 1 else collective,
                        "host_cpus_per_rank": len(pinned_cpus) if pinned_cpus else "unpinned"},
-            "e2e": e2e, "gpu_launches": args.steps * bench.kernels_per_step, "roofline": roof, "clocks": clocks,
+            "e2e": e2e, "gpu_launches": args.steps * ((bench.kernels_per_step - 1) * (len(graphs) if random_views else 1) + 1
+                                                         + (1 if bench.peer_volume is not None else 0)), "roofline": roof,
+            "clocks": clocks, "parity": parity,
         }
+        if softplus:
+            line["value_softplus"] = softplus["value"]
+            line["softplus"] = softplus
         if cpu:
             line["cpu_baseline"] = cpu
+        if gpu_baseline:
+            line["gpu_baseline"] = gpu_baseline
         if fused_step:
             line["fused_step"] = fused_step
         if serialized:
@@ -940,11 +1507,18 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--ref-device", choices=["cpu", "cuda"], default="cpu",
+                    help="--impl reference: cpu = the reference arm (host cores); cuda = the stock-ATen GPU baseline")
     ap.add_argument("--e2e-steps", type=int, default=8)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--ncu", action="store_true", help="profiler mode: run --steps eager frames and exit")
+    ap.add_argument("--check", action="store_true", help="rank-sum check of the CUDA path's gradients through every collective; not a bench line")
+    ap.add_argument("--parity", action="store_true", help="run the in-run oracle check for workloads other than cfg2 as well")
     ap.add_argument("--workload", choices=["cfg2", "cfg3", "cfg4", "cfg5"], default="cfg2",
-                    help="cfg2 is the headline (the line the driver reads); the others are recorded in DESIGN.md")
+                    help="cfg2 is the headline (the line the driver reads); the others are recorded in DESIGN.md / profiles/")
+    ap.add_argument("--collective", choices=["peer", "peer-p2p", "nccl"], default="peer",
+                    help="N > 1: voxe_allreduce_grads_peer on a peer-mapped gradient volume (multimem when the box has NVLS; peer-p2p "
+                         "forces plain peer loads/stores), or ncclAllReduce through torch.distributed")
     ap.add_argument("--lanes", type=int, default=3, help="ray batches in flight within a frame (streams)")
     ap.add_argument("--jitter", choices=["kernel", "buffer"], default="kernel",
                     help="stratified jitter of the device leg: generated inside the kernels (counter-based hash) or torch-drawn [R,S] buffers")
@@ -964,6 +1538,8 @@ def main():
         nat.set_tuning(*(int(x) for x in args.tune.split(",")))
     if args.impl == "reference":
         run_reference(args)
+    elif args.check:
+        run_check(args)
     else:
         run_ours(args)
 

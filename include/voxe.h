@@ -23,7 +23,7 @@
  * Conventions
  *   - every pointer is a DEVICE pointer to fp32 data owned by the caller (torch allocations in the Python
  *     binding); the library allocates nothing persistent and keeps no global state except a thread-local error
- *     string and the optional tuning override;
+ *     string, the optional tuning override and the run-time handle of libnccl (voxe_allreduce_grads only);
  *   - kernels are enqueued asynchronously on `stream`; the calls never synchronise;
  *   - return value 0 = success, otherwise a VOXE_ERR_* code (or a cudaError_t offset by VOXE_ERR_CUDA_BASE);
  *     `voxe_last_error()` describes the most recent failure on the calling thread;
@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define VOXE_ABI_VERSION 11
+#define VOXE_ABI_VERSION 12
 
 #if defined(__GNUC__)
 #define VOXE_API __attribute__((visibility("default")))
@@ -69,7 +69,8 @@ enum {
   VOXE_ERR_INVALID_ARGUMENT = 1,
   VOXE_ERR_UNSUPPORTED = 2,       /* combination outside the fused set (e.g. SH degree > 3, S > 4096)       */
   VOXE_ERR_NO_DEVICE = 3,
-  VOXE_ERR_CUDA_BASE = 1000       /* + cudaError_t */
+  VOXE_ERR_CUDA_BASE = 1000,      /* + cudaError_t */
+  VOXE_ERR_NCCL_BASE = 2000       /* + ncclResult_t (voxe_allreduce_grads and the voxe_nccl_* helpers) */
 };
 
 /* Geometry + activations of a voxel grid (VoxelGrid, voxels.py:46-130). */
@@ -97,6 +98,12 @@ typedef struct VoxeRenderDesc {
   float noise_std;        /* stochastic_density_noise_std; != 0 needs `noise` [R,S] (standard normal)       */
   uint64_t rng_seed;      /* VOXE_FLAG_PERTURB with jitter == NULL: the U[0,1) draws of sample.py:63 are generated */
   uint64_t rng_offset;    /* inside the kernels: a counter-based PCG hash of (rng_seed, rng_offset, ray, sample)     */
+  const int64_t* rng_seed_dev;   /* NULL, or DEVICE pointers to the seed and the offset of a generator whose state is  */
+  const int64_t* rng_offset_dev; /* registered with a CUDA graph (torch's PhiloxCudaState under capture): the kernels   */
+  uint64_t rng_offset_intragraph;/* then use (*rng_seed_dev, *rng_offset_dev + rng_offset_intragraph), re-read on replay */
+  uint64_t* stats;        /* NULL, or two DEVICE counters the backward adds to (measurement runs): [0] += in-grid     */
+                          /* samples it processed, [1] += samples whose 8-corner scatter it issued (a sample whose    */
+                          /* gradient is exactly zero -- e.g. ReLU at a non-positive density -- scatters nothing)     */
 } VoxeRenderDesc;
 
 VOXE_API int voxe_abi_version(void);
@@ -142,15 +149,25 @@ VOXE_API int voxe_render_fwd(const VoxeGridDesc* grid, const VoxeRenderDesc* ren
                     float* colour, float* depth, float* acc, float* disparity, float* saved, int64_t num_rays,
                     voxe_stream_t stream);
 
-/* Backward: re-gathers per sample (no O(R*S) activations are stored), and scatter-ADDS dL/d(packed) into
- * `packed_grad` (same layout and size as `packed`; caller-zeroed; accumulate-into, so several ray batches or both renders of a training step
- * can share one buffer).  `saved` is the workspace the matching forward call filled (same grid, rays, jitter, noise).
- * g_depth / g_acc / g_disp may be NULL (treated as zero).  The disparity gradient is applied only on rays whose
- * disparity is finite (depth/acc > 1e-10). */
+/* Backward: per sample, reloads the 16-byte vector the forward saved (no re-gather of the 8 corners, no O(R*S)
+ * activations beyond that vector), recomputes the compositing weights and scatter-ADDS dL/d(packed) into `packed_grad`
+ * (same layout and size as `packed`; caller-zeroed; accumulate-into, so several ray batches or both renders of a training
+ * step can share one buffer).  `saved` is the workspace the matching forward call filled (same grid, rays, jitter,
+ * noise, same voxe_set_tuning state).  g_depth / g_acc / g_disp may be NULL (treated as zero).  The disparity gradient
+ * is applied only on rays whose disparity is finite (depth/acc > 1e-10).
+ *   touched / touch_tag   NULL, or voxe_touched_bytes() bytes (one per 2x2x2 brick of the packed volume): every sample
+ *                         that scatters stores (uint8_t)touch_tag at the brick of its first corner, so that
+ *                         voxe_consume_grad can visit only what this call wrote.  Flags are never cleared by the
+ *                         library: use a new tag (1..255) for every backward/consume pair and memset the flags to 0
+ *                         before a tag value is used again. */
 VOXE_API int voxe_render_bwd(const VoxeGridDesc* grid, const VoxeRenderDesc* render, const float* packed,
                     const float* rays_o, const float* rays_d, const float* jitter, const float* noise,
                     const float* saved, const float* g_colour, const float* g_depth, const float* g_acc,
-                    const float* g_disp, float* packed_grad, int64_t num_rays, voxe_stream_t stream);
+                    const float* g_disp, float* packed_grad, uint8_t* touched, int32_t touch_tag, int64_t num_rays,
+                    voxe_stream_t stream);
+
+/* Bytes of a `touched` flag array for `grid`: one per 2x2x2 brick of the packed volume. */
+VOXE_API int64_t voxe_touched_bytes(const VoxeGridDesc* grid);
 
 /* Pinhole camera of voxe_render_camera (CameraIntrinsics + CameraPose, utils/imaging_utils.py:17-30). */
 typedef struct VoxeCameraDesc {
@@ -187,9 +204,11 @@ VOXE_API int voxe_jitter_fill(const VoxeRenderDesc* render, float* out, int64_t 
  * again when the call returns.  A ray batch touches a few percent of the voxels; this pass reads the volume once and
  * writes only what the batch touched, replacing zero-fill + voxe_unpack_grad + a dense `.grad +=` per backward call
  * (the autograd accumulation of trainers.py:350 / sds_trainer.py:332).  Requires d_* to hold valid values (zeros for
- * a fresh gradient). */
+ * a fresh gradient).
+ * With `touched` (the flag array the backward call(s) since the last consume wrote with `touch_tag`) only bricks that can
+ * hold gradients are read: ~1 byte per brick instead of the whole volume (0.5 MB against 68 MB at 160^3). */
 VOXE_API int voxe_consume_grad(const VoxeGridDesc* grid, float* packed_grad, float* d_densities, float* d_features,
-                      voxe_stream_t stream);
+                      const uint8_t* touched, int32_t touch_tag, voxe_stream_t stream);
 
 /* One Adam step on the two grids, fused with everything else the optimiser step does to them
  * (replaces `optimizer.zero_grad(); ...; optimizer.step()` of thre3d_atom/modules/trainers.py:247-255,348-351 and
@@ -200,7 +219,9 @@ VOXE_API int voxe_consume_grad(const VoxeGridDesc* grid, float* packed_grad, flo
  *   densities / features (reference layout), the moments packed_m / packed_v live in the packed layout
  *   (voxe_packed_floats() floats each; convert with voxe_pack_grid / voxe_unpack_grad for checkpoints), and
  *   `packed_grad` is zeroed -- one streaming pass, ten 16-byte-coalesced streams.
- * `step` is the 1-based step count AFTER this update (bias corrections 1 - beta^step). */
+ * `step` is the 1-based step count AFTER this update (bias corrections 1 - beta^step).  `densities` or `features` may be
+ * NULL: that tensor is frozen (requires_grad == False upstream) -- its values and moments are left untouched and whatever
+ * the backward scattered for it is discarded. */
 typedef struct VoxeAdamDesc {
   double lr;     /* doubles, like the Python scalars torch.optim.Adam derives 1 - beta and lr / (1 - beta1^step) from */
   double beta1;
@@ -269,6 +290,39 @@ VOXE_API int voxe_sample_rays(const VoxeSamplerDesc* sampler, const float* poses
                               const float* src_rays_d, const float* pixels, const int64_t* indices_in, int64_t sample_size,
                               int64_t* indices_out, float* rays_o, float* rays_d, float* pixels_out, voxe_stream_t stream);
 
+/* ---- the step's one collective (SURVEY.md row e): SUM of the packed gradient volume over the data-parallel ranks ----------
+ * The reference is single-GPU; with ray batches / views sharded over ranks and the grid replicated, the dense gradients
+ * autograd would have produced for the whole batch (trainers.py:350, sds_trainer.py:332) are the sum of the ranks' volumes.
+ *
+ * voxe_allreduce_grads_peer: own two-shot kernel over peer-mapped memory (NVLink / NVSwitch), in place, one launch per
+ * rank on `stream`; all ranks must call it with the same n_floats (a multiple of 4).  Every rank's volume and signal pad
+ * must be mapped into the calling process (CUDA IPC, VMM export, or torch's symmetric memory in the Python binding):
+ *   buffers[k]  rank k's gradient volume (buffers[rank] is the local one), 16-byte aligned, same size everywhere
+ *   signals[k]  rank k's signal pad: VOXE_SIGNAL_WORDS uint32, zeroed once at allocation, used only by this call
+ *   multicast   NVLS multicast mapping of the volumes (multimem.ld_reduce / multimem.st: the switch adds and
+ *               replicates), or NULL: plain peer loads and stores
+ *   fail_flag   NULL, or a device uint32 that is OR-ed with 1 when a peer did not arrive within ~2 s (the kernel then
+ *               gives up instead of hanging the GPU; the volume contents are undefined). */
+#define VOXE_MAX_PEERS 16
+#define VOXE_SIGNAL_WORDS 4096
+typedef struct VoxePeerDesc {
+  int32_t world_size, rank;
+  float* buffers[VOXE_MAX_PEERS];
+  uint32_t* signals[VOXE_MAX_PEERS];
+  float* multicast;
+} VoxePeerDesc;
+VOXE_API int voxe_allreduce_grads_peer(const VoxePeerDesc* peers, int64_t n_floats, uint32_t* fail_flag, voxe_stream_t stream);
+
+/* voxe_allreduce_grads: ncclAllReduce(SUM, fp32, in place) of `buf` on `nccl_comm` (an ncclComm_t) -- for hosts whose
+ * volumes are not peer-mapped.  libnccl.so.2 is opened at run time (no link-time dependency); the helpers below build a
+ * communicator without any other framework: rank 0 calls voxe_nccl_unique_id and ships the VOXE_NCCL_UNIQUE_ID_BYTES bytes
+ * to the other ranks by its own means, then every rank calls voxe_nccl_comm_create (collective). */
+#define VOXE_NCCL_UNIQUE_ID_BYTES 128
+VOXE_API int voxe_nccl_unique_id(void* id_out);
+VOXE_API int voxe_nccl_comm_create(void** nccl_comm_out, int32_t world_size, int32_t rank, const void* id);
+VOXE_API int voxe_nccl_comm_destroy(void* nccl_comm);
+VOXE_API int voxe_allreduce_grads(void* nccl_comm, float* buf, int64_t n_floats, voxe_stream_t stream);
+
 /* Launch-shape override for tuning runs: samples per thread (1..64; the number of depth segments per ray is
  * ceil(S / samples_per_thread)), rays per CTA (power of two <= 32) and the register budget of the kernel variant
  * (64, 80, 96 or 128); 0 restores the built-in choice of that knob.  Does not change results beyond fp32 summation
@@ -278,8 +332,9 @@ VOXE_API int voxe_set_tuning(int samples_per_thread, int rays_per_cta, int regis
 /* Number of kernels this library has launched on the calling process since load (for bench accounting). */
 VOXE_API int64_t voxe_launch_count(void);
 
-/* Render launches that took a flag-specialised kernel variant (environment VOXE_SPECIALISED_KERNELS=1, read once at the
- * first render call: same arithmetic as the generic kernels with the per-call switches resolved at compile time). */
+/* Render launches that took a flag-specialised kernel variant (same arithmetic as the generic kernels with the per-call
+ * switches resolved at compile time; the default wherever a variant exists, environment VOXE_SPECIALISED_KERNELS=0, read
+ * once at the first render call, forces the generic kernels). */
 VOXE_API int64_t voxe_specialised_launch_count(void);
 
 #ifdef __cplusplus

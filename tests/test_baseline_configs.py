@@ -6,7 +6,7 @@
   cfg 5  512^3 SH-2 grid (15 GB of parameters), 1024x1024 camera, S=512, a 65 536-ray batch
 
 Each is checked against the oracle on a strided subset of its rays (fp64 on the CPU; for the 15 GB grid the oracle runs
-its plain ATen arithmetic in fp32 on the device, forward only) and through size-independent properties: per-ray results
+its plain ATen arithmetic in fp32 on the device, forward AND autograd backward) and through size-independent properties: per-ray results
 do not depend on how rays are batched (bit-exact), the backward is linear in the upstream gradient, missing rays are
 pure background.
 """
@@ -153,6 +153,23 @@ def test_cfg5_hbm_stress_grid():
     scale_f, scale_d = float(grid.features.grad.abs().max()), float(grid.densities.grad.abs().max())
     assert float((g1 - grid.features.grad).abs().max()) <= 2e-5 * scale_f
     assert float((d1 - grid.densities.grad).abs().max()) <= 2e-5 * scale_d
-    del g1, d1, grid
+    del g1, d1
+    gc.collect()
+    torch.cuda.empty_cache()
+
+    # the backward itself against the oracle's autograd (plain ATen fp32 on the device): 256 rays strided over the batch,
+    # voxel gradients compared over the whole 512^3 x 28 volume (= over the touched voxels: both are zero elsewhere).  This
+    # is the one DRAM-sized case, and the one where the TMA-reduction scatter crosses 112-byte voxels at scale.
+    gsel = ga[sel].contiguous()
+    _render_all(grid, ro[sel].contiguous(), rd[sel].contiguous(), cfg, gsel)
+    got_f, got_d = grid.features.grad, grid.densities.grad
+    want = render_oracle_with_grads(grid.densities.detach(), grid.features.detach(), og, ro[sel], rd[sel], oc, gsel, dtype=torch.float32)
+    for name, got, ref in (("d_features", got_f, want["d_features"]), ("d_densities", got_d, want["d_densities"])):
+        norm, peak = float(ref.norm()), float(ref.abs().max())
+        assert peak > 0 and int((ref != 0).sum()) > 1000, name
+        ref.sub_(got)  # in place: these are 15 GB tensors
+        l2, linf = float(ref.norm()) / norm, float(ref.abs().max()) / peak
+        assert l2 <= 1e-4 and linf <= 1e-4, f"cfg5 {name}: relL2 {l2:.2e} maxabs/inf {linf:.2e}"
+    del want, got_f, got_d, grid
     gc.collect()
     torch.cuda.empty_cache()

@@ -17,12 +17,13 @@ thread_local char g_error[512] = "";
 std::atomic<int64_t> g_launches{0}, g_specialised{0};
 std::atomic<int> g_tune_l{0}, g_tune_rpc{0}, g_tune_reg{0};
 
-// VOXE_SPECIALISED_KERNELS=1: take the flag-specialised kernel variants where they exist (same arithmetic, fewer
-// instructions per sample; opt-in until their parity run on a B200 is recorded -- see DESIGN.md section 8)
+// The flag-specialised kernel variants (same arithmetic, per-call switches resolved at compile time: -14 % forward time on
+// the benchmark batch, parity suites green under them, profiles/r2a_specialised_ab.txt) are taken wherever they exist;
+// VOXE_SPECIALISED_KERNELS=0 forces the generic kernels (A/B runs, tests/test_specialised_kernels.py).
 bool specialised_kernels() {
   static const bool on = [] {
     const char* v = std::getenv("VOXE_SPECIALISED_KERNELS");
-    return v != nullptr && v[0] == '1';
+    return !(v != nullptr && v[0] == '0');
   }();
   return on;
 }
@@ -122,6 +123,11 @@ int fill_params(const VoxeGridDesc* g, const VoxeRenderDesc* r, int64_t R, voxe:
   p.noise_std = r->noise_std;
   p.rng_seed = r->rng_seed;
   p.rng_offset = r->rng_offset;
+  if (r->rng_seed_dev != nullptr && r->rng_offset_dev != nullptr) {
+    p.rng_seed_dev = reinterpret_cast<const long long*>(r->rng_seed_dev);
+    p.rng_offset_dev = reinterpret_cast<const long long*>(r->rng_offset_dev);
+    p.rng_intragraph = r->rng_offset_intragraph;
+  }
   p.lin_step = 1.0f / (float)(r->num_samples - 1);
   p.flags = r->flags;
   p.preact = g->preact;
@@ -195,19 +201,27 @@ int voxe_jitter_fill(const VoxeRenderDesc* render, float* out, int64_t num_rays,
   if (!render || render->num_samples < 1 || !out || num_rays < 0 || num_rays > 0x7fffffff)
     return fail(VOXE_ERR_INVALID_ARGUMENT, "voxe_jitter_fill: bad arguments");
   if (num_rays == 0) return VOXE_OK;
-  cudaError_t e = voxe::launch_jitter_fill((int)num_rays, render->num_samples, render->rng_seed, render->rng_offset, out,
-                                           (cudaStream_t)stream);
+  cudaError_t e = voxe::launch_jitter_fill((int)num_rays, render->num_samples, render->rng_seed, render->rng_offset,
+                                           reinterpret_cast<const long long*>(render->rng_seed_dev),
+                                           reinterpret_cast<const long long*>(render->rng_offset_dev), render->rng_offset_intragraph,
+                                           out, (cudaStream_t)stream);
   if (e != cudaSuccess) return cuda_fail(e, "voxe_jitter_fill launch");
   g_launches.fetch_add(1);
   return VOXE_OK;
 }
 
+int64_t voxe_touched_bytes(const VoxeGridDesc* grid) {
+  if (!grid || grid->dims[0] < 1 || grid->dims[1] < 1 || grid->dims[2] < 1) return 0;
+  return voxe::packed_bricks(grid->dims);
+}
+
 int voxe_consume_grad(const VoxeGridDesc* grid, float* packed_grad, float* d_densities, float* d_features,
-                      voxe_stream_t stream) {
+                      const uint8_t* touched, int32_t touch_tag, voxe_stream_t stream) {
   if (int rc = check_grid(grid)) return rc;
   if (!packed_grad) return fail(VOXE_ERR_INVALID_ARGUMENT, "voxe_consume_grad: NULL packed_grad");
+  if (touched && (touch_tag < 1 || touch_tag > 255)) return fail(VOXE_ERR_INVALID_ARGUMENT, "voxe_consume_grad: touch_tag must be in 1..255");
   cudaError_t e = voxe::launch_consume_grad(packed_grad, d_densities, d_features, grid->dims, grid->n_features,
-                                            grid->channels, (cudaStream_t)stream);
+                                            grid->channels, touched, touch_tag, (cudaStream_t)stream);
   if (e != cudaSuccess) return cuda_fail(e, "voxe_consume_grad launch");
   g_launches.fetch_add(1);
   return VOXE_OK;
@@ -218,8 +232,8 @@ int voxe_adam_step(const VoxeGridDesc* grid, const VoxeAdamDesc* adam, float* de
                    float* packed_v, voxe_stream_t stream) {
   if (int rc = check_grid(grid)) return rc;
   if (!adam) return fail(VOXE_ERR_INVALID_ARGUMENT, "voxe_adam_step: NULL descriptor");
-  if (!densities || !features || !packed || !packed_m || !packed_v)
-    return fail(VOXE_ERR_INVALID_ARGUMENT, "voxe_adam_step: NULL parameter / packed volume / moment buffer");
+  if ((!densities && !features) || !packed || !packed_m || !packed_v)
+    return fail(VOXE_ERR_INVALID_ARGUMENT, "voxe_adam_step: NULL parameters / packed volume / moment buffer");
   if (adam->step < 1) return fail(VOXE_ERR_INVALID_ARGUMENT, "voxe_adam_step: step must be >= 1 (got %d)", adam->step);
   if (!(adam->beta1 >= 0.0 && adam->beta1 < 1.0 && adam->beta2 >= 0.0 && adam->beta2 < 1.0 && adam->eps >= 0.0))
     return fail(VOXE_ERR_INVALID_ARGUMENT, "voxe_adam_step: betas must be in [0,1) and eps >= 0");
@@ -271,6 +285,58 @@ int voxe_pair_loss_grad(const float* a, const float* b, int64_t n, int32_t mode,
     return fail(VOXE_ERR_INVALID_ARGUMENT, "voxe_pair_loss_grad: correlation mode reads the workspace voxe_pair_loss filled");
   cudaError_t e = voxe::launch_pair_grad(a, b, n, mode, 1e-7f, workspace, upstream, scale, grad, accumulate != 0, (cudaStream_t)stream);
   if (e != cudaSuccess) return cuda_fail(e, "voxe_pair_loss_grad launch");
+  g_launches.fetch_add(1);
+  return VOXE_OK;
+}
+
+int voxe_allreduce_grads_peer(const VoxePeerDesc* peers, int64_t n_floats, uint32_t* fail_flag, voxe_stream_t stream) {
+  if (!peers) return fail(VOXE_ERR_INVALID_ARGUMENT, "voxe_allreduce_grads_peer: NULL descriptor");
+  if (peers->world_size < 1 || peers->world_size > VOXE_MAX_PEERS || peers->rank < 0 || peers->rank >= peers->world_size)
+    return fail(VOXE_ERR_INVALID_ARGUMENT, "voxe_allreduce_grads_peer: world_size must be in 1..%d and rank inside it", VOXE_MAX_PEERS);
+  if (n_floats < 0 || (n_floats & 3)) return fail(VOXE_ERR_INVALID_ARGUMENT, "voxe_allreduce_grads_peer: n_floats must be a multiple of 4");
+  for (int k = 0; k < peers->world_size; ++k) {
+    if (!peers->buffers[k] || !peers->signals[k]) return fail(VOXE_ERR_INVALID_ARGUMENT, "voxe_allreduce_grads_peer: NULL buffer / signal pad of rank %d", k);
+    if (reinterpret_cast<uintptr_t>(peers->buffers[k]) & 15) return fail(VOXE_ERR_INVALID_ARGUMENT, "voxe_allreduce_grads_peer: buffers must be 16-byte aligned");
+  }
+  if (reinterpret_cast<uintptr_t>(peers->multicast) & 15) return fail(VOXE_ERR_INVALID_ARGUMENT, "voxe_allreduce_grads_peer: multicast mapping must be 16-byte aligned");
+  if (n_floats == 0 || peers->world_size == 1) return VOXE_OK;
+  cudaError_t e = voxe::launch_allreduce_peer(*peers, n_floats, fail_flag, (cudaStream_t)stream);
+  if (e != cudaSuccess) return cuda_fail(e, "voxe_allreduce_grads_peer launch");
+  g_launches.fetch_add(1);
+  return VOXE_OK;
+}
+
+static int nccl_fail(int rc, const char* what) {
+  return fail(VOXE_ERR_NCCL_BASE + rc, "%s: NCCL error %d (%s)", what, rc, voxe::nccl_error_string(rc));
+}
+
+int voxe_nccl_unique_id(void* id_out) {
+  if (!id_out) return fail(VOXE_ERR_INVALID_ARGUMENT, "voxe_nccl_unique_id: NULL output");
+  if (const char* why = voxe::nccl_unavailable()) return fail(VOXE_ERR_UNSUPPORTED, "NCCL is not available: %s", why);
+  if (int rc = voxe::nccl_unique_id(id_out)) return nccl_fail(rc, "ncclGetUniqueId");
+  return VOXE_OK;
+}
+
+int voxe_nccl_comm_create(void** nccl_comm_out, int32_t world_size, int32_t rank, const void* id) {
+  if (!nccl_comm_out || !id || world_size < 1 || rank < 0 || rank >= world_size)
+    return fail(VOXE_ERR_INVALID_ARGUMENT, "voxe_nccl_comm_create: bad arguments");
+  if (const char* why = voxe::nccl_unavailable()) return fail(VOXE_ERR_UNSUPPORTED, "NCCL is not available: %s", why);
+  if (int rc = voxe::nccl_comm_create(nccl_comm_out, world_size, rank, id)) return nccl_fail(rc, "ncclCommInitRank");
+  return VOXE_OK;
+}
+
+int voxe_nccl_comm_destroy(void* nccl_comm) {
+  if (!nccl_comm) return VOXE_OK;
+  if (const char* why = voxe::nccl_unavailable()) return fail(VOXE_ERR_UNSUPPORTED, "NCCL is not available: %s", why);
+  if (int rc = voxe::nccl_comm_destroy(nccl_comm)) return nccl_fail(rc, "ncclCommDestroy");
+  return VOXE_OK;
+}
+
+int voxe_allreduce_grads(void* nccl_comm, float* buf, int64_t n_floats, voxe_stream_t stream) {
+  if (!nccl_comm || !buf || n_floats < 0) return fail(VOXE_ERR_INVALID_ARGUMENT, "voxe_allreduce_grads: NULL communicator / buffer");
+  if (const char* why = voxe::nccl_unavailable()) return fail(VOXE_ERR_UNSUPPORTED, "NCCL is not available: %s", why);
+  if (n_floats == 0) return VOXE_OK;
+  if (int rc = voxe::nccl_allreduce_sum_f32(nccl_comm, buf, (size_t)n_floats, (cudaStream_t)stream)) return nccl_fail(rc, "ncclAllReduce");
   g_launches.fetch_add(1);
   return VOXE_OK;
 }
@@ -407,9 +473,11 @@ int voxe_render_infer(const VoxeGridDesc* grid, const VoxeRenderDesc* render, co
 int voxe_render_bwd(const VoxeGridDesc* grid, const VoxeRenderDesc* render, const float* packed,
                     const float* rays_o, const float* rays_d, const float* jitter, const float* noise,
                     const float* saved, const float* g_colour, const float* g_depth, const float* g_acc,
-                    const float* g_disp, float* packed_grad, int64_t num_rays, voxe_stream_t stream) {
+                    const float* g_disp, float* packed_grad, uint8_t* touched, int32_t touch_tag, int64_t num_rays,
+                    voxe_stream_t stream) {
   if (int rc = check_grid(grid)) return rc;
   if (int rc = check_render(grid, render, jitter, noise)) return rc;
+  if (touched && (touch_tag < 1 || touch_tag > 255)) return fail(VOXE_ERR_INVALID_ARGUMENT, "voxe_render_bwd: touch_tag must be in 1..255");
   if (num_rays < 0 || num_rays > 0x7fffffff) return fail(VOXE_ERR_INVALID_ARGUMENT, "num_rays out of range");
   if (num_rays == 0) return VOXE_OK;
   if (!packed || !rays_o || !rays_d || !g_colour || !packed_grad || !saved)
@@ -428,6 +496,9 @@ int voxe_render_bwd(const VoxeGridDesc* grid, const VoxeRenderDesc* render, cons
   p.g_depth = g_depth;
   p.g_acc = g_acc;
   p.g_disp = g_disp;
+  p.touched = touched;
+  p.touch_tag = touch_tag;
+  p.stats = reinterpret_cast<unsigned long long*>(render->stats);
   bool took_specialised = false;
   cudaError_t e = voxe::launch_render(p, render->sh_degree, render->n_colour, regcap, true, specialised_kernels(), (cudaStream_t)stream,
                                       &took_specialised);

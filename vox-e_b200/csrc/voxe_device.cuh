@@ -74,8 +74,15 @@ struct KParams {
   int flags, preact, postact;
   int rpc, nseg, L;  // rays per CTA, sample segments per ray, samples per segment (threads = rpc * nseg -> x32)
   unsigned long long rng_seed, rng_offset;  // in-kernel jitter (kPerturb with jitter == nullptr)
+  const long long* rng_seed_dev;            // non-null: the generator state lives in device memory (CUDA-graph replays):
+  const long long* rng_offset_dev;          //   seed = *rng_seed_dev, offset = *rng_offset_dev + rng_intragraph
+  unsigned long long rng_intragraph;
   float* saved;      // workspace written by the forward / read by the backward (or null): [nseg*L][R] float4 sample
                      // vectors, then [NCOL+3][nseg][R] segment summaries (16-byte aligned)
+  unsigned char* touched;  // backward, optional: one byte per 2x2x2 brick of the gradient volume; a sample that scatters
+  int touch_tag;           // stores touch_tag at the brick of its corner 0 (its 8 corners lie in that brick and its +1
+                           // neighbours), so that voxe_consume_grad visits only what this call wrote
+  unsigned long long* stats;  // backward, optional device counters: [0] += in-grid samples, [1] += samples that scattered
 };
 
 // ---------------------------------------------------------------------------------------------------------
@@ -357,15 +364,22 @@ struct JitterSource {
 
   __device__ __forceinline__ void init(const KParams& p, int ray_index) {
     row = p.jitter ? p.jitter + (size_t)ray_index * p.S : nullptr;
-    unsigned k = pcg_hash((unsigned)p.rng_seed ^ pcg_hash((unsigned)(p.rng_seed >> 32)));
-    k = pcg_hash(k ^ (unsigned)p.rng_offset);
-    k = pcg_hash(k ^ (unsigned)(p.rng_offset >> 32));
+    unsigned long long seed = p.rng_seed, offset = p.rng_offset;
+    if (p.rng_seed_dev != nullptr) {
+      seed = (unsigned long long)__ldg(p.rng_seed_dev);
+      offset = (unsigned long long)__ldg(p.rng_offset_dev) + p.rng_intragraph;
+    }
+    unsigned k = pcg_hash((unsigned)seed ^ pcg_hash((unsigned)(seed >> 32)));
+    k = pcg_hash(k ^ (unsigned)offset);
+    k = pcg_hash(k ^ (unsigned)(offset >> 32));
     base = pcg_hash(k ^ (unsigned)ray_index) + (unsigned)ray_index * 0x9E3779B9u;  // per-ray stream start
   }
   template <class SP = SpecDynamic>
   __device__ __forceinline__ float at(const KParams& p, int i) const {
     if (SP::jitter_buffer(row)) return __ldg(row + i);
-    return (float)(pcg_hash(base + (unsigned)i) >> 8) * (1.0f / 16777216.0f);
+    // (ray, sample) hashed jointly: the sample index enters through a multiply and an XOR, so two rays whose stream
+    // starts happen to lie within S of each other do not replay each other's draws with a shift
+    return (float)(pcg_hash(base ^ ((unsigned)i * 0x85EBCA6Bu)) >> 8) * (1.0f / 16777216.0f);
   }
 };
 

@@ -109,6 +109,55 @@ __global__ void __launch_bounds__(256) consume_grad_kernel(float4* __restrict__ 
   }
 }
 
+// The same hand-over when the backward call left a trail: `touched` holds one byte per 2x2x2 brick, and a sample that
+// scattered stored `tag` at the brick of its corner 0 -- its 8 corners lie in that brick and the +1 neighbours in x, y, z.
+// A brick can therefore hold gradients only if one of the 8 flags at (bx-dx, by-dy, bz-dz) carries the tag.  Eight
+// consecutive lanes own one brick (one voxel slot each): lane k of the group loads the flag of neighbour k, a ballot
+// combines them, and only tagged bricks read their gradient vectors.  A 4096-ray batch tags a few percent of the
+// bricks, so the pass reads ~1 byte per brick (0.5 MB at 160^3) instead of the whole 68 MB volume.  Flags are not
+// cleared: the next call uses another tag (the caller clears them when it wraps the tag, see voxe.h).
+__global__ void __launch_bounds__(256) consume_touched_kernel(float4* __restrict__ pg, float* __restrict__ d_dens,
+                                                              float* __restrict__ d_feat,
+                                                              const unsigned char* __restrict__ touched, int tag,
+                                                              int64_t n_slots, int F, int CV, BrickDims d) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int lane = threadIdx.x & 31, group_shift = lane & ~7, k = lane & 7;
+  const int dx = k >> 2, dy = (k >> 1) & 1, dz = k & 1;
+  // warp-uniform loop (the ballot needs all 32 lanes): a warp owns 32 consecutive slots = 4 bricks per iteration
+  for (int64_t base = (int64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31); base < n_slots; base += stride) {
+    const int64_t slot = base + lane;
+    const int64_t brick = slot >> 3;
+    const int bz = (int)(brick % d.BZ);
+    const int64_t t = brick / d.BZ;
+    const int by = (int)(t % d.BY), bx = (int)(t / d.BY);
+    bool mine = false;
+    if (slot < n_slots && bx >= dx && by >= dy && bz >= dz)
+      mine = __ldg(touched + ((int64_t)(bx - dx) * d.BY + (by - dy)) * d.BZ + (bz - dz)) == (unsigned char)tag;
+    const unsigned group = (__ballot_sync(0xffffffffu, mine) >> group_shift) & 0xffu;
+    if (group == 0u || slot >= n_slots) continue;
+    const int x = 2 * bx + dx - 1, y = 2 * by + dy - 1, z = 2 * bz + dz - 1;  // this lane's voxel slot is (dx, dy, dz)
+    const bool real = x >= 0 && y >= 0 && z >= 0 && x < d.X && y < d.Y && z < d.Z;
+    const int64_t v = ((int64_t)x * d.Y + y) * d.Z + z;
+    for (int j = 0; j < CV; ++j) {
+      float4* src = pg + slot * CV + j;
+      const float4 g = *src;
+      if (g.x == 0.f && g.y == 0.f && g.z == 0.f && g.w == 0.f) continue;
+      *src = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (!real) continue;  // apron / padding slot: whatever was scattered there is dropped
+      const float in[4] = {g.x, g.y, g.z, g.w};
+#pragma unroll
+      for (int c4 = 0; c4 < 4; ++c4) {
+        const int c = 4 * j + c4;
+        if (c < F) {
+          if (d_feat) d_feat[v * F + c] += in[c4];
+        } else if (c == F) {
+          if (d_dens) d_dens[v] += in[c4];
+        }
+      }
+    }
+  }
+}
+
 // Fused per-step grid pass: consume the packed gradient volume (plus optional dense gradients from torch-side losses),
 // apply one Adam step to the reference-layout parameters and their moments, refresh the packed volume and zero the
 // packed gradients -- one launch instead of zero-fill + unpack + AccumulateGrad + ~10 optimiser kernels + repack.
@@ -146,6 +195,7 @@ __global__ void __launch_bounds__(256) adam_step_kernel(float4* __restrict__ pac
   for (int k = 0; k < 4; ++k) {
     const int c = c0 + k;
     if (c > F) continue;  // channel padding
+    if ((c < F) ? (feat == nullptr) : (dens == nullptr)) continue;  // frozen tensor: value and moments stay as they are
     float* dst = (c < F) ? feat + v * F + c : dens + v;
     float grad = g[k];
     if (c < F) {
@@ -195,11 +245,21 @@ cudaError_t launch_unpack_grad(const float* packed_grad, float* d_densities, flo
   return cudaGetLastError();
 }
 
+int64_t packed_bricks(const int dims[3]) { return packed_voxel_slots(dims) / 8; }
+
 cudaError_t launch_consume_grad(float* packed_grad, float* d_densities, float* d_features, const int dims[3],
-                                int n_features, int channels, cudaStream_t stream) {
+                                int n_features, int channels, const unsigned char* touched, int tag, cudaStream_t stream) {
   const int CV = channels / 4;
   const int64_t n_vec = packed_voxel_slots(dims) * CV;
   const int threads = 256;
+  if (touched != nullptr) {
+    const int64_t n_slots = packed_voxel_slots(dims);
+    const int64_t want = (n_slots + threads - 1) / threads;
+    const int blocks = (int)(want < 148 * 16 ? want : 148 * 16);  // persistent: 16 CTAs per SM, grid-stride over the bricks
+    consume_touched_kernel<<<blocks, threads, 0, stream>>>(reinterpret_cast<float4*>(packed_grad), d_densities, d_features,
+                                                            touched, tag, n_slots, n_features, CV, brick_dims(dims));
+    return cudaGetLastError();
+  }
   const int64_t blocks = (n_vec + threads - 1) / threads;
   consume_grad_kernel<<<(unsigned)blocks, threads, 0, stream>>>(reinterpret_cast<float4*>(packed_grad), d_densities,
                                                                 d_features, n_vec, n_features, CV, brick_dims(dims));

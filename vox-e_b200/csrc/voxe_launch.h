@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "voxe.h"
+
 namespace voxe {
 
 struct KParams;
@@ -13,7 +15,8 @@ cudaError_t launch_render(const KParams& p, int sh_degree, int n_colour, int reg
                           cudaStream_t stream, bool* took_specialised);
 cudaError_t launch_camera(const KParams& p, const CameraParams& cam, int sh_degree, int n_colour, cudaStream_t stream);
 int max_threads_per_cta(int regcap);
-cudaError_t launch_jitter_fill(int R, int S, unsigned long long seed, unsigned long long offset, float* out, cudaStream_t stream);
+cudaError_t launch_jitter_fill(int R, int S, unsigned long long seed, unsigned long long offset, const long long* seed_dev,
+                               const long long* offset_dev, unsigned long long intragraph, float* out, cudaStream_t stream);
 int saved_floats_per_segment(int n_colour, int samples_per_segment);  // segment summary + one float4 per sample
 
 // full-grid passes (voxe_grid_ops.cu)
@@ -23,8 +26,10 @@ cudaError_t launch_pack_grid(const float* densities, const float* features, floa
 cudaError_t launch_unpack_grad(const float* packed_grad, float* d_densities, float* d_features, const int dims[3],
                                int n_features, int channels, bool accumulate, cudaStream_t stream);
 
+// touched != nullptr: visit only the bricks whose (dilated) flag equals tag (written by the backward kernel)
 cudaError_t launch_consume_grad(float* packed_grad, float* d_densities, float* d_features, const int dims[3],
-                                int n_features, int channels, cudaStream_t stream);
+                                int n_features, int channels, const unsigned char* touched, int tag, cudaStream_t stream);
+int64_t packed_bricks(const int dims[3]);  // 2x2x2 bricks of the packed volume = bytes of a `touched` flag array
 
 cudaError_t launch_adam_step(float* packed, float* packed_grad, float* packed_m, float* packed_v, float* densities,
                              float* features, const float* dense_gd, const float* dense_gf, const int dims[3], int n_features,
@@ -43,5 +48,14 @@ cudaError_t launch_sample_rays(long long n, long long k, int H, int W, int C, fl
                                unsigned long long offset, const float* poses, const float* src_o, const float* src_d,
                                const float* pixels, const long long* idx_in, long long* idx_out, float* rays_o, float* rays_d,
                                float* pixels_out, cudaStream_t stream);
+
+// gradient all-reduce (voxe_collective.cu)
+cudaError_t launch_allreduce_peer(const VoxePeerDesc& peers, int64_t n_floats, unsigned* fail_flag, cudaStream_t stream);
+const char* nccl_unavailable();  // nullptr when libnccl could be opened
+const char* nccl_error_string(int rc);
+int nccl_unique_id(void* out128);
+int nccl_comm_create(void** comm, int world, int rank, const void* id128);
+int nccl_comm_destroy(void* comm);
+int nccl_allreduce_sum_f32(void* comm, float* buf, size_t n, cudaStream_t stream);
 
 }  // namespace voxe

@@ -430,6 +430,7 @@ __global__ void __launch_bounds__(Bounds<REGCAP>::kThreads, Bounds<REGCAP>::kMin
   sh_basis<DEG>(rc.d[0] * inv, rc.d[1] * inv, rc.d[2] * inv, (p.flags & kDiffuse) != 0, Y);
   float prefix = 0.f;  // sum of w*q over this segment's samples up to and including the current one
   int stage_buf = 0;
+  unsigned n_in = 0, n_scatter = 0;  // p.stats only
 
   float4 sv_next = __ldg(samples);  // the sample vectors are fetched one iteration ahead of their use
 #pragma unroll(kSampleUnroll)
@@ -466,6 +467,7 @@ __global__ void __launch_bounds__(Bounds<REGCAP>::kThreads, Bounds<REGCAP>::kMin
     const float dsigma = delta * (Tnext * q - behind);
     Tcur = Tnext;
     if (!in) continue;  // masked samples pass no gradient
+    ++n_in;
     const float dsraw = dsigma * dpost * p.dscale;
     float draw[NCOL];
     bool any = (dsraw != 0.f);
@@ -475,8 +477,10 @@ __global__ void __launch_bounds__(Bounds<REGCAP>::kThreads, Bounds<REGCAP>::kMin
       any |= (draw[k] != 0.f);
     }
     if (!any) continue;
+    ++n_scatter;
     Corners c;
     make_corners(p, px, py, pz, c);
+    if (p.touched != nullptr) p.touched[c.idx[0] >> 3] = (unsigned char)p.touch_tag;  // brick of corner 0 (8 slots per brick)
     const unsigned signs = SP::pre_abs(p.preact) ? corner_signs<DEG, NCOL>(p, c) : 0u;
     float gfe[LT::CV * 4];
 #pragma unroll
@@ -509,6 +513,10 @@ __global__ void __launch_bounds__(Bounds<REGCAP>::kThreads, Bounds<REGCAP>::kMin
     }
   }
   if constexpr (LT::CV > 1) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // staging slots die with the CTA
+  if (p.stats != nullptr) {  // measurement runs only (bench.py bills the bytes the kernel really moves)
+    atomicAdd(p.stats, (unsigned long long)n_in);
+    atomicAdd(p.stats + 1, (unsigned long long)n_scatter);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -705,12 +713,18 @@ __global__ void __launch_bounds__(256) jitter_fill_kernel(KParams p, float* out)
 }
 }  // namespace
 
-cudaError_t launch_jitter_fill(int R, int S, unsigned long long seed, unsigned long long offset, float* out, cudaStream_t stream) {
+cudaError_t launch_jitter_fill(int R, int S, unsigned long long seed, unsigned long long offset, const long long* seed_dev,
+                               const long long* offset_dev, unsigned long long intragraph, float* out, cudaStream_t stream) {
   KParams p{};
   p.R = R;
   p.S = S;
   p.rng_seed = seed;
   p.rng_offset = offset;
+  if (seed_dev != nullptr && offset_dev != nullptr) {
+    p.rng_seed_dev = seed_dev;
+    p.rng_offset_dev = offset_dev;
+    p.rng_intragraph = intragraph;
+  }
   const long long n = (long long)R * S;
   jitter_fill_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(p, out);
   return cudaGetLastError();

@@ -106,7 +106,8 @@ class RenderFn : public torch::autograd::Function<RenderFn> {
   static variable_list forward(AutogradContext* ctx, const Tensor& densities, const Tensor& features, const Tensor& packed,
                                const Tensor& rays_o, const Tensor& rays_d, const c10::optional<Tensor>& jitter,
                                const c10::optional<Tensor>& noise, const c10::optional<Tensor>& grad_volume,
-                               const c10::optional<Tensor>& dirty_flag, const std::string& gdesc, const std::string& rdesc,
+                               const c10::optional<Tensor>& dirty_flag, const c10::optional<Tensor>& touched,
+                               const c10::optional<Tensor>& touch_tag, const std::string& gdesc, const std::string& rdesc,
                                int64_t mode) {
     const auto gd = unpack_desc<VoxeGridDesc>(gdesc);
     const auto rd = unpack_desc<VoxeRenderDesc>(rdesc);  // carries this call's (rng_seed, rng_offset)
@@ -119,6 +120,8 @@ class RenderFn : public torch::autograd::Function<RenderFn> {
     // not SavedVariables: both are written between forward and backward by design (no version check wanted)
     ctx->saved_data["grad_volume"] = grad_volume.value_or(Tensor());
     ctx->saved_data["dirty_flag"] = dirty_flag.value_or(Tensor());
+    ctx->saved_data["touched"] = touched.value_or(Tensor());      // uint8 [bricks], device: trail of the backward's scatter
+    ctx->saved_data["touch_tag"] = touch_tag.value_or(Tensor());  // int64 [1], host: last tag handed out for `touched`
     ctx->saved_data["gd"] = gdesc;
     ctx->saved_data["rd"] = rdesc;
     ctx->saved_data["mode"] = mode;
@@ -126,7 +129,7 @@ class RenderFn : public torch::autograd::Function<RenderFn> {
   }
 
   static variable_list backward(AutogradContext* ctx, variable_list grads) {
-    variable_list out(12);  // one (undefined) slot per forward argument
+    variable_list out(14);  // one (undefined) slot per forward argument
     const bool need_d = ctx->needs_input_grad(0), need_f = ctx->needs_input_grad(1);
     if (!need_d && !need_f) return out;
     bool any = false;
@@ -143,6 +146,10 @@ class RenderFn : public torch::autograd::Function<RenderFn> {
     const auto dev = packed.device();
     const c10::cuda::CUDAGuard guard(dev);
     const int64_t R = rays_o.size(0);
+    // the workspace layout follows the launch shape, which voxe_set_tuning can change between the two calls
+    TORCH_CHECK(voxe_saved_floats(&rd, R) == work.numel(),
+                "voxe_set_tuning changed the launch shape between a render's forward and its backward (workspace of ", work.numel(),
+                " floats, the backward now expects ", voxe_saved_floats(&rd, R), "); retune only between whole forward/backward pairs");
 
     Tensor g[4];
     for (int k = 0; k < 4; ++k)
@@ -152,8 +159,19 @@ class RenderFn : public torch::autograd::Function<RenderFn> {
     if (!grad_volume.defined()) grad_volume = at::zeros_like(packed);  // no persistent volume attached: a fresh one
 
     const auto stream = stream_of(dev);
+    // Sparse hand-over: the kernel tags the bricks it scatters into and voxe_consume_grad visits only those.  A fresh tag
+    // per backward; stale tags of earlier calls only cost the consume pass a few reads (it skips all-zero vectors), so the
+    // flags are never cleared.
+    const Tensor touched = mode == kSink ? Tensor() : ctx->saved_data["touched"].toTensor();
+    int32_t tag = 0;
+    if (touched.defined()) {
+      int64_t* last = ctx->saved_data["touch_tag"].toTensor().data_ptr<int64_t>();
+      *last = (*last % 255) + 1;
+      tag = (int32_t)*last;
+    }
+    uint8_t* touched_ptr = touched.defined() ? touched.data_ptr<uint8_t>() : nullptr;
     check(voxe_render_bwd(&gd, &rd, cptr(packed), cptr(rays_o), cptr(rays_d), cptr(jitter), cptr(noise), cptr(work),
-                          cptr(g[0]), cptr(g[1]), cptr(g[2]), cptr(g[3]), mptr(grad_volume), R, stream),
+                          cptr(g[0]), cptr(g[1]), cptr(g[2]), cptr(g[3]), mptr(grad_volume), touched_ptr, tag, R, stream),
           "voxe_render_bwd");
     if (mode == kSink) {
       if (dirty_flag.defined()) dirty_flag.data_ptr<int64_t>()[0] = 1;  // CPU flag owned by the accumulator
@@ -172,7 +190,7 @@ class RenderFn : public torch::autograd::Function<RenderFn> {
       if (need_d) d_dens = at::zeros(densities.sizes(), densities.options());
       if (need_f) d_feat = at::zeros(features.sizes(), features.options());
     }
-    check(voxe_consume_grad(&gd, mptr(grad_volume), mptr(d_dens), mptr(d_feat), stream), "voxe_consume_grad");
+    check(voxe_consume_grad(&gd, mptr(grad_volume), mptr(d_dens), mptr(d_feat), touched_ptr, tag, stream), "voxe_consume_grad");
     if (!direct) {
       out[0] = d_dens;
       out[1] = d_feat;
@@ -191,6 +209,7 @@ class RenderFn : public torch::autograd::Function<RenderFn> {
 std::vector<Tensor> render(const Tensor& densities, const Tensor& features, const Tensor& packed, const Tensor& rays_o_in,
                            const Tensor& rays_d_in, const c10::optional<Tensor>& jitter_in, const c10::optional<Tensor>& noise_in,
                            const c10::optional<Tensor>& grad_volume, const c10::optional<Tensor>& dirty_flag,
+                           const c10::optional<Tensor>& touched, const c10::optional<Tensor>& touch_tag,
                            const std::string& gdesc, const std::string& rdesc, int64_t mode, bool strict_rng,
                            const c10::optional<at::Generator>& generator) {
   const auto dev = packed.device();
@@ -216,9 +235,17 @@ std::vector<Tensor> render(const Tensor& densities, const Tensor& features, cons
         auto* gen = at::get_generator_or_default<at::CUDAGeneratorImpl>(generator, at::cuda::detail::getDefaultCUDAGenerator(dev.index()));
         std::lock_guard<std::mutex> lock(gen->mutex_);
         const at::PhiloxCudaState st = gen->philox_cuda_state(4);
-        TORCH_CHECK(!st.captured_, "in-kernel jitter cannot be captured into a CUDA graph through this path; pass `jitter` explicitly");
-        rd.rng_seed = st.seed_.val;
-        rd.rng_offset = st.offset_.val;
+        if (st.captured_) {
+          // under CUDA-graph capture the generator's state lives in device memory and is advanced by the graph on every
+          // replay (the generator is registered with the graph by torch): the kernels read it there, so replays of a
+          // captured render draw fresh jitter, forward and backward of one call the same
+          rd.rng_seed_dev = st.seed_.ptr;
+          rd.rng_offset_dev = st.offset_.ptr;
+          rd.rng_offset_intragraph = st.offset_intragraph_;
+        } else {
+          rd.rng_seed = st.seed_.val;
+          rd.rng_offset = st.offset_.val;
+        }
       }
       TORCH_CHECK(!jitter.defined() || (jitter.dim() == 2 && jitter.size(0) == R && jitter.size(1) == S), "jitter must be [R, S]");
     }
@@ -239,7 +266,7 @@ std::vector<Tensor> render(const Tensor& densities, const Tensor& features, cons
     return {o.colour, o.depth, o.acc, o.disp};
   }
   return RenderFn::apply(densities, features, packed, rays_o, rays_d, c10::optional<Tensor>(jitter),
-                         c10::optional<Tensor>(noise), grad_volume, dirty_flag, gdesc, rdesc_call, mode);
+                         c10::optional<Tensor>(noise), grad_volume, dirty_flag, touched, touch_tag, gdesc, rdesc_call, mode);
 }
 
 }  // namespace
@@ -250,7 +277,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.attr("MODE_DIRECT") = (int64_t)kDirect;
   m.attr("MODE_SINK") = (int64_t)kSink;
   m.def("render", &render, py::arg("densities"), py::arg("features"), py::arg("packed"), py::arg("rays_o"), py::arg("rays_d"),
-        py::arg("jitter"), py::arg("noise"), py::arg("grad_volume"), py::arg("dirty_flag"), py::arg("gdesc"), py::arg("rdesc"),
+        py::arg("jitter"), py::arg("noise"), py::arg("grad_volume"), py::arg("dirty_flag"), py::arg("touched"), py::arg("touch_tag"),
+        py::arg("gdesc"), py::arg("rdesc"),
         py::arg("mode"), py::arg("strict_rng"), py::arg("generator"));
   m.def("abi_version", []() { return voxe_abi_version(); });
 }

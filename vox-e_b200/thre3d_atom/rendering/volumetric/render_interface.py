@@ -105,3 +105,22 @@ ProcessedPointsOnRays = SampledPointsOnRays
 RaySamplerFunction = Callable[[Rays, CameraBounds, int], SampledPointsOnRays]
 PointProcessorFunction = Callable[[SampledPointsOnRays, Rays], ProcessedPointsOnRays]
 AccumulatorFunction = Callable[[ProcessedPointsOnRays, Rays], RenderOut]
+
+
+def render(rays: Rays, camera_bounds: CameraBounds, num_samples: int, sampler_fn: RaySamplerFunction,
+           point_processor_fn: PointProcessorFunction, accumulator_fn: AccumulatorFunction) -> RenderOut:
+    """The reference's three-stage driver (render_interface.py:140-171 upstream).  Name kept for import compatibility: the
+    stages are fused into one kernel pair here, so there is no pipeline of callables to drive."""
+    raise NotImplementedError(
+        "render() drives the reference's unfused sampler -> processor -> accumulator callables; this package renders through "
+        "thre3d_atom.thre3d_reprs.renderers.render_sh_voxel_grid (one fused CUDA launch, no PyTorch fallback)"
+    )
+
+
+def render_attn(rays: Rays, camera_bounds: CameraBounds, num_samples: int, sampler_fn: RaySamplerFunction,
+                point_processor_fn: PointProcessorFunction, accumulator_fn: AccumulatorFunction) -> RenderOutAttn:
+    """Attention twin of ``render`` (render_interface.py:174-205 upstream); see there."""
+    raise NotImplementedError(
+        "render_attn() drives the reference's unfused callables; this package renders through "
+        "thre3d_atom.thre3d_reprs.renderers.render_sh_voxel_grid_attn"
+    )

@@ -58,6 +58,24 @@ def compute_expected_density_scale_for_relu_field_grid(grid_world_size: Tuple[fl
     return ((float(np.sqrt(3.0**3)) * 100.0) / diagonal) / NUM_COORD_DIMENSIONS
 
 
+def ndcize_rays(rays: Rays, camera_intrinsics: CameraIntrinsics) -> Rays:
+    """Rays in normalised device coordinates (forward-facing scenes; the canvas becomes the cube [-1, 1]^3): origins are
+    moved onto the near plane z = -1 and both origins and directions go through the pinhole projection
+    (misc.py:90-123; used by visualizations/static.py:48-49)."""
+    height, width, focal = camera_intrinsics
+    near = 1.0
+    origins, directions = rays.origins, rays.directions
+    shift = -(near + origins[..., 2]) / directions[..., 2]
+    origins = origins + shift[..., None] * directions
+    sx, sy = -1.0 / (width / (2.0 * focal)), -1.0 / (height / (2.0 * focal))
+    ox_z, oy_z = origins[..., 0] / origins[..., 2], origins[..., 1] / origins[..., 2]
+    ndc_o = torch.stack([sx * ox_z, sy * oy_z, 1.0 + 2.0 * near / origins[..., 2]], -1)
+    ndc_d = torch.stack(
+        [sx * (directions[..., 0] / directions[..., 2] - ox_z), sy * (directions[..., 1] / directions[..., 2] - oy_z),
+         -2.0 * near / origins[..., 2]], -1)
+    return Rays(ndc_o, ndc_d)
+
+
 def sample_random_rays_and_pixels_synchronously(rays: Rays, pixels: Tensor, sample_size: int) -> Tuple[Rays, Tensor]:
     """Random ray batch for reconstruction training: the first ``sample_size`` entries of a permutation of all pixels.
     fp32 CUDA tensors take one launch of ``voxe_sample_rays`` (distinct indices from a keyed permutation evaluated on demand,
@@ -81,6 +99,18 @@ def sample_rays_and_pixels_synchronously(rays: Rays, pixels: Tensor, indices: li
     if sample_size == 1:
         picked_indices = [picked_indices]
     return picked_rays, picked_pixels, picked_indices, chosen.tolist()
+
+
+def sample_rays_directions_and_pixels_synchronously(rays: Rays, pixels: Tensor, directions: list, indices: list, sample_size: int):
+    """Whole-image variant that also returns the view-direction words of the picked images (misc.py:160-182)."""
+    chosen = torch.randperm(pixels.shape[0], dtype=torch.long, device=pixels.device)[:sample_size]
+    picked_rays = flatten_rays(Rays(rays.origins[chosen, :], rays.directions[chosen, :]))
+    picked_pixels = pixels[chosen, :].permute(0, 2, 3, 1).reshape(-1, pixels.shape[1])
+    picked_directions = directions[chosen]
+    picked_indices = indices[chosen.to("cpu")]
+    if sample_size == 1:
+        picked_directions, picked_indices = [picked_directions], [picked_indices]
+    return picked_rays, picked_pixels, picked_directions, picked_indices, chosen.tolist()
 
 
 def _collate(chunks: Sequence[Any], main: str, out_type):

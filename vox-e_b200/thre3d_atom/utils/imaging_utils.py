@@ -1,15 +1,18 @@
 """Camera model helpers used by the render path and its harnesses.
 
 Reference: thre3d_atom/utils/imaging_utils.py -- camera tuples :17-30, ``adjust_dynamic_range`` :42-71, intrinsics scaling
-:140-150, pose construction :153-232.  The matplotlib-based depth colouring (:99-137) is visualisation, not render path,
-and is not provided.
+:140-150, pose construction :153-232.  ``postprocess_depth_map`` (:93-125, depth colouring for the reference's
+visualisation modules) is kept so that ``visualizations/{static,animations}.py`` import against this module; matplotlib
+is imported when it is called, not at module import.
 """
 import math
-from typing import NamedTuple, Sequence, Tuple, Union
+from typing import NamedTuple, Optional, Sequence, Tuple, Union
 
 import numpy as np
 import torch
 from torch import Tensor
+
+from thre3d_atom.utils.constants import NUM_COLOUR_CHANNELS
 
 
 class CameraIntrinsics(NamedTuple):
@@ -57,6 +60,26 @@ def get_2d_coordinates(height: int, width: int, drange: Tuple[float, float] = (-
     rows = torch.linspace(lo, hi, height, dtype=torch.float32)
     cols = torch.linspace(lo, hi, width, dtype=torch.float32)
     return torch.stack(torch.meshgrid(rows, cols, indexing="ij"), dim=-1)
+
+
+def postprocess_depth_map(
+    depth_map: np.array, camera_bounds: Optional[CameraBounds] = None, acc_map: Optional[np.array] = None
+) -> np.array:
+    """Colour a depth map with the "magma" colour map (8-bit RGB).  With ``acc_map`` the range tops out at the largest
+    *foreground* depth and the result is composited over white with the squared-transparency weighting of
+    imaging_utils.py:117-122.  ``camera_bounds`` is accepted and unused, as upstream."""
+    import matplotlib.pyplot as plt  # visualisation-only dependency, deliberately not a module-level import
+
+    if depth_map.ndim == 3 and depth_map.shape[-1] == 1:
+        depth_map = depth_map[..., 0]
+    lo = depth_map.min()
+    hi = (depth_map * acc_map[..., 0]).max() if acc_map is not None else depth_map.max()
+    unit = adjust_dynamic_range(depth_map, drange_in=(lo, hi), drange_out=(0, 1), slack=True)
+    coloured = plt.get_cmap("magma", lut=1024)(unit)[..., :NUM_COLOUR_CHANNELS]
+    if acc_map is None:
+        return to8b(coloured)
+    see_through = (1.0 - acc_map) ** 2
+    return to8b((coloured * acc_map + see_through) / (acc_map + see_through))
 
 
 def scale_camera_intrinsics(camera_intrinsics: CameraIntrinsics, scale_factor: float = 1.0) -> CameraIntrinsics:

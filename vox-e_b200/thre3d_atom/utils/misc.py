@@ -1,6 +1,8 @@
-"""Small host-side helpers (reference: thre3d_atom/utils/misc.py:10-50).  ``log_config_to_disk`` is not part of the
-render path and is omitted together with its ``easydict`` dependency."""
-from typing import Any, Callable, List, Optional, Sequence, Tuple
+"""Small host-side helpers (reference: thre3d_atom/utils/misc.py:10-58).  ``log_config_to_disk`` is kept because every
+training / editing script of the reference imports it from here at top level; it takes any mapping (the scripts pass an
+``EasyDict``), so this module does not import ``easydict``."""
+from pathlib import Path
+from typing import Any, Callable, List, Mapping, Optional, Sequence, Tuple
 
 import numpy as np
 
@@ -39,3 +41,13 @@ def compute_thre3d_grid_sizes(
     for _ in range(num_stages - 1):
         sizes.insert(0, tuple(int(np.ceil(v / scale_factor)) for v in sizes[0]))
     return sizes
+
+
+def log_config_to_disk(args: Mapping[str, Any], output_dir: Path, config_file_name: str = "config.yml") -> None:
+    """Write the run configuration as block-style YAML into ``output_dir`` (created if missing)."""
+    import yaml
+
+    output_dir = Path(output_dir)
+    output_dir.mkdir(exist_ok=True, parents=True)
+    with open(output_dir / config_file_name, "w") as handle:
+        yaml.dump(dict(args), handle, default_flow_style=False)

@@ -16,7 +16,7 @@ _lock = threading.Lock()
 _lib: Optional[ctypes.CDLL] = None
 
 # ---- enums of include/voxe.h -------------------------------------------------------------------------------
-ABI_VERSION = 11
+ABI_VERSION = 12
 PREACT_IDENTITY, PREACT_ABS = 0, 1
 POSTACT_IDENTITY, POSTACT_RELU, POSTACT_SOFTPLUS = 0, 1, 2
 FLAG_PERTURB, FLAG_AABB_SAMPLING, FLAG_DISPARITY_SAMPLING = 1, 2, 4
@@ -55,6 +55,10 @@ class VoxeRenderDesc(ctypes.Structure):
         ("noise_std", ctypes.c_float),
         ("rng_seed", ctypes.c_uint64),
         ("rng_offset", ctypes.c_uint64),
+        ("rng_seed_dev", ctypes.c_void_p),
+        ("rng_offset_dev", ctypes.c_void_p),
+        ("rng_offset_intragraph", ctypes.c_uint64),
+        ("stats", ctypes.c_void_p),
     ]
 
 
@@ -66,6 +70,14 @@ class VoxeCameraDesc(ctypes.Structure):
 class VoxeSamplerDesc(ctypes.Structure):
     _fields_ = [("num_pixels", ctypes.c_int64), ("height", ctypes.c_int32), ("width", ctypes.c_int32), ("focal", ctypes.c_float),
                 ("pixel_channels", ctypes.c_int32), ("rng_seed", ctypes.c_uint64), ("rng_offset", ctypes.c_uint64)]
+
+
+MAX_PEERS, SIGNAL_WORDS, NCCL_UNIQUE_ID_BYTES = 16, 4096, 128
+
+
+class VoxePeerDesc(ctypes.Structure):
+    _fields_ = [("world_size", ctypes.c_int32), ("rank", ctypes.c_int32), ("buffers", ctypes.c_void_p * MAX_PEERS),
+                ("signals", ctypes.c_void_p * MAX_PEERS), ("multicast", ctypes.c_void_p)]
 
 
 class VoxeAdamDesc(ctypes.Structure):
@@ -83,7 +95,8 @@ EXPORTS = {
     "voxe_packed_floats": (ctypes.c_int64, [_GD]),
     "voxe_pack_grid": (ctypes.c_int, [_GD, _P, _P, _P, _P]),
     "voxe_unpack_grad": (ctypes.c_int, [_GD, _P, _P, _P, ctypes.c_int, _P]),
-    "voxe_consume_grad": (ctypes.c_int, [_GD, _P, _P, _P, _P]),
+    "voxe_consume_grad": (ctypes.c_int, [_GD, _P, _P, _P, _P, ctypes.c_int32, _P]),
+    "voxe_touched_bytes": (ctypes.c_int64, [_GD]),
     "voxe_jitter_fill": (ctypes.c_int, [_RD, _P, ctypes.c_int64, _P]),
     "voxe_adam_step": (ctypes.c_int, [_GD, ctypes.POINTER(VoxeAdamDesc), _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "voxe_saved_floats": (ctypes.c_int64, [_RD, ctypes.c_int64]),
@@ -91,12 +104,17 @@ EXPORTS = {
     "voxe_render_camera": (ctypes.c_int, [_GD, _RD, ctypes.POINTER(VoxeCameraDesc), _P, ctypes.c_int64, ctypes.c_int64, _P, _P, _P, _P,
                                           ctypes.c_float, _P]),
     "voxe_render_infer": (ctypes.c_int, [_GD, _RD, _P, _P, _P, _P, _P, _P, _P, _P, ctypes.c_int64, ctypes.c_float, _P]),
-    "voxe_render_bwd": (ctypes.c_int, [_GD, _RD, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, ctypes.c_int64, _P]),
+    "voxe_render_bwd": (ctypes.c_int, [_GD, _RD, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, ctypes.c_int32, ctypes.c_int64, _P]),
     "voxe_tv_regularizer": (ctypes.c_int, [_P, ctypes.POINTER(ctypes.c_int32 * 3), ctypes.c_int32, ctypes.c_int32, _P, _P, _P,
                                            ctypes.c_float, _P, ctypes.c_int32, _P]),
     "voxe_pair_loss": (ctypes.c_int, [_P, _P, ctypes.c_int64, ctypes.c_int32, _P, _P, _P, _P]),
     "voxe_pair_loss_grad": (ctypes.c_int, [_P, _P, ctypes.c_int64, ctypes.c_int32, _P, _P, ctypes.c_float, _P, ctypes.c_int32, _P]),
     "voxe_sample_rays": (ctypes.c_int, [ctypes.POINTER(VoxeSamplerDesc), _P, _P, _P, _P, _P, ctypes.c_int64, _P, _P, _P, _P, _P]),
+    "voxe_allreduce_grads_peer": (ctypes.c_int, [ctypes.POINTER(VoxePeerDesc), ctypes.c_int64, _P, _P]),
+    "voxe_nccl_unique_id": (ctypes.c_int, [_P]),
+    "voxe_nccl_comm_create": (ctypes.c_int, [ctypes.POINTER(ctypes.c_void_p), ctypes.c_int32, ctypes.c_int32, _P]),
+    "voxe_nccl_comm_destroy": (ctypes.c_int, [_P]),
+    "voxe_allreduce_grads": (ctypes.c_int, [_P, _P, ctypes.c_int64, _P]),
     "voxe_set_tuning": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int]),
     "voxe_launch_count": (ctypes.c_int64, []),
     "voxe_specialised_launch_count": (ctypes.c_int64, []),

@@ -76,11 +76,43 @@ class VoxelGradAllReducer:
     parameter.  ``reduce_flat`` is the same on a caller-owned buffer (e.g. the packed gradient volume of the C ABI).
     """
 
-    def __init__(self, params: Iterable[Tensor], group: Optional[dist.ProcessGroup] = None) -> None:
+    def __init__(self, params: Iterable[Tensor], group: Optional[dist.ProcessGroup] = None, grids: Sequence = ()) -> None:
         self.params: List[Tensor] = [p for p in params]
         self.group = group
+        self.grids = list(grids)  # VoxelGrids whose render gradients may be deferred (accumulate_render_gradients / FusedVoxelAdam)
         self._flat: Optional[Tensor] = None
         self.num_collectives = 0
+
+    def _deferred_grids(self) -> list:
+        """Grids that own one of ``self.params`` and keep render gradients in a packed sink volume: the ones handed to the
+        constructor plus any other grid registered with ``voxe_b200.optim`` (so that a forgotten ``grids=`` cannot make the
+        ranks step on local, unreduced render gradients)."""
+        from voxe_b200 import optim
+
+        owned = {id(p) for p in self.params}
+        grids = list(self.grids)
+        for grid in list(optim._tracked):
+            if grid not in grids and (id(grid.densities) in owned or id(grid.features) in owned):
+                grids.append(grid)
+        return [g for g in grids if g.render_gradient_accumulator is not None]
+
+    def reduce_deferred(self) -> int:
+        """All-reduce the packed sink volumes of the deferred grids in place (ONE collective per grid on the volume the
+        backward kernels scattered into; ``FusedVoxelAdam`` or the optimiser pre-step hook then consume the summed
+        gradients).  Ranks whose volume is clean still take part (their zeros are part of the sum).  Returns the number
+        of volumes reduced."""
+        rank, world = world_info(self.group)
+        n = 0
+        for grid in self._deferred_grids():
+            acc = grid.render_gradient_accumulator
+            if acc.buffer is None:  # nothing rendered yet on this rank: allocate the (zero) volume so the collective matches
+                spec = grid.fused_spec()
+                acc.get(grid.packed_cache().get(spec, grid.densities, grid.features))
+            if world > 1:
+                self.reduce_flat(acc.buffer)
+                acc.dirty = True  # the sum may be non-zero even where this rank's share was
+            n += 1
+        return n
 
     def _buffer(self) -> Tensor:
         numel = sum(p.numel() for p in self.params)
@@ -97,10 +129,14 @@ class VoxelGradAllReducer:
         return flat
 
     def __call__(self) -> None:
-        """In-place: every ``p.grad`` becomes the sum over ranks (parameters without a gradient contribute zeros)."""
+        """In-place: every ``p.grad`` becomes the sum over ranks (parameters without a gradient contribute zeros).
+        Render gradients that are still deferred in a grid's packed sink volume are materialised into ``.grad`` first, so
+        the one collective below carries them (use ``reduce_deferred`` to reduce the packed volumes themselves)."""
         rank, world = world_info(self.group)
         if world == 1 or not self.params:
             return
+        for grid in self._deferred_grids():
+            grid.materialize_render_gradients()
         flat = self._buffer()
         offset = 0
         for p in self.params:
@@ -119,3 +155,65 @@ class VoxelGradAllReducer:
             else:
                 p.grad.copy_(flat[offset : offset + n].reshape(p.shape))
             offset += n
+
+
+class PeerGradVolume:
+    """A packed gradient volume that every rank of the group maps into its address space, reduced in place by the
+    library's own kernel (``voxe_allreduce_grads_peer``: two-shot over NVLink peer memory, through the NVSwitch's
+    multicast reduction when the mapping has one) instead of an NCCL call.
+
+    The memory comes from torch's symmetric-memory allocator -- plumbing only: it allocates, exchanges the handles and
+    maps the peers; the exchange itself is ``csrc/voxe_collective.cu``.  ``buffer`` is an ordinary fp32 CUDA tensor; hand
+    it to the backward kernels as their gradient volume (``adopt``) and call ``allreduce()`` once per optimiser step."""
+
+    def __init__(self, n_floats: int, device: torch.device, group: Optional[dist.ProcessGroup] = None, multicast: bool = True) -> None:
+        import ctypes
+
+        import torch.distributed._symmetric_memory as symm_mem
+
+        from voxe_b200 import _native as nat
+
+        group = group if group is not None else dist.group.WORLD
+        self._nat, self._lib = nat, nat.load_library()
+        self.group = group
+        self.n_floats = int(n_floats)
+        if self.n_floats % 4:
+            raise ValueError("the volume must be a whole number of 16-byte vectors")
+        self.buffer = symm_mem.empty(self.n_floats, dtype=torch.float32, device=device)
+        self.buffer.zero_()
+        self._signals = symm_mem.empty(nat.SIGNAL_WORDS, dtype=torch.int32, device=device)
+        self._signals.zero_()
+        self._fail = torch.zeros(1, dtype=torch.int32, device=device)
+        h_buf = symm_mem.rendezvous(self.buffer, group)
+        h_sig = symm_mem.rendezvous(self._signals, group)
+        self.rank, self.world_size = int(h_buf.rank), int(h_buf.world_size)
+        if self.world_size > nat.MAX_PEERS:
+            raise ValueError(f"at most {nat.MAX_PEERS} ranks")
+        desc = nat.VoxePeerDesc()
+        desc.world_size, desc.rank = self.world_size, self.rank
+        for k in range(self.world_size):
+            desc.buffers[k] = int(h_buf.buffer_ptrs[k])
+            desc.signals[k] = int(h_sig.buffer_ptrs[k])
+        mc = int(h_buf.multicast_ptr) if multicast else 0
+        desc.multicast = mc if mc else None
+        self.multicast = bool(mc)
+        self._desc, self._handles = desc, (h_buf, h_sig)
+        torch.cuda.synchronize(device)
+        dist.barrier(group)  # every rank's zero-fill of its signal pad is done before anybody's first launch
+
+    def allreduce(self) -> None:
+        """buffer <- sum over ranks, in place, on the current stream (one launch; every rank must call it)."""
+        dev = self.buffer.device
+        with torch.cuda.device(dev):
+            self._nat.check(self._lib.voxe_allreduce_grads_peer(self._desc, self.n_floats, self._fail.data_ptr(),
+                                                                torch.cuda.current_stream(dev).cuda_stream), "voxe_allreduce_grads_peer")
+
+    def failed(self) -> bool:
+        """True when a launch gave up waiting for a peer (synchronises)."""
+        return bool(self._fail.item())
+
+    def adopt(self, accumulator) -> None:
+        """Make this volume the gradient volume of a ``PackedGradAccumulator`` (a grid's deferred-gradient sink)."""
+        accumulator.buffer = self.buffer
+        accumulator.touched = None
+        accumulator.dirty = False

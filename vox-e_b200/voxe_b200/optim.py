@@ -94,6 +94,17 @@ class FusedVoxelAdam(Optimizer):
         gd = spec.to_native()
         cache = grid.packed_cache()
         packed = cache.get(spec, dens, feat)  # no-op when the volume already mirrors the parameters
+        acc = grid.render_gradient_accumulator
+        packed_grad = acc.buffer if (acc is not None and acc.dirty) else None
+        dense = [None if (p.grad is None or not p.requires_grad) else p.grad.contiguous() for p in (dens, feat)]
+        if packed_grad is None and dense[0] is None and dense[1] is None:
+            return loss  # no gradient anywhere: like torch.optim.Adam, which skips parameters whose .grad is None
+        # a frozen tensor (requires_grad == False) is passed as NULL: the kernel leaves it and its moments alone
+        live = [p if p.requires_grad else None for p in (dens, feat)]
+        if live[0] is None and live[1] is None:
+            if acc is not None:
+                acc.zero()
+            return loss
         st = self.state[dens]  # one shared record: the moments live in the packed layout, next to the packed volume
         if len(st) == 0:
             st["step"] = torch.tensor(0.0, dtype=torch.float32)
@@ -101,16 +112,13 @@ class FusedVoxelAdam(Optimizer):
             st["packed_exp_avg_sq"] = torch.zeros_like(packed)
         st["step"] += 1
         step = int(st["step"].item())
-        acc = grid.render_gradient_accumulator
-        packed_grad = acc.buffer if (acc is not None and acc.dirty) else None
         adam = nat.VoxeAdamDesc(lr=float(group["lr"]), beta1=float(group["betas"][0]), beta2=float(group["betas"][1]),
                                 eps=float(group["eps"]), step=step)
-        dense = [None if p.grad is None else p.grad.contiguous() for p in (dens, feat)]
         ptr = lambda t: None if t is None else t.data_ptr()  # noqa: E731
         lib = nat.load_library()
         with torch.cuda.device(dens.device):
             nat.check(
-                lib.voxe_adam_step(gd, adam, dens.data_ptr(), feat.data_ptr(), packed.data_ptr(), ptr(packed_grad), ptr(dense[0]),
+                lib.voxe_adam_step(gd, adam, ptr(live[0]), ptr(live[1]), packed.data_ptr(), ptr(packed_grad), ptr(dense[0]),
                                    ptr(dense[1]), st["packed_exp_avg"].data_ptr(), st["packed_exp_avg_sq"].data_ptr(),
                                    _stream_ptr(dens.device)),
                 "voxe_adam_step",

@@ -197,7 +197,12 @@ class PackedVolumeCache:
     def get(self, spec: FusedGridSpec, densities: Tensor, features: Tensor) -> Tensor:
         key = (densities.data_ptr(), densities._version, features.data_ptr(), features._version, densities.device, spec)
         if self._packed is None or key != self._key:
-            self._packed = pack_volume(spec, densities, features, out=self._packed)
+            # Repack in place only while nobody else holds the buffer.  An autograd graph that is still alive saved it for
+            # its backward (a render of other tensors through the same cache -- render_rays_attn with and without
+            # orig_densities -- or of a parameter that has been replaced since): that graph keeps the old buffer and this
+            # call gets a fresh one.  (Python wrapper = 1 use; every live graph node adds one.)
+            reuse = self._packed if self._packed is not None and self._packed._use_count() <= 1 else None
+            self._packed = pack_volume(spec, densities, features, out=reuse)
             self._key = key
         return self._packed
 
@@ -215,6 +220,10 @@ class PackedGradAccumulator:
     def __init__(self) -> None:
         self.buffer: Optional[Tensor] = None
         self.flag = torch.zeros(1, dtype=torch.int64)  # set by the C++ backward node when it scatters into the buffer
+        # trail of the backward's scatter (one byte per 2x2x2 brick, include/voxe.h: voxe_render_bwd) and the last tag
+        # handed out for it; used by the sparse direct hand-over, ignored by the deferred mode
+        self.touched: Optional[Tensor] = None
+        self.touch_tag = torch.zeros(1, dtype=torch.int64)
 
     @property
     def dirty(self) -> bool:
@@ -227,8 +236,15 @@ class PackedGradAccumulator:
     def get(self, like: Tensor) -> Tensor:
         if self.buffer is None or self.buffer.numel() != like.numel() or self.buffer.device != like.device:
             self.buffer = torch.zeros_like(like)
+            self.touched = None
             self.dirty = False
         return self.buffer
+
+    def get_touched(self, spec: "FusedGridSpec") -> Tensor:
+        if self.touched is None or self.touched.device != self.buffer.device:
+            n = int(nat.load_library().voxe_touched_bytes(spec.to_native()))
+            self.touched = torch.zeros(n, dtype=torch.uint8, device=self.buffer.device)
+        return self.touched
 
     def zero(self) -> None:
         if self.buffer is not None and self.dirty:
@@ -305,15 +321,18 @@ def fused_render(
     if R == 0:
         z = torch.zeros((0, 1), dtype=torch.float32, device=dev)
         return torch.zeros((0, rspec.n_colour), dtype=torch.float32, device=dev), z, z.clone(), z.clone()
-    volume = flag = None
+    volume = flag = touched = tag = None
     mode = ext.MODE_DENSE
     if torch.is_grad_enabled() and (densities.requires_grad or features.requires_grad):
         if grad_sink is not None:  # deferred gradients (opt-in): leave them in the grid's persistent volume
             volume, flag, mode = grad_sink.get(packed), grad_sink.flag, ext.MODE_SINK
         elif grad_scratch is not None:  # persistent all-zero-between-calls volume: no allocation / zero-fill per call
             volume = grad_scratch.get(packed)
+            touched, tag = grad_scratch.touched, grad_scratch.touch_tag
+            if touched is None:
+                touched = grad_scratch.get_touched(gspec)
             mode = ext.MODE_DIRECT if DIRECT_GRAD_ACCUMULATION else ext.MODE_DENSE
-    colour, depth, acc, disparity = ext.render(densities, features, packed, rays_o, rays_d, jitter, noise, volume, flag,
+    colour, depth, acc, disparity = ext.render(densities, features, packed, rays_o, rays_d, jitter, noise, volume, flag, touched, tag,
                                                gspec.native_bytes(), rspec.native_bytes(), mode, STRICT_REFERENCE_RNG, generator)
     return colour, depth, acc, disparity
 
