@@ -943,7 +943,7 @@ def oracle_frame(bench, pose, want_grads=True, ray_stride=1):
     (voxe_jitter_fill with the per-batch (seed, offset) of DeviceBench._jitter_arg).  Test infrastructure used as the
     checker of the timed leg, never timed as the product.  Returns colour [R,3] (NaN rows where ray_stride skipped) and,
     with want_grads, the frame's dense voxel gradients."""
-    from oracle.voxe_oracle import OracleConfig, OracleGrid, render_oracle, render_oracle_with_grads
+    from oracle.voxe_oracle import OracleConfig, OracleGrid, relu_kink_voxels, render_oracle, render_oracle_with_grads
 
     o, d = bench.rays[pose]
     voxel = tuple(w / n for w, n in zip(WL["world"], WL["dims"]))
@@ -952,6 +952,9 @@ def oracle_frame(bench, pose, want_grads=True, ray_stride=1):
     colour = torch.full((bench.R, 3), float("nan"), device=bench.device)
     gd = torch.zeros_like(bench.dens) if want_grads else None
     gf = torch.zeros_like(bench.feat) if want_grads else None
+    # ReLU field: voxels that are corners of a sample whose interpolated density is within rounding of the kink (its
+    # derivative is decided by fp32 evaluation order; tests/test_cuda_parity.py masks the same set)
+    kink = torch.zeros(bench.dens.shape[:3], dtype=torch.bool, device=bench.device) if (want_grads and bench.postact == "relu") else None
     rd = bench.nat.VoxeRenderDesc.from_buffer_copy(bench.rspec.native_bytes())
     chunk = 8192
     for b0, b1 in bench.batches:
@@ -971,11 +974,13 @@ def oracle_frame(bench, pose, want_grads=True, ray_stride=1):
                 res = render_oracle_with_grads(bench.dens, bench.feat, ogrid, o[sel], d[sel], ocfg, bench.G[sel], jitter=j, dtype=torch.float32)
                 gd += res["d_densities"]
                 gf += res["d_features"]
+                if kink is not None:
+                    kink |= relu_kink_voxels(bench.dens, ogrid, o[sel], d[sel], ocfg, jitter=j)
             else:
                 with torch.no_grad():
                     res = render_oracle(bench.dens, bench.feat, ogrid, o[sel], d[sel], ocfg, jitter=j, dtype=torch.float32)
             colour[sel] = res["colour"]
-    return colour, gd, gf
+    return colour, gd, gf, kink
 
 
 def parity_of_timed_leg(bench, pose, copy, world):
@@ -985,17 +990,21 @@ def parity_of_timed_leg(bench, pose, copy, world):
     colour_timed = bench.colour.clone()
     want_grads = world == 1
     got_d, got_f = (bench.d_dens.clone(), bench.d_feat.clone()) if want_grads else (None, None)
-    colour, gd, gf = oracle_frame(bench, pose, want_grads=want_grads)
+    colour, gd, gf, kink = oracle_frame(bench, pose, want_grads=want_grads)
     out = {"frame": f"last timed frame (pose {pose}, packed-volume copy {copy}), all {bench.R} rays",
            "oracle": "oracle/voxe_oracle.py, fp32 ATen ops on the same GPU, jitter = voxe_jitter_fill of the launches' (seed, offset)",
            "colour_max_abs": float((colour_timed - colour).abs().max()), "colour_tol": 1e-4}
     ok = out["colour_max_abs"] <= out["colour_tol"]
     if want_grads:
         # ReLU: a sample whose interpolated density is within rounding of 0 flips its derivative between two fp32
-        # evaluation orders (floor 3.5e-4 of ||g||inf at 160^3); Softplus has no kink
-        tol = 2e-3 if bench.postact == "relu" else 2e-4
+        # evaluation orders, which moves only that sample's scatter into its 8 corner voxels of d_densities: those voxels
+        # (oracle.relu_kink_voxels, margin 2e-3) are excluded there, everything else is held to the tolerance
+        tol = 2e-4
         for name, got, want in (("d_densities", got_d, gd), ("d_features", got_f, gf)):
             diff = (got - want)
+            if kink is not None and name == "d_densities":
+                diff = diff * (~kink)[..., None]
+                out["relu_kink_voxels_excluded"] = {"count": int(kink.sum()), "of": kink.numel()}
             out[name] = {"rel_l2": float(diff.norm() / want.norm().clamp_min(1e-30)),
                          "max_abs_over_inf": float(diff.abs().max() / want.abs().max().clamp_min(1e-30))}
             ok = ok and out[name]["rel_l2"] <= tol and out[name]["max_abs_over_inf"] <= tol
@@ -1007,22 +1016,24 @@ def parity_of_timed_leg(bench, pose, copy, world):
 
 
 def l2_probe(device):
-    """Measured L2 bandwidth: device-to-device copy between two 24 MB buffers (both resident in the 126 MB L2), read +
-    write bytes, best of 20, CUDA events -- the same recipe MEASURED_PEAKS.json uses for HBM, at an L2-resident size."""
-    n = 6 * 2**20
-    a, b = torch.empty(n, device=device), torch.empty(n, device=device)
+    """Measured L2 read bandwidth: torch.sum over a 64 MB buffer that stays resident in the 126 MB L2 between launches
+    (bytes read / time, best of 20 runs of 10 back-to-back launches, CUDA events).  Copies and elementwise kernels at
+    L2-resident sizes are launch-latency bound on this chip and only show HBM-class rates; a read-only reduction does not
+    write, so it is the closest stock-torch probe of what the L2 can deliver to loads."""
+    n = 16 * 2**20
+    a = torch.rand(n, device=device)
     for _ in range(5):
-        b.copy_(a)
+        a.sum()
     best = float("inf")
     for _ in range(20):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(10):
-            b.copy_(a)
+            a.sum()
         e1.record()
         torch.cuda.synchronize(device)
         best = min(best, e0.elapsed_time(e1) / 10)
-    return 2 * n * 4 / (best * 1e-3) / 1e9
+    return n * 4 / (best * 1e-3) / 1e9
 
 
 def ncu_capture(kernel_substring):
@@ -1378,7 +1389,7 @@ def run_ours(args):
             "model_frac": round(gbs(model_bwd, bwd_us) / peak, 4),
             "model_note": "SURVEY.md 8d contract (backward billed 2 x 8 corners x (F+1) x 4 B per in-AABB sample: a re-gather the kernel "
                           "replaced by the 16-byte reload, and a scatter for every sample) -- kept for continuity, not a ceiling",
-            "l2": {"peak_measured": round(l2_peak, 1), "unit": "GB/s", "how": "torch copy between two 24 MB (L2-resident) buffers, read+write bytes, best of 20",
+            "l2": {"peak_measured": round(l2_peak, 1), "unit": "GB/s", "how": "torch.sum over a 64 MB L2-resident buffer, bytes read / time, best of 20",
                    "lts_bytes_per_launch": None if not cap else cap.get("lts_bytes"),
                    "achieved": None if not cap or not cap.get("lts_bytes") else round(gbs(cap["lts_bytes"], bwd_us), 1),
                    "frac": None if not cap or not cap.get("lts_bytes") else round(gbs(cap["lts_bytes"], bwd_us) / l2_peak, 4)},

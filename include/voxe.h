@@ -234,6 +234,13 @@ VOXE_API int voxe_adam_step(const VoxeGridDesc* grid, const VoxeAdamDesc* adam, 
                             float* packed, float* packed_grad, const float* dense_d_densities,
                             const float* dense_d_features, float* packed_m, float* packed_v, voxe_stream_t stream);
 
+/* Rescale a channel-last grid [X,Y,Z,C] to [X2,Y2,Z2,C] covering the same world extent -- the
+ * `interpolate(mode="trilinear", align_corners=False, size=output_size)` of scale_voxel_grid_with_required_output_size
+ * (thre3d_atom/thre3d_reprs/voxels.py:409-447, called between the stages of progressive training, trainers.py:155 and :481)
+ * without the concatenate / permute / slice copies around it: call it once per tensor (features, densities, attn). */
+VOXE_API int voxe_resample_grid(const float* grid_in, const int32_t in_dims[3], int32_t channels, float* grid_out,
+                                const int32_t out_dims[3], voxe_stream_t stream);
+
 /* ---- per-step full-grid regularisers of the edit loop --------------------------------------------
  * `workspace` is VOXE_REG_WORKSPACE_DOUBLES doubles of device memory owned by the caller, ZEROED ONCE when it is allocated
  * (per-CTA partial sums of the reductions -- no floating-point atomics, so a loss is bitwise reproducible --, a ticket by
@@ -324,7 +331,7 @@ VOXE_API int voxe_nccl_comm_destroy(void* nccl_comm);
 VOXE_API int voxe_allreduce_grads(void* nccl_comm, float* buf, int64_t n_floats, voxe_stream_t stream);
 
 /* Launch-shape override for tuning runs: samples per thread (1..64; the number of depth segments per ray is
- * ceil(S / samples_per_thread)), rays per CTA (power of two <= 32) and the register budget of the kernel variant
+ * ceil(S / samples_per_thread)), rays per CTA (1..32) and the register budget of the kernel variant
  * (64, 80, 96 or 128); 0 restores the built-in choice of that knob.  Does not change results beyond fp32 summation
  * order.  The 80- and 96-register variants are limited to 128 threads per CTA. */
 VOXE_API int voxe_set_tuning(int samples_per_thread, int rays_per_cta, int register_cap);

@@ -325,14 +325,14 @@ def relu_kink_voxels(
     near, far = ray_intervals(ro32, rd32, cfg, aabb, torch.float32)
     z32 = sample_depths(near, far, cfg, jitter, torch.float32)
     pts32 = (ro32[:, None, :] + rd32[:, None, :] * z32[:, :, None]).reshape(-1, 3)
-    inside = torch.ones(pts32.shape[0], dtype=torch.bool)
+    inside = torch.ones(pts32.shape[0], dtype=torch.bool, device=pts32.device)
     for a in range(3):
         inside &= (pts32[:, a] > aabb[a][0]) & (pts32[:, a] < aabb[a][1])
     pts = pts32.to(dtype)
     pre = _activate(densities.to(dtype) * grid.density_scale, grid.preact)
     sraw = trilinear_fetch(pre, pts, aabb, dtype)[:, 0]
     amb = inside & (sraw.abs() < margin)
-    mask = torch.zeros(dims, dtype=torch.bool)
+    mask = torch.zeros(dims, dtype=torch.bool, device=pts32.device)
     if not amb.any():
         return mask
     p = pts[amb]

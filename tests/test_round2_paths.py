@@ -187,12 +187,18 @@ def test_render_and_backward_capture_into_a_cuda_graph():
     assert not torch.equal(colours[0], colours[1]) and not torch.equal(colours[1], colours[2]), "replays must draw fresh jitter"
     assert float((colours[0] - colours[1]).abs().max()) < 0.2  # the same picture, another jitter realisation
     # gradients of a replay belong to that replay's draws: re-zeroed and re-accumulated, never summed over replays
-    assert float((grads[0] - grads[1]).abs().max()) < 0.5 * float(grads[0].abs().max())
+    assert all(torch.isfinite(g).all() for g in grads)
+    assert abs(float(grads[2].abs().sum()) / float(grads[0].abs().sum()) - 1.0) < 0.2  # would be ~3 if replays accumulated
     # un-jittered twin: a replay equals the eager result exactly (pixels) / to atomics order (gradients)
     grid2, vm2, rays2, gcol2 = _scene(perturb=False, n_rays=640)
-    eager = vm2.render_rays(rays2)
-    eager.colour.backward(gcol2)
-    want_c, want_g = eager.colour.detach().clone(), grid2.features.grad.clone()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):  # eager reference + warm-up off the default stream, as torch's capture recipe asks
+        eager = vm2.render_rays(rays2)
+        eager.colour.backward(gcol2)
+        want_c, want_g = eager.colour.detach().clone(), grid2.features.grad.clone()
+        del eager  # a live graph keeps the leaves' AccumulateGrad nodes -- and the (uncaptured) stream they were made on -- alive
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
     grid2.densities.grad = grid2.features.grad = None
     g2 = torch.cuda.CUDAGraph()
     with torch.cuda.graph(g2):
@@ -212,7 +218,7 @@ def test_retuning_between_forward_and_backward_is_refused():
     grid, vm, rays, gcol = _scene()
     try:
         out = vm.render_rays(rays)
-        nat.set_tuning(8, 4, 128)  # another launch shape => another workspace layout
+        nat.set_tuning(16, 4, 128)  # 16 instead of 8 samples per thread at S=64 => another workspace layout
         with pytest.raises(RuntimeError, match="voxe_set_tuning"):
             out.colour.backward(gcol)
     finally:
@@ -269,3 +275,59 @@ def test_fused_adam_skips_without_gradients_and_leaves_frozen_tensors_alone():
 
     spec = grid.fused_spec()
     assert torch.equal(grid.packed_cache().get(spec, grid.densities, grid.features), pack_volume(spec, grid.densities, grid.features))
+
+
+OVERLAY_IMPORT = r"""
+import importlib, pathlib, sys, types, warnings
+warnings.simplefilter("ignore")
+overlay, product = sys.argv[1], sys.argv[2]
+
+class Stub(types.ModuleType):
+    # stand-in for third-party packages that are not installed in the build container (imageio, lpips, diffusers, ...)
+    def __getattr__(self, name):
+        if name.startswith("__"):
+            raise AttributeError(name)
+        m = Stub(self.__name__ + "." + name)
+        setattr(self, name, m)
+        sys.modules[m.__name__] = m
+        return m
+    def __call__(self, *a, **k):
+        return Stub("call")
+    def __mro_entries__(self, bases):
+        return (object,)
+
+for name in ("matplotlib", "matplotlib.pyplot", "easydict", "imageio", "lpips", "diffusers", "maxflow", "cc3d", "cv2"):
+    try:
+        importlib.import_module(name)
+    except ImportError:
+        sys.modules[name] = Stub(name)
+sys.path[:0] = [overlay, product]
+count = 0
+for p in sorted(pathlib.Path(overlay, "thre3d_atom").rglob("*.py")):
+    rel = p.relative_to(overlay).with_suffix("")
+    if "tests" in rel.parts or rel.name in ("conftest", "__init__"):
+        continue
+    importlib.import_module(".".join(rel.parts))
+    count += 1
+import thre3d_atom.thre3d_reprs.renderers as r
+assert "vox-e_b200" not in r.__file__ and hasattr(r, "render_sh_voxel_grid_camera"), r.__file__  # the overlaid file, from the checkout
+from thre3d_atom.modules import trainers, sds_trainer, attn_grid_trainer  # the reference's trainers, importing the replaced modules
+print("imported", count)
+"""
+
+
+@pytest.mark.skipif(not REFERENCE.is_dir(), reason="the reference tree only exists in the build container")
+def test_overlay_acceptance_every_reference_module_imports_over_the_replaced_ones(tmp_path):
+    """INTEGRATION.md route 1, executed: copy the reference's thre3d_atom, copy this package's thre3d_atom over it, and
+    import EVERY module of the result (trainers, SDS / attention trainers, visualisations, data) in a fresh interpreter.
+    Third-party packages absent from the build container are stubbed; everything under thre3d_atom is real code."""
+    import shutil
+    import subprocess
+    import sys
+
+    overlay = tmp_path / "Vox-E"
+    shutil.copytree(REFERENCE / "thre3d_atom", overlay / "thre3d_atom")
+    shutil.copytree(ROOT / "vox-e_b200" / "thre3d_atom", overlay / "thre3d_atom", dirs_exist_ok=True)
+    r = subprocess.run([sys.executable, "-c", OVERLAY_IMPORT, str(overlay), str(ROOT / "vox-e_b200")], capture_output=True, text=True, cwd=tmp_path)
+    assert r.returncode == 0, r.stderr[-3000:]
+    assert int(r.stdout.split()[-1]) >= 30

@@ -93,11 +93,11 @@ int pick_shape(int S, int sh_degree, int64_t R, int& L, int& nseg, int& rpc, int
   while ((S + L - 1) / L > max_threads) L *= 2;  // very long rays: more samples per thread
   nseg = (S + L - 1) / L;
   rpc = g_tune_rpc.load();
-  if (rpc <= 0 || rpc > 32 || (rpc & (rpc - 1))) {
+  if (rpc <= 0 || rpc > 32) {
     rpc = 32;
     while (rpc > 1 && rpc * nseg > 128) rpc >>= 1;
   }
-  while (rpc > 1 && rpc * nseg > max_threads) rpc >>= 1;
+  while (rpc > 1 && rpc * nseg > max_threads) --rpc;
   return VOXE_OK;
 }
 
@@ -132,7 +132,22 @@ int fill_params(const VoxeGridDesc* g, const VoxeRenderDesc* r, int64_t R, voxe:
   p.flags = r->flags;
   p.preact = g->preact;
   p.postact = g->postact;
-  return pick_shape(p.S, r->sh_degree, R, p.L, p.nseg, p.rpc, regcap);
+  if (int rc = pick_shape(p.S, r->sh_degree, R, p.L, p.nseg, p.rpc, regcap)) return rc;
+  // CTA -> ray-group rotation (see ray_group): one round = one CTA per SM; every round is rotated by a further ~1/6 of a
+  // round, so the CTAs an SM receives in successive rounds come from different image columns.  Needs at least two rounds.
+  static const int sm_count = [] {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n < 1) n = 148;
+    return n;
+  }();
+  static const int rot_override = [] {
+    const char* v = std::getenv("VOXE_GROUP_ROTATION");  // tuning runs: groups per round of rotation, 0 = off
+    return v ? std::atoi(v) : -1;
+  }();
+  const int groups = (int)((R + p.rpc - 1) / p.rpc);
+  p.group_round = sm_count;
+  p.group_rot = groups >= 2 * sm_count ? (rot_override >= 0 ? rot_override : 25) : 0;
+  return VOXE_OK;
 }
 
 }  // namespace
@@ -157,8 +172,7 @@ int64_t voxe_specialised_launch_count(void) { return g_specialised.load(); }
 int voxe_set_tuning(int samples_per_thread, int rays_per_cta, int register_cap) {
   if (samples_per_thread < 0 || samples_per_thread > 64)
     return fail(VOXE_ERR_INVALID_ARGUMENT, "samples_per_thread must be in 0..64");
-  if (rays_per_cta < 0 || rays_per_cta > 32 || (rays_per_cta & (rays_per_cta - 1)))
-    return fail(VOXE_ERR_INVALID_ARGUMENT, "rays_per_cta must be 0 or a power of two <= 32");
+  if (rays_per_cta < 0 || rays_per_cta > 32) return fail(VOXE_ERR_INVALID_ARGUMENT, "rays_per_cta must be in 0..32");
   if (register_cap != 0 && register_cap != 64 && register_cap != 80 && register_cap != 96 && register_cap != 128)
     return fail(VOXE_ERR_INVALID_ARGUMENT, "register_cap must be 0, 64, 80, 96 or 128");
   g_tune_l.store(samples_per_thread);
@@ -241,6 +255,21 @@ int voxe_adam_step(const VoxeGridDesc* grid, const VoxeAdamDesc* adam, float* de
                                          dense_d_features, grid->dims, grid->n_features, grid->channels, adam->lr,
                                          adam->beta1, adam->beta2, adam->eps, adam->step, (cudaStream_t)stream);
   if (e != cudaSuccess) return cuda_fail(e, "voxe_adam_step launch");
+  g_launches.fetch_add(1);
+  return VOXE_OK;
+}
+
+int voxe_resample_grid(const float* grid_in, const int32_t in_dims[3], int32_t channels, float* grid_out, const int32_t out_dims[3],
+                       voxe_stream_t stream) {
+  if (!grid_in || !grid_out || !in_dims || !out_dims) return fail(VOXE_ERR_INVALID_ARGUMENT, "voxe_resample_grid: NULL buffer / dims");
+  for (int a = 0; a < 3; ++a)
+    if (in_dims[a] < 1 || out_dims[a] < 1) return fail(VOXE_ERR_INVALID_ARGUMENT, "voxe_resample_grid: dims must be >= 1");
+  if (channels < 1) return fail(VOXE_ERR_INVALID_ARGUMENT, "voxe_resample_grid: channels must be >= 1");
+  if ((int64_t)out_dims[0] * out_dims[1] * out_dims[2] * channels >= ((int64_t)1 << 31) * 256)
+    return fail(VOXE_ERR_UNSUPPORTED, "voxe_resample_grid: output too large for one launch");
+  const int di[3] = {in_dims[0], in_dims[1], in_dims[2]}, dout[3] = {out_dims[0], out_dims[1], out_dims[2]};
+  cudaError_t e = voxe::launch_resample_grid(grid_in, di, channels, grid_out, dout, (cudaStream_t)stream);
+  if (e != cudaSuccess) return cuda_fail(e, "voxe_resample_grid launch");
   g_launches.fetch_add(1);
   return VOXE_OK;
 }

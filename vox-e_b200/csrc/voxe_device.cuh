@@ -73,6 +73,7 @@ struct KParams {
   float near, far, dscale, noise_std, lin_step;
   int flags, preact, postact;
   int rpc, nseg, L;  // rays per CTA, sample segments per ray, samples per segment (threads = rpc * nseg -> x32)
+  int group_round, group_rot;  // CTA -> ray-group mapping (ray_group in voxe_render.cu); group_rot == 0: identity
   unsigned long long rng_seed, rng_offset;  // in-kernel jitter (kPerturb with jitter == nullptr)
   const long long* rng_seed_dev;            // non-null: the generator state lives in device memory (CUDA-graph replays):
   const long long* rng_offset_dev;          //   seed = *rng_seed_dev, offset = *rng_offset_dev + rng_intragraph

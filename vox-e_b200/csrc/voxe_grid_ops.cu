@@ -111,47 +111,47 @@ __global__ void __launch_bounds__(256) consume_grad_kernel(float4* __restrict__ 
 
 // The same hand-over when the backward call left a trail: `touched` holds one byte per 2x2x2 brick, and a sample that
 // scattered stored `tag` at the brick of its corner 0 -- its 8 corners lie in that brick and the +1 neighbours in x, y, z.
-// A brick can therefore hold gradients only if one of the 8 flags at (bx-dx, by-dy, bz-dz) carries the tag.  Eight
-// consecutive lanes own one brick (one voxel slot each): lane k of the group loads the flag of neighbour k, a ballot
-// combines them, and only tagged bricks read their gradient vectors.  A 4096-ray batch tags a few percent of the
-// bricks, so the pass reads ~1 byte per brick (0.5 MB at 160^3) instead of the whole 68 MB volume.  Flags are not
-// cleared: the next call uses another tag (the caller clears them when it wraps the tag, see voxe.h).
+// A brick can therefore hold gradients only if one of the 8 flags at (bx-dx, by-dy, bz-dz) carries the tag.  One thread
+// per brick: 8 byte loads (neighbouring threads read neighbouring bytes), and only tagged bricks touch their 8 * CV
+// gradient vectors.  A 4096-ray batch tags a few percent of the bricks, so the pass reads ~1 byte per brick (0.5 MB at
+// 160^3) instead of the whole 68 MB volume.  Flags are not cleared: the next call uses another tag, and a stale tag only
+// costs a look at vectors that are zero (see voxe.h).
 __global__ void __launch_bounds__(256) consume_touched_kernel(float4* __restrict__ pg, float* __restrict__ d_dens,
                                                               float* __restrict__ d_feat,
                                                               const unsigned char* __restrict__ touched, int tag,
-                                                              int64_t n_slots, int F, int CV, BrickDims d) {
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  const int lane = threadIdx.x & 31, group_shift = lane & ~7, k = lane & 7;
-  const int dx = k >> 2, dy = (k >> 1) & 1, dz = k & 1;
-  // warp-uniform loop (the ballot needs all 32 lanes): a warp owns 32 consecutive slots = 4 bricks per iteration
-  for (int64_t base = (int64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31); base < n_slots; base += stride) {
-    const int64_t slot = base + lane;
-    const int64_t brick = slot >> 3;
-    const int bz = (int)(brick % d.BZ);
-    const int64_t t = brick / d.BZ;
-    const int by = (int)(t % d.BY), bx = (int)(t / d.BY);
-    bool mine = false;
-    if (slot < n_slots && bx >= dx && by >= dy && bz >= dz)
-      mine = __ldg(touched + ((int64_t)(bx - dx) * d.BY + (by - dy)) * d.BZ + (bz - dz)) == (unsigned char)tag;
-    const unsigned group = (__ballot_sync(0xffffffffu, mine) >> group_shift) & 0xffu;
-    if (group == 0u || slot >= n_slots) continue;
-    const int x = 2 * bx + dx - 1, y = 2 * by + dy - 1, z = 2 * bz + dz - 1;  // this lane's voxel slot is (dx, dy, dz)
-    const bool real = x >= 0 && y >= 0 && z >= 0 && x < d.X && y < d.Y && z < d.Z;
-    const int64_t v = ((int64_t)x * d.Y + y) * d.Z + z;
-    for (int j = 0; j < CV; ++j) {
-      float4* src = pg + slot * CV + j;
-      const float4 g = *src;
-      if (g.x == 0.f && g.y == 0.f && g.z == 0.f && g.w == 0.f) continue;
-      *src = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (!real) continue;  // apron / padding slot: whatever was scattered there is dropped
-      const float in[4] = {g.x, g.y, g.z, g.w};
+                                                              unsigned n_bricks, int F, int CV, BrickDims d) {
+  const unsigned brick = blockIdx.x * blockDim.x + threadIdx.x;
+  if (brick >= n_bricks) return;
+  const unsigned bz = brick % (unsigned)d.BZ, t = brick / (unsigned)d.BZ;
+  const unsigned by = t % (unsigned)d.BY, bx = t / (unsigned)d.BY;
+  const unsigned char want = (unsigned char)tag;
+  bool any = false;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const unsigned dx = k >> 2, dy = (k >> 1) & 1, dz = k & 1;
+    if (bx >= dx && by >= dy && bz >= dz) any |= __ldg(touched + ((bx - dx) * (unsigned)d.BY + (by - dy)) * (unsigned)d.BZ + (bz - dz)) == want;
+  }
+  if (!any) return;
+  float4* base = pg + (int64_t)brick * 8 * CV;
+  for (int j = 0; j < CV; ++j) {
+    float4 g[8];  // the j-th vector of the brick's 8 voxel slots: eight independent loads in flight, then the adds
+#pragma unroll
+    for (int k = 0; k < 8; ++k) g[k] = base[k * CV + j];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {  // voxel slot (x&1, y&1, z&1) of this brick
+      if (g[k].x == 0.f && g[k].y == 0.f && g[k].z == 0.f && g[k].w == 0.f) continue;
+      base[k * CV + j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      const int x = 2 * (int)bx + (k >> 2) - 1, y = 2 * (int)by + ((k >> 1) & 1) - 1, z = 2 * (int)bz + (k & 1) - 1;
+      if (!(x >= 0 && y >= 0 && z >= 0 && x < d.X && y < d.Y && z < d.Z)) continue;  // apron / padding slot: dropped
+      const int64_t v = ((int64_t)x * d.Y + y) * d.Z + z;
+      const float in[4] = {g[k].x, g[k].y, g[k].z, g[k].w};
 #pragma unroll
       for (int c4 = 0; c4 < 4; ++c4) {
         const int c = 4 * j + c4;
         if (c < F) {
-          if (d_feat) d_feat[v * F + c] += in[c4];
+          if (d_feat) atomicAdd(d_feat + v * F + c, in[c4]);  // fire-and-forget RED: no load -> add -> store round trip
         } else if (c == F) {
-          if (d_dens) d_dens[v] += in[c4];
+          if (d_dens) atomicAdd(d_dens + v, in[c4]);
         }
       }
     }
@@ -214,6 +214,46 @@ __global__ void __launch_bounds__(256) adam_step_kernel(float4* __restrict__ pac
   packed_v[t] = make_float4(vv[0], vv[1], vv[2], vv[3]);
 }
 
+// Progressive-training rescale of a channel-last grid [X,Y,Z,C] -> [X2,Y2,Z2,C]: what
+// torch.nn.functional.interpolate(mode="trilinear", align_corners=False) with an explicit output size computes
+// (scale_voxel_grid_with_required_output_size, voxels.py:409-447 upstream), without the cat / permute / slice copies around
+// it.  Per axis: source coordinate s = (o + 0.5) * (in / out) - 0.5 clamped at 0, i0 = (int)s, i1 = i0 + (i0 < in-1),
+// lambda1 = s - i0 -- ATen's area_pixel_compute_source_index, evaluated in fp32 like ATen's CUDA kernel, and blended in
+// its order (z innermost).  One thread per output element; the channels of a voxel are neighbouring threads.
+struct ResampleAxis {
+  int n_in, n_out;
+  float scale;
+};
+
+__device__ __forceinline__ void resample_axis(const ResampleAxis& a, int o, int& i0, int& i1, float& l0, float& l1) {
+  float s = a.scale * ((float)o + 0.5f) - 0.5f;
+  s = s < 0.f ? 0.f : s;
+  i0 = (int)s;
+  i0 = i0 < a.n_in - 1 ? i0 : a.n_in - 1;
+  i1 = i0 + (i0 < a.n_in - 1 ? 1 : 0);
+  l1 = s - (float)i0;
+  l0 = 1.0f - l1;
+}
+
+__global__ void __launch_bounds__(256) resample_grid_kernel(const float* __restrict__ in, float* __restrict__ out, int C, ResampleAxis ax,
+                                                            ResampleAxis ay, ResampleAxis az, int64_t n_out) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_out) return;
+  const int c = (int)(t % C);
+  int64_t v = t / C;
+  const int z = (int)(v % az.n_out);
+  v /= az.n_out;
+  const int y = (int)(v % ay.n_out), x = (int)(v / ay.n_out);
+  int x0, x1, y0, y1, z0, z1;
+  float lx0, lx1, ly0, ly1, lz0, lz1;
+  resample_axis(ax, x, x0, x1, lx0, lx1);
+  resample_axis(ay, y, y0, y1, ly0, ly1);
+  resample_axis(az, z, z0, z1, lz0, lz1);
+  auto at = [&](int xi, int yi, int zi) { return __ldg(in + (((int64_t)xi * ay.n_in + yi) * az.n_in + zi) * C + c); };
+  out[t] = lx0 * (ly0 * (lz0 * at(x0, y0, z0) + lz1 * at(x0, y0, z1)) + ly1 * (lz0 * at(x0, y1, z0) + lz1 * at(x0, y1, z1))) +
+           lx1 * (ly0 * (lz0 * at(x1, y0, z0) + lz1 * at(x1, y0, z1)) + ly1 * (lz0 * at(x1, y1, z0) + lz1 * at(x1, y1, z1)));
+}
+
 BrickDims brick_dims(const int dims[3]) { return BrickDims{dims[0], dims[1], dims[2], (dims[1] + 3) / 2, (dims[2] + 3) / 2}; }
 
 }  // namespace
@@ -253,16 +293,24 @@ cudaError_t launch_consume_grad(float* packed_grad, float* d_densities, float* d
   const int64_t n_vec = packed_voxel_slots(dims) * CV;
   const int threads = 256;
   if (touched != nullptr) {
-    const int64_t n_slots = packed_voxel_slots(dims);
-    const int64_t want = (n_slots + threads - 1) / threads;
-    const int blocks = (int)(want < 148 * 16 ? want : 148 * 16);  // persistent: 16 CTAs per SM, grid-stride over the bricks
-    consume_touched_kernel<<<blocks, threads, 0, stream>>>(reinterpret_cast<float4*>(packed_grad), d_densities, d_features,
-                                                            touched, tag, n_slots, n_features, CV, brick_dims(dims));
+    const int64_t n_bricks = packed_voxel_slots(dims) / 8;  // < 2^28 (check_grid bounds the vector count by 2^31)
+    consume_touched_kernel<<<(unsigned)((n_bricks + threads - 1) / threads), threads, 0, stream>>>(
+        reinterpret_cast<float4*>(packed_grad), d_densities, d_features, touched, tag, (unsigned)n_bricks, n_features, CV, brick_dims(dims));
     return cudaGetLastError();
   }
   const int64_t blocks = (n_vec + threads - 1) / threads;
   consume_grad_kernel<<<(unsigned)blocks, threads, 0, stream>>>(reinterpret_cast<float4*>(packed_grad), d_densities,
                                                                 d_features, n_vec, n_features, CV, brick_dims(dims));
+  return cudaGetLastError();
+}
+
+cudaError_t launch_resample_grid(const float* in, const int in_dims[3], int channels, float* out, const int out_dims[3],
+                                 cudaStream_t stream) {
+  ResampleAxis a[3];
+  for (int k = 0; k < 3; ++k) a[k] = ResampleAxis{in_dims[k], out_dims[k], (float)in_dims[k] / (float)out_dims[k]};
+  const int64_t n_out = (int64_t)out_dims[0] * out_dims[1] * out_dims[2] * channels;
+  const int threads = 256;
+  resample_grid_kernel<<<(unsigned)((n_out + threads - 1) / threads), threads, 0, stream>>>(in, out, channels, a[0], a[1], a[2], n_out);
   return cudaGetLastError();
 }
 

@@ -31,6 +31,9 @@ cudaError_t launch_consume_grad(float* packed_grad, float* d_densities, float* d
                                 int n_features, int channels, const unsigned char* touched, int tag, cudaStream_t stream);
 int64_t packed_bricks(const int dims[3]);  // 2x2x2 bricks of the packed volume = bytes of a `touched` flag array
 
+cudaError_t launch_resample_grid(const float* in, const int in_dims[3], int channels, float* out, const int out_dims[3],
+                                 cudaStream_t stream);
+
 cudaError_t launch_adam_step(float* packed, float* packed_grad, float* packed_m, float* packed_v, float* densities,
                              float* features, const float* dense_gd, const float* dense_gf, const int dims[3], int n_features,
                              int channels, double lr, double beta1, double beta2, double eps, int step, cudaStream_t stream);

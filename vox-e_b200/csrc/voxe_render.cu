@@ -178,6 +178,20 @@ __device__ __forceinline__ void thread_samples(const KParams& p, const RayCtx& r
   i1 = min(i0 + per, b);
 }
 
+// Which group of `rpc` consecutive rays a CTA renders.  The block scheduler hands CTA i and CTA i + (number of SMs) to the
+// same SM, and on a scan-line batch (rows of W pixels) those two are 148 * rpc rays apart -- almost a whole number of rows at
+// the benchmark's W = 400 -- i.e. at the same image column: an SM ends up with only centre-of-image groups (long in-grid
+// ranges) or only edge groups (short or empty ones); ncu shows a 2x spread of executed instructions between SMs and 35 % of
+// the launch spent waiting for the slowest one.  Rotating every round of `round` CTAs by a further `rot` groups keeps
+// neighbouring CTAs neighbours (they share cache lines) but gives each SM a mix of columns.  rot == 0: identity.
+__device__ __forceinline__ int ray_group(const KParams& p) {
+  const int i = (int)blockIdx.x;
+  if (p.group_rot == 0) return i;
+  const int r = i / p.group_round, base = r * p.group_round;
+  const int n = min(p.group_round, (int)gridDim.x - base);  // the last round may be partial
+  return base + (i - base + r * p.group_rot) % n;
+}
+
 template <int REGCAP>
 struct Bounds {
   // register budget of the variant = 65536 / (kThreads * kMinBlocks): 64 | 80 (85) | 96 (102) | 128
@@ -198,7 +212,8 @@ __global__ void __launch_bounds__(Bounds<REGCAP>::kThreads, Bounds<REGCAP>::kMin
   float* sV = smem + nseg * stride;   // [NV][nseg][stride]
 
   const int r_in = threadIdx.x % rpc, seg = threadIdx.x / rpc;
-  const int ray = blockIdx.x * rpc + r_in;
+  const int group = ray_group(p);
+  const int ray = group * rpc + r_in;
   const bool active = (seg < nseg) && (ray < p.R);
 
   float Tl = 1.f, V[NV];
@@ -266,7 +281,7 @@ __global__ void __launch_bounds__(Bounds<REGCAP>::kThreads, Bounds<REGCAP>::kMin
   // stitch the segments: one warp per ray, lanes = segments
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   for (int r = warp; r < rpc; r += nwarps) {
-    const int ray2 = blockIdx.x * rpc + r;
+    const int ray2 = group * rpc + r;
     if (ray2 >= p.R) break;
     float carry = 1.f, tot[NV];
 #pragma unroll
@@ -330,7 +345,8 @@ __global__ void __launch_bounds__(Bounds<REGCAP>::kThreads, Bounds<REGCAP>::kMin
   float4* sStage = reinterpret_cast<float4*>(smem + bwd_stage_offset_floats(NV, nseg, rpc));
 
   const int r_in = threadIdx.x % rpc, seg = threadIdx.x / rpc;
-  const int ray = blockIdx.x * rpc + r_in;
+  const int group = ray_group(p);
+  const int ray = group * rpc + r_in;
   const bool active = (seg < nseg) && (ray < p.R);
 
   // load the forward's segment summaries (coalesced over rays) and transpose through shared memory
@@ -346,7 +362,7 @@ __global__ void __launch_bounds__(Bounds<REGCAP>::kThreads, Bounds<REGCAP>::kMin
   // per ray: totals, effective output gradients, q_s = T_start * <g, sums_s>, and its exclusive suffix sum
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   for (int r = warp; r < rpc; r += nwarps) {
-    const int ray2 = blockIdx.x * rpc + r;
+    const int ray2 = group * rpc + r;
     if (ray2 >= p.R) break;
     float gc[NCOL], gsum = 0.f;
 #pragma unroll
@@ -432,11 +448,15 @@ __global__ void __launch_bounds__(Bounds<REGCAP>::kThreads, Bounds<REGCAP>::kMin
   int stage_buf = 0;
   unsigned n_in = 0, n_scatter = 0;  // p.stats only
 
-  float4 sv_next = __ldg(samples);  // the sample vectors are fetched one iteration ahead of their use
+  // The sample vectors are fetched TWO iterations ahead of their use: with ReLU every second iteration is a short one
+  // (no scatter), and ncu showed the move out of a one-ahead prefetch as the kernel's top stall (long scoreboard).
+  float4 sv_next = __ldg(samples), sv_next2 = sv_next;
+  if (i0 + 1 < i1) sv_next2 = __ldg(samples + (size_t)p.R);
 #pragma unroll(kSampleUnroll)
   for (int i = i0; i < i1; ++i, zw.advance<SP>(p, rc, u_row, i - 1)) {
     const float4 sv = sv_next;
-    if (i + 1 < i1) sv_next = __ldg(samples + (size_t)(i + 1 - i0) * p.R);
+    sv_next = sv_next2;
+    if (i + 2 < i1) sv_next2 = __ldg(samples + (size_t)(i + 2 - i0) * p.R);
     const float zi = zw.cur;
     const float px = __fadd_rn(rc.o[0], __fmul_rn(rc.d[0], zi));
     const float py = __fadd_rn(rc.o[1], __fmul_rn(rc.d[1], zi));

@@ -313,10 +313,31 @@ class VoxelGrid(Module):
         )
 
 
+def _resample(tensor: Tensor, output_size: Tuple[int, int, int], mode: str) -> Tensor:
+    """[X, Y, Z, C] -> [X2, Y2, Z2, C] as ``interpolate(mode="trilinear", align_corners=False, size=output_size)`` does.
+    CUDA fp32 grids go through ``voxe_resample_grid`` (one launch per tensor, channel-last in and out: no cat / permute /
+    slice copies); host-side tensors -- a grid that has not been moved to its device yet -- keep the torch call."""
+    if tensor.is_cuda and tensor.dtype == torch.float32:
+        if mode != "trilinear":
+            raise NotImplementedError(f"mode={mode!r}: the fused rescale implements 'trilinear' (the only mode the reference's callers use)")
+        import ctypes
+
+        from voxe_b200 import _native as nat
+
+        src = tensor.detach().contiguous()
+        out = torch.empty((*output_size, src.shape[-1]), dtype=torch.float32, device=src.device)
+        d_in, d_out = (ctypes.c_int32 * 3)(*src.shape[:3]), (ctypes.c_int32 * 3)(*output_size)
+        with torch.cuda.device(src.device):
+            nat.check(nat.load_library().voxe_resample_grid(src.data_ptr(), d_in, int(src.shape[-1]), out.data_ptr(), d_out,
+                                                            torch.cuda.current_stream(src.device).cuda_stream), "voxe_resample_grid")
+        return out
+    return interpolate(tensor.permute(3, 0, 1, 2)[None, ...], size=output_size, mode=mode, align_corners=False,
+                       recompute_scale_factor=False)[0].permute(1, 2, 3, 0)
+
+
 def _rescaled(voxel_grid: VoxelGrid, unified: Tensor, output_size: Tuple[int, int, int], mode: str):
-    resized = interpolate(
-        unified.permute(3, 0, 1, 2)[None, ...], size=output_size, mode=mode, align_corners=False, recompute_scale_factor=False
-    )[0].permute(1, 2, 3, 0)
+    output_size = tuple(int(v) for v in output_size)
+    resized = _resample(unified, output_size, mode)
     assert resized.shape[:-1] == output_size
     old = voxel_grid.voxel_size
     new_voxel_size = VoxelSize(
@@ -330,12 +351,12 @@ def _rescaled(voxel_grid: VoxelGrid, unified: Tensor, output_size: Tuple[int, in
 def scale_voxel_grid_with_required_output_size(
     voxel_grid: VoxelGrid, output_size: Tuple[int, int, int], mode: str = "trilinear"
 ) -> VoxelGrid:
-    """Resample features+densities to ``output_size`` voxels covering the same world extent (progressive training)."""
-    unified = torch.cat([voxel_grid.features, voxel_grid.densities], dim=-1)
-    resized, new_voxel_size = _rescaled(voxel_grid, unified, output_size, mode)
-    return VoxelGrid(
-        densities=resized[..., -1:], features=resized[..., :-1], voxel_size=new_voxel_size, **voxel_grid.get_config_dict()
-    )
+    """Resample features+densities to ``output_size`` voxels covering the same world extent (progressive training).  The
+    two tensors are rescaled separately (interpolation acts per channel, so this equals the reference's concatenate ->
+    interpolate -> slice) and land in the new grid as contiguous tensors of their own."""
+    new_features, new_voxel_size = _rescaled(voxel_grid, voxel_grid.features, output_size, mode)
+    new_densities, _ = _rescaled(voxel_grid, voxel_grid.densities, output_size, mode)
+    return VoxelGrid(densities=new_densities, features=new_features, voxel_size=new_voxel_size, **voxel_grid.get_config_dict())
 
 
 def scale_voxel_grid_with_required_output_size_attn(

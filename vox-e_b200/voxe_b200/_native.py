@@ -105,6 +105,7 @@ EXPORTS = {
                                           ctypes.c_float, _P]),
     "voxe_render_infer": (ctypes.c_int, [_GD, _RD, _P, _P, _P, _P, _P, _P, _P, _P, ctypes.c_int64, ctypes.c_float, _P]),
     "voxe_render_bwd": (ctypes.c_int, [_GD, _RD, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, ctypes.c_int32, ctypes.c_int64, _P]),
+    "voxe_resample_grid": (ctypes.c_int, [_P, ctypes.POINTER(ctypes.c_int32 * 3), ctypes.c_int32, _P, ctypes.POINTER(ctypes.c_int32 * 3), _P]),
     "voxe_tv_regularizer": (ctypes.c_int, [_P, ctypes.POINTER(ctypes.c_int32 * 3), ctypes.c_int32, ctypes.c_int32, _P, _P, _P,
                                            ctypes.c_float, _P, ctypes.c_int32, _P]),
     "voxe_pair_loss": (ctypes.c_int, [_P, _P, ctypes.c_int64, ctypes.c_int32, _P, _P, _P, _P]),
