@@ -688,21 +688,35 @@ def e2e_leg(device, rank, world, steps, warmup, dist, deferred=False, engine_thr
         with torch.cuda.graph(cuda_graph):
             static_colour, static_loss = render_frame(*static)
 
-    def one_frame(idx):
-        o_h, d_h, g_h = host[idx % len(host)]
+    # Input pipeline: the host -> device copy of a step's inputs (rays + upstream gradients of the whole frame, pinned
+    # memory) is issued on a copy stream one step ahead, the way a training loop's data loader prefetches; every step's
+    # copy still happens inside the timed region, overlapped with the previous step's kernels.
+    copy_stream = torch.cuda.Stream(device)
+    staged = {}
+
+    def stage(idx):
+        with torch.cuda.stream(copy_stream):
+            bufs = [h.to(device, non_blocking=True) for h in host[idx % len(host)]]
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+        staged[idx] = (bufs, ev)
+
+    def one_frame(idx, nxt=None):
+        if idx not in staged:
+            stage(idx)
+        (o, d, gc), ev = staged.pop(idx)
+        if nxt is not None:
+            stage(nxt)
+        torch.cuda.current_stream(device).wait_event(ev)
         if graph:
-            # the step's inputs land in the graph's static buffers; .grad is re-zeroed by the graph itself (the first
-            # backward of the captured frame created it with a zero-fill that is part of the graph)
-            for t, h in zip(static, (o_h, d_h, g_h)):
-                t.copy_(h, non_blocking=True)
+            # the step's inputs land in the graph's static buffers (device -> device); .grad is re-zeroed by the graph itself
+            # (the first backward of the captured frame created it with a zero-fill that is part of the graph)
+            for t, src in zip(static, (o, d, gc)):
+                t.copy_(src, non_blocking=True)
             cuda_graph.replay()
             return finish(static_colour, static_loss)
         grid.densities.grad = None
         grid.features.grad = None
-        # the step's inputs: rays and upstream gradients of the whole frame, pinned host memory -> device
-        o = o_h.to(device, non_blocking=True)
-        d = d_h.to(device, non_blocking=True)
-        gc = g_h.to(device, non_blocking=True)
         return finish(*render_frame(o, d, gc))
 
     with torch.autograd.set_multithreading_enabled(engine_threads):
@@ -711,9 +725,10 @@ def e2e_leg(device, rank, world, steps, warmup, dist, deferred=False, engine_thr
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(device)
+        frames = [(warmup + k) * world + rank for k in range(steps)]
         t0 = time.perf_counter()
-        for k in range(steps):
-            one_frame((warmup + k) * world + rank)
+        for k, idx in enumerate(frames):
+            one_frame(idx, frames[k + 1] if k + 1 < steps else None)
         torch.cuda.synchronize(device)
         elapsed = time.perf_counter() - t0
     if world > 1:
@@ -721,7 +736,8 @@ def e2e_leg(device, rank, world, steps, warmup, dist, deferred=False, engine_thr
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         elapsed = float(t.item())
     api = ("per 4096-ray batch: VolumetricModel.render_rays(Rays) -> out.colour.backward(dL/dcolour); per frame: one pinned H2D copy "
-           "of rays + upstream gradients, one D2H copy of the rendered colours and the loss")
+           "of rays + upstream gradients (issued one frame ahead on a copy stream, inside the timed region), one D2H copy of the "
+           "rendered colours and the loss")
     if graph:
         api += "; the frame's API calls captured once with torch.cuda.graph and replayed per frame on static input buffers"
     return {"value": world * R * steps / elapsed, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -1016,24 +1032,29 @@ def parity_of_timed_leg(bench, pose, copy, world):
 
 
 def l2_probe(device):
-    """Measured L2 read bandwidth: torch.sum over a 64 MB buffer that stays resident in the 126 MB L2 between launches
-    (bytes read / time, best of 20 runs of 10 back-to-back launches, CUDA events).  Copies and elementwise kernels at
-    L2-resident sizes are launch-latency bound on this chip and only show HBM-class rates; a read-only reduction does not
-    write, so it is the closest stock-torch probe of what the L2 can deliver to loads."""
-    n = 16 * 2**20
-    a = torch.rand(n, device=device)
-    for _ in range(5):
-        a.sum()
-    best = float("inf")
-    for _ in range(20):
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(10):
-            a.sum()
-        e1.record()
-        torch.cuda.synchronize(device)
-        best = min(best, e0.elapsed_time(e1) / 10)
-    return n * 4 / (best * 1e-3) / 1e9
+    """Measured L2 bandwidth: an elementwise kernel (torch.mul) streaming one buffer into another, both resident in the
+    126 MB L2 after the first pass; read + write bytes / time, best over buffer sizes of 8..40 MB and 20 runs of 10
+    back-to-back launches each, CUDA events.  (Stock-torch probe: small sizes are launch-latency bound, large ones spill
+    out of the L2, a same-dtype copy_ goes through the copy engine -- the best of the sizes is the figure reported.)"""
+    best_gbs, best_mb = 0.0, 0
+    for mb in (8, 16, 24, 32, 40):
+        n = mb * 2**18
+        a, b = torch.rand(n, device=device), torch.empty(n, device=device)
+        for _ in range(5):
+            torch.mul(a, 1.0001, out=b)
+        best = float("inf")
+        for _ in range(20):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(10):
+                torch.mul(a, 1.0001, out=b)
+            e1.record()
+            torch.cuda.synchronize(device)
+            best = min(best, e0.elapsed_time(e1) / 10)
+        gbs = 2 * n * 4 / (best * 1e-3) / 1e9
+        if gbs > best_gbs:
+            best_gbs, best_mb = gbs, mb
+    return best_gbs, best_mb
 
 
 def ncu_capture(kernel_substring):
@@ -1056,7 +1077,11 @@ def make_peer_volume_factory(device, world, collective):
         return None
     from voxe_b200.dist import PeerGradVolume
 
-    return lambda n_floats: PeerGradVolume(n_floats, device, multicast=(collective != "peer-p2p"))
+    # two ranks exchange as many bytes with plain peer loads / stores as through the switch's multicast reduction, and the
+    # plain path has the lower latency (measured at N = 2, 68 MB: 127 us against 205 us); from three ranks on the switch
+    # halves the bytes each link carries
+    multicast = collective == "peer" and world > 2
+    return lambda n_floats: PeerGradVolume(n_floats, device, multicast=multicast)
 
 
 def run_check(args):
@@ -1198,6 +1223,7 @@ def run_ours(args):
     torch.manual_seed(WL["seed"] + rank)
 
     headline = args.workload == "cfg2"
+    full = headline and not args.device_only  # --device-only: comparison runs keep the device leg, its parity check and roofline
     collective = args.collective
     peer_factory = None
     if world > 1 and collective != "nccl":
@@ -1252,7 +1278,7 @@ def run_ours(args):
                 bench.saved_lane = [bench.saved] + [torch.empty_like(bench.saved) for _ in range(bench.n_lanes - 1)]
                 res = {}
                 for what in ("fwd", "bwd", "both"):
-                    gs = bench.capture(what, poses=[0, 3, 5])
+                    gs = bench.capture(what, poses=sorted({0, 3 % len(bench.poses), 5 % len(bench.poses)}))
                     t_ms = bench.time_graphs(gs, 12, 3)
                     res[what] = round(1e3 * t_ms / (12 * len(bench.batches)), 2)
                     del gs
@@ -1296,7 +1322,7 @@ def run_ours(args):
 
     # strictly serialised variant first (one batch in flight), reported beside the headline
     serialized = None
-    if bench.n_lanes > 1 and headline:
+    if bench.n_lanes > 1 and full:
         lanes = bench.n_lanes
         bench.n_lanes = 1
         g1 = bench.capture("both")
@@ -1323,7 +1349,7 @@ def run_ours(args):
 
     # the same frame on a Softplus field (the reference scripts' default): every in-grid sample scatters
     softplus = None
-    if headline:
+    if full:
         twin = DeviceBench(device, rank, world, count_s_in=False, n_lanes=args.lanes, kernel_jitter=args.jitter == "kernel",
                            postact="softplus", share=bench)
         tg = twin.capture("both")
@@ -1369,7 +1395,7 @@ def run_ours(args):
         model_step = s_in_mean * (MODEL_BYTES_PER_SAMPLE_FWD + MODEL_BYTES_PER_SAMPLE_BWD) + bench.R * 96
         moved_step = (bwd_bytes + fwd_bytes) * n_b
         gbs = lambda nbytes, us: nbytes / (us * 1e-6) / 1e9  # noqa: E731
-        l2_peak = l2_probe(device)
+        l2_peak, l2_mb = l2_probe(device)
         cap, cap_src = ncu_capture("render_bwd_kernel") if args.workload == "cfg2" else (None, None)
         cap_f, _ = ncu_capture("render_fwd_kernel") if args.workload == "cfg2" else (None, None)
         step_us = ms_per_step * 1e3 / (len(graphs) if random_views else 1)
@@ -1389,7 +1415,7 @@ def run_ours(args):
             "model_frac": round(gbs(model_bwd, bwd_us) / peak, 4),
             "model_note": "SURVEY.md 8d contract (backward billed 2 x 8 corners x (F+1) x 4 B per in-AABB sample: a re-gather the kernel "
                           "replaced by the 16-byte reload, and a scatter for every sample) -- kept for continuity, not a ceiling",
-            "l2": {"peak_measured": round(l2_peak, 1), "unit": "GB/s", "how": "torch.sum over a 64 MB L2-resident buffer, bytes read / time, best of 20",
+            "l2": {"peak_measured": round(l2_peak, 1), "unit": "GB/s", "how": f"torch.mul between two {l2_mb} MB L2-resident buffers (best of 8..40 MB), read+write bytes / time",
                    "lts_bytes_per_launch": None if not cap else cap.get("lts_bytes"),
                    "achieved": None if not cap or not cap.get("lts_bytes") else round(gbs(cap["lts_bytes"], bwd_us), 1),
                    "frac": None if not cap or not cap.get("lts_bytes") else round(gbs(cap["lts_bytes"], bwd_us) / l2_peak, 4)},
@@ -1412,7 +1438,7 @@ def run_ours(args):
         dist.barrier()
 
     e2e = None
-    if headline:
+    if full:
         n_e2e, w_e2e = max(2, min(args.steps, args.e2e_steps)), min(args.warmup, 3)
         e2e = e2e_leg(device, rank, world, n_e2e, w_e2e, dist)
         variants = {
@@ -1434,7 +1460,7 @@ def run_ours(args):
         e2e["collective"] = None if world == 1 else "one per frame: VoxelGradAllReducer (flat buffer of both dense gradients, ncclAllReduce)"
 
     cpu = gpu_baseline = None
-    if rank == 0 and world == 1 and headline:
+    if rank == 0 and world == 1 and full:
         if not args.no_cpu:
             r = reference_subprocess("cpu", 8, 1)
             if "error" in r:
@@ -1451,15 +1477,15 @@ def run_ours(args):
                             "ours_serialized_over_baseline": None if not serialized else round(serialized["value"] / r["value"], 1)}
 
     fused_step = None
-    if rank == 0 and world == 1 and headline:
+    if rank == 0 and world == 1 and full:
         fused_step = fused_step_leg(device, peak)
 
     inference = None
-    if rank == 0 and world == 1 and headline:
+    if rank == 0 and world == 1 and full:
         inference = inference_leg(device)
 
     regularizers = sampler = None
-    if rank == 0 and world == 1 and headline:
+    if rank == 0 and world == 1 and full:
         regularizers = regularizers_leg(device, peak)
         sampler = sampler_leg(device)
 
@@ -1522,6 +1548,7 @@ def main():
                     help="--impl reference: cpu = the reference arm (host cores); cuda = the stock-ATen GPU baseline")
     ap.add_argument("--e2e-steps", type=int, default=8)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--device-only", action="store_true", help="comparison runs: skip the e2e / baseline / side legs (not the driver's line)")
     ap.add_argument("--ncu", action="store_true", help="profiler mode: run --steps eager frames and exit")
     ap.add_argument("--check", action="store_true", help="rank-sum check of the CUDA path's gradients through every collective; not a bench line")
     ap.add_argument("--parity", action="store_true", help="run the in-run oracle check for workloads other than cfg2 as well")

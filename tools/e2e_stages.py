@@ -82,6 +82,8 @@ def one_frame(idx):
     return v
 
 
+if "nothreads" in sys.argv:  # backward on the calling thread (the stock caller-side switch)
+    torch.autograd.set_multithreading_enabled(False)
 for k in range(3):
     one_frame(k)
 acc.clear()

@@ -17,6 +17,15 @@ for what in "$@"; do
         timeout 300 python -m pytest tests/test_round2_paths.py -q -m gpu -k $t > gpurun_out/${tag}_$t.log 2>&1
         echo "$t rc=$?"; grep -n "^E \|Error\|passed\|failed" gpurun_out/${tag}_$t.log | head -12
       done ;;
+    stages)
+      timeout 200 python tools/e2e_stages.py > gpurun_out/${tag}_stages.txt 2>&1; timeout 200 python tools/e2e_stages.py nothreads >> gpurun_out/${tag}_stages.txt 2>&1
+      cat gpurun_out/${tag}_stages.txt ;;
+    cfg5sweep2)
+      timeout 600 python bench.py --workload cfg5 --lanes 1 --sweep "64,16,128;64,32,128;32,16,128;32,32,128;16,16,128;48,16,128;64,24,128" 2>&1 | grep sweep
+      echo cfg3; timeout 600 python bench.py --workload cfg3 --lanes 1 --sweep "16,8,128;16,16,128;16,32,128;32,16,128;32,32,128;64,32,128" 2>&1 | grep sweep
+      echo cfg4; timeout 600 python bench.py --workload cfg4 --lanes 1 --sweep "16,8,80;16,8,96;32,16,64;16,16,64;16,32,64;32,32,64;16,8,128;16,16,128;32,16,128" 2>&1 | grep sweep ;;
+    cfg5sweep)
+      timeout 600 python bench.py --workload cfg5 --lanes 1 --sweep "16,4,128;32,8,128;64,16,128;32,4,128;64,8,128;16,8,128" 2>&1 | grep sweep ;;
     rpc)
       timeout 300 python bench.py --lanes 1 --sweep "16,8,96;16,7,96;16,6,96;16,5,96;16,4,96;15,7,96;14,7,96;16,7,80;16,7,128" 2>&1 | grep sweep
       echo "3 lanes"; timeout 300 python bench.py --lanes 3 --sweep "16,8,96;16,7,96;16,4,96" 2>&1 | grep sweep ;;

@@ -79,7 +79,18 @@ int check_render(const VoxeGridDesc* g, const VoxeRenderDesc* r, const float* ji
 // the 148 SMs; the 128-register variant has no spills and, with fewer and longer threads, leaves room for a second
 // batch's kernels to run beside it (a frame keeps 2-3 batches in flight): 30 us per 4096-ray batch fwd+bwd against
 // 38 us for 4 rays x 32 segments at 64 registers, although the kernels timed alone are equal.
-int pick_shape(int S, int sh_degree, int64_t R, int& L, int& nseg, int& rpc, int& regcap) {
+int sm_count() {
+  static const int n = [] {
+    int dev = 0, v = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v < 1) v = 148;
+    return v;
+  }();
+  return n;
+}
+
+// `backward` only affects rays per CTA (the workspace layout depends on L and nseg alone, so the two kernels of a render
+// may group rays differently).
+int pick_shape(int S, int sh_degree, int64_t R, bool backward, int& L, int& nseg, int& rpc, int& regcap) {
   // Register budget (does not affect the workspace layout).  With several batches in flight, or one large launch, the
   // number of resident CTAs is limited by registers, and the SH-0 kernels fit 96 / 80 registers without spilling:
   // 96 costs nothing on a lone 4096-ray launch and gains 5 % with three batches in flight; 80 is best for launches that
@@ -88,20 +99,35 @@ int pick_shape(int S, int sh_degree, int64_t R, int& L, int& nseg, int& rpc, int
   regcap = g_tune_reg.load();
   if (regcap != 64 && regcap != 80 && regcap != 96 && regcap != 128) regcap = (sh_degree == 0) ? (R >= 16384 ? 80 : 96) : 128;
   const int max_threads = voxe::max_threads_per_cta(regcap);
+  // Multi-vector voxels (SH degree >= 1: 64 / 112 / 208 bytes per corner): the gather wants WIDE ray bundles -- 16
+  // neighbouring rays at the same depth read neighbouring voxels, so a warp-wide load touches a few long runs instead of
+  // eight scattered ones -- and therefore few, long depth segments (~8-11 per ray).  Measured on the 15 GB grid of
+  // BASELINE.json's configuration 5 (512^3 SH-2, S = 512, 65 536 rays; profiles/r2_shape_sweeps.txt): forward 7.57 ms with
+  // 4 rays x 32 segments per CTA, 2.44 ms with 16 rays x 11 segments (8.4 TB/s of corner bytes: the L2 now serves the
+  // overlap between neighbouring rays); the backward (one TMA reduction per corner) is indifferent and keeps 8 rays.
+  const bool wide = sh_degree >= 1;
   L = g_tune_l.load();
-  if (L < 1 || L > 64) L = (S <= 32) ? 4 : (S < 128 ? 8 : 16);
+  if (L < 1 || L > 256) {
+    if (wide && S > 128) L = (((S + 10) / 11) + 15) / 16 * 16;  // ~11 segments, a multiple of 16 samples each
+    else L = (S <= 32) ? 4 : (S < 128 ? 8 : 16);
+  }
   while ((S + L - 1) / L > max_threads) L *= 2;  // very long rays: more samples per thread
   nseg = (S + L - 1) / L;
   rpc = g_tune_rpc.load();
   if (rpc <= 0 || rpc > 32) {
-    rpc = 32;
-    while (rpc > 1 && rpc * nseg > 128) rpc >>= 1;
+    if (wide && !backward && (R + 15) / 16 >= 2 * (int64_t)sm_count()) {
+      rpc = 16;
+      while (rpc > 8 && rpc * nseg > 256) rpc >>= 1;
+    } else {
+      rpc = 32;
+      while (rpc > 1 && rpc * nseg > 128) rpc >>= 1;
+    }
   }
   while (rpc > 1 && rpc * nseg > max_threads) --rpc;
   return VOXE_OK;
 }
 
-int fill_params(const VoxeGridDesc* g, const VoxeRenderDesc* r, int64_t R, voxe::KParams& p, int& regcap) {
+int fill_params(const VoxeGridDesc* g, const VoxeRenderDesc* r, int64_t R, bool backward, voxe::KParams& p, int& regcap) {
   std::memset(&p, 0, sizeof(p));
   p.R = (int)R;
   p.S = r->num_samples;
@@ -132,21 +158,17 @@ int fill_params(const VoxeGridDesc* g, const VoxeRenderDesc* r, int64_t R, voxe:
   p.flags = r->flags;
   p.preact = g->preact;
   p.postact = g->postact;
-  if (int rc = pick_shape(p.S, r->sh_degree, R, p.L, p.nseg, p.rpc, regcap)) return rc;
-  // CTA -> ray-group rotation (see ray_group): one round = one CTA per SM; every round is rotated by a further ~1/6 of a
-  // round, so the CTAs an SM receives in successive rounds come from different image columns.  Needs at least two rounds.
-  static const int sm_count = [] {
-    int dev = 0, n = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n < 1) n = 148;
-    return n;
-  }();
+  if (int rc = pick_shape(p.S, r->sh_degree, R, backward, p.L, p.nseg, p.rpc, regcap)) return rc;
+  // CTA -> ray-group rotation (see ray_group in voxe_render.cu), off by default: on the benchmark frames the work per
+  // group varies by +-8 % only and rotating the rounds changed nothing (profiles/r2_shape_sweeps.txt); kept as a tuning
+  // knob (VOXE_GROUP_ROTATION = groups of rotation per round of one CTA per SM) for batches with emptier image borders.
   static const int rot_override = [] {
-    const char* v = std::getenv("VOXE_GROUP_ROTATION");  // tuning runs: groups per round of rotation, 0 = off
-    return v ? std::atoi(v) : -1;
+    const char* v = std::getenv("VOXE_GROUP_ROTATION");
+    return v ? std::atoi(v) : 0;
   }();
   const int groups = (int)((R + p.rpc - 1) / p.rpc);
-  p.group_round = sm_count;
-  p.group_rot = groups >= 2 * sm_count ? (rot_override >= 0 ? rot_override : 25) : 0;
+  p.group_round = sm_count();
+  p.group_rot = (rot_override > 0 && groups >= 2 * sm_count()) ? rot_override : 0;
   return VOXE_OK;
 }
 
@@ -170,8 +192,8 @@ int64_t voxe_launch_count(void) { return g_launches.load(); }
 int64_t voxe_specialised_launch_count(void) { return g_specialised.load(); }
 
 int voxe_set_tuning(int samples_per_thread, int rays_per_cta, int register_cap) {
-  if (samples_per_thread < 0 || samples_per_thread > 64)
-    return fail(VOXE_ERR_INVALID_ARGUMENT, "samples_per_thread must be in 0..64");
+  if (samples_per_thread < 0 || samples_per_thread > 256)
+    return fail(VOXE_ERR_INVALID_ARGUMENT, "samples_per_thread must be in 0..256");
   if (rays_per_cta < 0 || rays_per_cta > 32) return fail(VOXE_ERR_INVALID_ARGUMENT, "rays_per_cta must be in 0..32");
   if (register_cap != 0 && register_cap != 64 && register_cap != 80 && register_cap != 96 && register_cap != 128)
     return fail(VOXE_ERR_INVALID_ARGUMENT, "register_cap must be 0, 64, 80, 96 or 128");
@@ -184,7 +206,7 @@ int voxe_set_tuning(int samples_per_thread, int rays_per_cta, int register_cap) 
 int64_t voxe_saved_floats(const VoxeRenderDesc* render, int64_t num_rays) {
   if (!render || render->num_samples < 2 || num_rays < 0) return 0;
   int L, nseg, rpc, regcap;
-  if (pick_shape(render->num_samples, render->sh_degree, num_rays, L, nseg, rpc, regcap)) return 0;
+  if (pick_shape(render->num_samples, render->sh_degree, num_rays, false, L, nseg, rpc, regcap)) return 0;
   return (int64_t)voxe::saved_floats_per_segment(render->n_colour, L) * nseg * num_rays;
 }
 
@@ -413,7 +435,7 @@ int voxe_render_fwd(const VoxeGridDesc* grid, const VoxeRenderDesc* render, cons
     return fail(VOXE_ERR_INVALID_ARGUMENT, "voxe_render_fwd: NULL buffer");
   voxe::KParams p;
   int regcap = 0;
-  if (int rc = fill_params(grid, render, num_rays, p, regcap)) return rc;
+  if (int rc = fill_params(grid, render, num_rays, false, p, regcap)) return rc;
   p.grid = reinterpret_cast<const float4*>(packed);
   p.rays_o = rays_o;
   p.rays_d = rays_d;
@@ -449,7 +471,7 @@ int voxe_render_camera(const VoxeGridDesc* grid, const VoxeRenderDesc* render, c
   if (!(min_transmittance >= 0.f)) return fail(VOXE_ERR_INVALID_ARGUMENT, "voxe_render_camera: min_transmittance must be >= 0");
   voxe::KParams p;
   int regcap = 0;
-  if (int rc = fill_params(grid, render, num_pixels, p, regcap)) return rc;
+  if (int rc = fill_params(grid, render, num_pixels, false, p, regcap)) return rc;
   p.grid = reinterpret_cast<const float4*>(packed);
   p.colour = colour;
   p.depth = depth;
@@ -481,7 +503,7 @@ int voxe_render_infer(const VoxeGridDesc* grid, const VoxeRenderDesc* render, co
   if (!(min_transmittance >= 0.f)) return fail(VOXE_ERR_INVALID_ARGUMENT, "voxe_render_infer: min_transmittance must be >= 0");
   voxe::KParams p;
   int regcap = 0;
-  if (int rc = fill_params(grid, render, num_rays, p, regcap)) return rc;
+  if (int rc = fill_params(grid, render, num_rays, false, p, regcap)) return rc;
   p.grid = reinterpret_cast<const float4*>(packed);
   p.rays_o = rays_o;
   p.rays_d = rays_d;
@@ -513,7 +535,7 @@ int voxe_render_bwd(const VoxeGridDesc* grid, const VoxeRenderDesc* render, cons
     return fail(VOXE_ERR_INVALID_ARGUMENT, "voxe_render_bwd: NULL buffer (saved is the workspace filled by voxe_render_fwd)");
   voxe::KParams p;
   int regcap = 0;
-  if (int rc = fill_params(grid, render, num_rays, p, regcap)) return rc;
+  if (int rc = fill_params(grid, render, num_rays, true, p, regcap)) return rc;
   p.saved = const_cast<float*>(saved);
   p.grid = reinterpret_cast<const float4*>(packed);
   p.grad = reinterpret_cast<float4*>(packed_grad);

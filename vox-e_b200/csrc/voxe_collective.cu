@@ -99,7 +99,7 @@ __global__ void __launch_bounds__(kThreads, 1) allreduce_peer_kernel(const __gri
   bool ok = peer_barrier(p, 0, &s_fail);
   if (ok) {
     if constexpr (MULTICAST) {
-      constexpr int U = 4;  // independent 16-byte requests per thread in flight (a round trip through the switch is ~2 us)
+      constexpr int U = 8;  // independent 16-byte requests per thread in flight (a round trip through the switch is ~2 us)
       for (long long i = r0 + threadIdx.x; i < r1; i += (long long)kThreads * U) {
         float4 acc[U];
 #pragma unroll

@@ -3,9 +3,10 @@
 //
 // It replaces, for one render call, everything the reference does between `render_sh_voxel_grid(...)`
 // (thre3d_atom/thre3d_reprs/renderers.py:50-105) and the ATen kernels: the sampler -> processor -> accumulator
-// chain of render_interface.py:140-171 and its autograd graph become ONE autograd node whose forward is
-// voxe_render_fwd and whose backward is voxe_render_bwd.  The node lives in C++ so that a 4096-ray training batch
-// costs a few microseconds of host time per direction instead of ~100 (Python autograd.Function + ctypes marshalling).
+// chain of render_interface.py:140-171 and its autograd graph become ONE autograd node (RenderNode below) created by a
+// voxe_render_fwd launch and whose backward is a voxe_render_bwd launch.  The node lives in C++ so that a 4096-ray
+// training batch costs a few microseconds of host time per direction instead of ~100 (Python autograd.Function + ctypes
+// marshalling).
 //
 // Gradient hand-over (backward): the kernel scatter-adds into the grid's persistent packed gradient volume
 // (always all-zero between calls), then one of
@@ -20,6 +21,7 @@
 #include <ATen/cuda/CUDAGeneratorImpl.h>
 #include <c10/cuda/CUDAGuard.h>
 #include <c10/cuda/CUDAStream.h>
+#include <torch/csrc/autograd/functions/utils.h>
 #include <torch/csrc/autograd/graph_task.h>
 
 #include <cstring>
@@ -101,54 +103,51 @@ bool direct_ok(const Tensor& param) {
          g.layout() == at::kStrided && !g.requires_grad();
 }
 
-class RenderFn : public torch::autograd::Function<RenderFn> {
- public:
-  static variable_list forward(AutogradContext* ctx, const Tensor& densities, const Tensor& features, const Tensor& packed,
-                               const Tensor& rays_o, const Tensor& rays_d, const c10::optional<Tensor>& jitter,
-                               const c10::optional<Tensor>& noise, const c10::optional<Tensor>& grad_volume,
-                               const c10::optional<Tensor>& dirty_flag, const c10::optional<Tensor>& touched,
-                               const c10::optional<Tensor>& touch_tag, const std::string& gdesc, const std::string& rdesc,
-                               int64_t mode) {
-    const auto gd = unpack_desc<VoxeGridDesc>(gdesc);
-    const auto rd = unpack_desc<VoxeRenderDesc>(rdesc);  // carries this call's (rng_seed, rng_offset)
-    const Tensor jit = jitter.value_or(Tensor()), noi = noise.value_or(Tensor());
-    const int64_t R = rays_o.size(0);
-    Tensor saved = at::empty({voxe_saved_floats(&rd, R)}, rays_o.options());
-    Outputs o = run_forward(gd, rd, packed, rays_o, rays_d, jit, noi, saved);
-    ctx->set_materialize_grads(false);
-    ctx->save_for_backward({densities, features, packed, rays_o, rays_d, jit, noi, saved});
-    // not SavedVariables: both are written between forward and backward by design (no version check wanted)
-    ctx->saved_data["grad_volume"] = grad_volume.value_or(Tensor());
-    ctx->saved_data["dirty_flag"] = dirty_flag.value_or(Tensor());
-    ctx->saved_data["touched"] = touched.value_or(Tensor());      // uint8 [bricks], device: trail of the backward's scatter
-    ctx->saved_data["touch_tag"] = touch_tag.value_or(Tensor());  // int64 [1], host: last tag handed out for `touched`
-    ctx->saved_data["gd"] = gdesc;
-    ctx->saved_data["rd"] = rdesc;
-    ctx->saved_data["mode"] = mode;
-    return {o.colour, o.depth, o.acc, o.disp};
+// The autograd node of one render call.  A hand-written torch::autograd::Node rather than a torch::autograd::Function:
+// the per-call cost of the Function machinery (AutogradContext, SavedVariable wrapping of eight tensors, string-keyed
+// saved_data, output wrapping and validation -- ~15 us per forward/backward pair on the bench hosts) is a third of the host
+// time of a 4096-ray batch, and none of it is needed here: the only inputs autograd differentiates are the two parameter
+// tensors, everything else the backward reads is private to this node.
+struct RenderNode : public torch::autograd::Node {
+  Tensor densities, features;  // the parameters this render read (next edges 0 and 1)
+  uint32_t dens_version = 0, feat_version = 0;
+  Tensor packed, rays_o, rays_d, jitter, noise, work, grad_volume, dirty_flag, touched, touch_tag;
+  VoxeGridDesc gd{};
+  VoxeRenderDesc rd{};  // carries this call's (rng_seed, rng_offset)
+  int64_t mode = kDense;
+  int64_t work_floats = 0;
+  bool released = false;
+
+  std::string name() const override { return "VoxeRenderBackward"; }
+
+  void release_variables() override {
+    std::lock_guard<std::mutex> lock(mutex_);
+    released = true;
+    packed.reset(); rays_o.reset(); rays_d.reset(); jitter.reset(); noise.reset(); work.reset();
+    grad_volume.reset(); dirty_flag.reset(); touched.reset(); touch_tag.reset();
   }
 
-  static variable_list backward(AutogradContext* ctx, variable_list grads) {
-    variable_list out(14);  // one (undefined) slot per forward argument
-    const bool need_d = ctx->needs_input_grad(0), need_f = ctx->needs_input_grad(1);
+  variable_list apply(variable_list&& grads) override {
+    std::lock_guard<std::mutex> lock(mutex_);
+    variable_list out(2);  // dL/d densities, dL/d features (undefined = no gradient through that edge)
+    TORCH_CHECK(!released, "Trying to backward through the render a second time (its workspace has already been freed). "
+                           "Specify retain_graph=True when calling backward the first time.");
+    const bool need_d = task_should_compute_output(0), need_f = task_should_compute_output(1);
     if (!need_d && !need_f) return out;
     bool any = false;
     for (const auto& g : grads) any |= g.defined();
     if (!any) return out;
-    const auto saved = ctx->get_saved_variables();
-    const Tensor &densities = saved[0], &features = saved[1], &packed = saved[2], &rays_o = saved[3], &rays_d = saved[4],
-                 &jitter = saved[5], &noise = saved[6], &work = saved[7];
-    Tensor grad_volume = ctx->saved_data["grad_volume"].toTensor();
-    const Tensor dirty_flag = ctx->saved_data["dirty_flag"].toTensor();
-    const auto gd = unpack_desc<VoxeGridDesc>(ctx->saved_data["gd"].toStringRef());
-    const auto rd = unpack_desc<VoxeRenderDesc>(ctx->saved_data["rd"].toStringRef());
-    const int64_t mode = ctx->saved_data["mode"].toInt();
+    // what SavedVariable would have checked for the two parameters: an in-place write (an optimiser step, say) between
+    // this render's forward and its backward would make the backward differentiate another function
+    TORCH_CHECK((!densities.defined() || densities._version() == dens_version) && (!features.defined() || features._version() == feat_version),
+                "one of the variables needed for gradient computation has been modified by an inplace operation: the voxel grid's "
+                "densities / features changed between a render's forward and its backward");
     const auto dev = packed.device();
     const c10::cuda::CUDAGuard guard(dev);
     const int64_t R = rays_o.size(0);
     // the workspace layout follows the launch shape, which voxe_set_tuning can change between the two calls
-    TORCH_CHECK(voxe_saved_floats(&rd, R) == work.numel(),
-                "voxe_set_tuning changed the launch shape between a render's forward and its backward (workspace of ", work.numel(),
+    TORCH_CHECK(voxe_saved_floats(&rd, R) == work_floats,
+                "voxe_set_tuning changed the launch shape between a render's forward and its backward (workspace of ", work_floats,
                 " floats, the backward now expects ", voxe_saved_floats(&rd, R), "); retune only between whole forward/backward pairs");
 
     Tensor g[4];
@@ -156,22 +155,23 @@ class RenderFn : public torch::autograd::Function<RenderFn> {
       if (grads[k].defined())
         g[k] = (grads[k].scalar_type() == at::kFloat && grads[k].is_contiguous()) ? grads[k] : grads[k].to(at::kFloat).contiguous();
     if (!g[0].defined()) g[0] = at::zeros({R, (int64_t)rd.n_colour}, rays_o.options());
-    if (!grad_volume.defined()) grad_volume = at::zeros_like(packed);  // no persistent volume attached: a fresh one
+    Tensor volume = grad_volume;
+    if (!volume.defined()) volume = at::zeros_like(packed);  // no persistent volume attached: a fresh one
 
     const auto stream = stream_of(dev);
     // Sparse hand-over: the kernel tags the bricks it scatters into and voxe_consume_grad visits only those.  A fresh tag
     // per backward; stale tags of earlier calls only cost the consume pass a few reads (it skips all-zero vectors), so the
     // flags are never cleared.
-    const Tensor touched = mode == kSink ? Tensor() : ctx->saved_data["touched"].toTensor();
+    const bool sparse = mode != kSink && touched.defined() && grad_volume.defined();
     int32_t tag = 0;
-    if (touched.defined()) {
-      int64_t* last = ctx->saved_data["touch_tag"].toTensor().data_ptr<int64_t>();
+    if (sparse) {
+      int64_t* last = touch_tag.data_ptr<int64_t>();
       *last = (*last % 255) + 1;
       tag = (int32_t)*last;
     }
-    uint8_t* touched_ptr = touched.defined() ? touched.data_ptr<uint8_t>() : nullptr;
+    uint8_t* touched_ptr = sparse ? touched.data_ptr<uint8_t>() : nullptr;
     check(voxe_render_bwd(&gd, &rd, cptr(packed), cptr(rays_o), cptr(rays_d), cptr(jitter), cptr(noise), cptr(work),
-                          cptr(g[0]), cptr(g[1]), cptr(g[2]), cptr(g[3]), mptr(grad_volume), touched_ptr, tag, R, stream),
+                          cptr(g[0]), cptr(g[1]), cptr(g[2]), cptr(g[3]), mptr(volume), touched_ptr, tag, R, stream),
           "voxe_render_bwd");
     if (mode == kSink) {
       if (dirty_flag.defined()) dirty_flag.data_ptr<int64_t>()[0] = 1;  // CPU flag owned by the accumulator
@@ -190,7 +190,7 @@ class RenderFn : public torch::autograd::Function<RenderFn> {
       if (need_d) d_dens = at::zeros(densities.sizes(), densities.options());
       if (need_f) d_feat = at::zeros(features.sizes(), features.options());
     }
-    check(voxe_consume_grad(&gd, mptr(grad_volume), mptr(d_dens), mptr(d_feat), touched_ptr, tag, stream), "voxe_consume_grad");
+    check(voxe_consume_grad(&gd, mptr(volume), mptr(d_dens), mptr(d_feat), touched_ptr, tag, stream), "voxe_consume_grad");
     if (!direct) {
       out[0] = d_dens;
       out[1] = d_feat;
@@ -259,14 +259,39 @@ std::vector<Tensor> render(const Tensor& densities, const Tensor& features, cons
   }
   const bool differentiable = at::GradMode::is_enabled() && ((densities.defined() && densities.requires_grad()) ||
                                                              (features.defined() && features.requires_grad()));
-  const std::string rdesc_call(reinterpret_cast<const char*>(&rd), sizeof(rd));  // with this call's RNG state
+  const auto gd = unpack_desc<VoxeGridDesc>(gdesc);
   if (!differentiable) {
-    const auto gd = unpack_desc<VoxeGridDesc>(gdesc);
     Outputs o = run_forward(gd, rd, packed, rays_o, rays_d, jitter, noise, Tensor());
     return {o.colour, o.depth, o.acc, o.disp};
   }
-  return RenderFn::apply(densities, features, packed, rays_o, rays_d, c10::optional<Tensor>(jitter),
-                         c10::optional<Tensor>(noise), grad_volume, dirty_flag, touched, touch_tag, gdesc, rdesc_call, mode);
+  const int64_t R = rays_o.size(0);
+  auto node = std::shared_ptr<RenderNode>(new RenderNode(), torch::autograd::deleteNode);
+  node->set_next_edges(torch::autograd::collect_next_edges(densities, features));
+  node->densities = densities;
+  node->features = features;
+  node->dens_version = densities.defined() ? densities._version() : 0;
+  node->feat_version = features.defined() ? features._version() : 0;
+  node->work_floats = voxe_saved_floats(&rd, R);
+  Outputs o;
+  {
+    at::NoGradGuard no_grad;
+    node->work = at::empty({node->work_floats}, rays_o.options());
+    o = run_forward(gd, rd, packed, rays_o, rays_d, jitter, noise, node->work);
+  }
+  node->packed = packed;
+  node->rays_o = rays_o;
+  node->rays_d = rays_d;
+  node->jitter = jitter;
+  node->noise = noise;
+  node->grad_volume = grad_volume.value_or(Tensor());
+  node->dirty_flag = dirty_flag.value_or(Tensor());
+  node->touched = touched.value_or(Tensor());      // uint8 [bricks], device: trail of the backward's scatter
+  node->touch_tag = touch_tag.value_or(Tensor());  // int64 [1], host: last tag handed out for `touched`
+  node->gd = gd;
+  node->rd = rd;
+  node->mode = mode;
+  torch::autograd::set_history({o.colour, o.depth, o.acc, o.disp}, node);
+  return {o.colour, o.depth, o.acc, o.disp};
 }
 
 }  // namespace
