@@ -627,7 +627,23 @@ def e2e_leg(device, rank, world, steps, warmup, dist, deferred=False, engine_thr
             packed = grid.packed_cache().get(spec, grid.densities, grid.features)
             volume = peer_volume(packed.numel())
             volume.adopt(grid.render_gradient_accumulator)
-    reducer = VoxelGradAllReducer([grid.densities, grid.features]) if world > 1 else None
+    # N > 1, dense gradients: .grad of both parameters are views into ONE peer-mapped buffer reduced in place by the library's
+    # kernel (PeerGradients); without peer mapping, one flat staging buffer through ncclAllReduce (VoxelGradAllReducer)
+    reducer = peer_grads = None
+    if world > 1 and not deferred:
+        if peer_volume is not None:
+            from voxe_b200.dist import PeerGradients
+
+            peer_grads = PeerGradients([grid.densities, grid.features])
+        else:
+            reducer = VoxelGradAllReducer([grid.densities, grid.features])
+
+    def clear_grads():
+        if peer_grads is not None:
+            peer_grads.zero()  # in place: the views stay attached (optimizer.zero_grad(set_to_none=False) semantics)
+        else:
+            grid.densities.grad = None
+            grid.features.grad = None
     poses = make_poses()
     host = []
     g = torch.Generator().manual_seed(7)
@@ -662,8 +678,10 @@ def e2e_leg(device, rank, world, steps, warmup, dist, deferred=False, engine_thr
             elif world > 1:
                 dist.all_reduce(grid.render_gradient_accumulator.buffer)
             grid.materialize_render_gradients()
+        elif peer_grads is not None:
+            peer_grads.allreduce()  # ONE collective, in place on the memory .grad lives in
         elif world > 1:
-            reducer()  # ONE collective: both dense gradients through one flat buffer
+            reducer()  # ONE collective: both dense gradients through one flat staging buffer
         return float(loss_total.item())  # D2H of the step's result; also orders the colour copy
 
     static = None
@@ -671,21 +689,20 @@ def e2e_leg(device, rank, world, steps, warmup, dist, deferred=False, engine_thr
         static = [torch.empty(R, 3, device=device) for _ in range(3)]
         for t, h in zip(static, host[0]):
             t.copy_(h)
-        grid.densities.grad = None
-        grid.features.grad = None
+        clear_grads()
         side = torch.cuda.Stream(device)
         side.wait_stream(torch.cuda.current_stream(device))
         with torch.cuda.stream(side):  # warm-up on a side stream, as torch's CUDA-graph recipe asks
             for _ in range(2):
-                grid.densities.grad = None
-                grid.features.grad = None
+                clear_grads()
                 render_frame(*static)
         torch.cuda.current_stream(device).wait_stream(side)
         torch.cuda.synchronize(device)
-        grid.densities.grad = None
-        grid.features.grad = None
+        clear_grads()
         cuda_graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(cuda_graph):
+            if peer_grads is not None:
+                peer_grads.zero()  # part of the replayed frame
             static_colour, static_loss = render_frame(*static)
 
     # Input pipeline: the host -> device copy of a step's inputs (rays + upstream gradients of the whole frame, pinned
@@ -715,8 +732,7 @@ def e2e_leg(device, rank, world, steps, warmup, dist, deferred=False, engine_thr
                 t.copy_(src, non_blocking=True)
             cuda_graph.replay()
             return finish(static_colour, static_loss)
-        grid.densities.grad = None
-        grid.features.grad = None
+        clear_grads()
         return finish(*render_frame(o, d, gc))
 
     with torch.autograd.set_multithreading_enabled(engine_threads):
@@ -1396,8 +1412,10 @@ def run_ours(args):
         moved_step = (bwd_bytes + fwd_bytes) * n_b
         gbs = lambda nbytes, us: nbytes / (us * 1e-6) / 1e9  # noqa: E731
         l2_peak, l2_mb = l2_probe(device)
-        cap, cap_src = ncu_capture("render_bwd_kernel") if args.workload == "cfg2" else (None, None)
-        cap_f, _ = ncu_capture("render_fwd_kernel") if args.workload == "cfg2" else (None, None)
+        # the committed captures: cfg 2 (<0, 3, 96>) and cfg 5 (<2, 3, 128>) kernels
+        has_capture = args.workload in ("cfg2", "cfg5") and args.batch == 0
+        cap, cap_src = ncu_capture(f"render_bwd_kernel<{WL['sh_degree']}, 3") if has_capture else (None, None)
+        cap_f, _ = ncu_capture(f"render_fwd_kernel<{WL['sh_degree']}, 3") if has_capture else (None, None)
         step_us = ms_per_step * 1e3 / (len(graphs) if random_views else 1)
         roof = {
             "bound": "hbm", "achieved": round(gbs(bwd_bytes, bwd_us), 1), "peak": peak, "unit": "GB/s",
@@ -1440,15 +1458,15 @@ def run_ours(args):
     e2e = None
     if full:
         n_e2e, w_e2e = max(2, min(args.steps, args.e2e_steps)), min(args.warmup, 3)
-        e2e = e2e_leg(device, rank, world, n_e2e, w_e2e, dist)
+        e2e = e2e_leg(device, rank, world, n_e2e, w_e2e, dist, peer_volume=peer_factory)
         variants = {
-            "cuda_graph": (dict(graph=True), "the same API calls of a frame captured once with torch.cuda.graph and replayed (stock torch; "
+            "cuda_graph": (dict(graph=True, peer_volume=peer_factory), "the same API calls of a frame captured once with torch.cuda.graph and replayed (stock torch; "
                                              "H2D of the frame's inputs and D2H of its results stay in the timed region)"),
-            "calling_thread_engine": (dict(engine_threads=False), "same loop under torch.autograd.set_multithreading_enabled(False): backward() "
+            "calling_thread_engine": (dict(engine_threads=False, peer_volume=peer_factory), "same loop under torch.autograd.set_multithreading_enabled(False): backward() "
                                                                   "runs on the calling thread (a caller-side switch)"),
             "deferred_grads": (dict(deferred=True, peer_volume=peer_factory), "same loop with VoxelGrid.accumulate_render_gradients(): gradients "
                                                                               "materialised once per frame"),
-            "whole_frame_call": (dict(whole_frame=True), "not the headline workload: the same frame as ONE render_rays(160000 rays) + ONE backward() "
+            "whole_frame_call": (dict(whole_frame=True, peer_volume=peer_factory), "not the headline workload: the same frame as ONE render_rays(160000 rays) + ONE backward() "
                                                          "(the SDS edit loop's calling pattern)"),
         }
         for name, (kw, note) in variants.items():
@@ -1457,7 +1475,9 @@ def run_ours(args):
                 e2e[name] = {"value": r["value"], "ms_per_step": r["ms_per_step"], "note": note}
             except Exception as exc:  # noqa: BLE001 -- a variant that cannot run is reported, the headline stands
                 e2e[name] = {"error": str(exc)[:300], "note": note}
-        e2e["collective"] = None if world == 1 else "one per frame: VoxelGradAllReducer (flat buffer of both dense gradients, ncclAllReduce)"
+        e2e["collective"] = None if world == 1 else (
+            "one per frame: voxe_allreduce_grads_peer in place on the peer-mapped buffer both .grad tensors are views of (voxe_b200.dist.PeerGradients)"
+            if peer_factory is not None else "one per frame: VoxelGradAllReducer (flat staging buffer of both dense gradients, ncclAllReduce)")
 
     cpu = gpu_baseline = None
     if rank == 0 and world == 1 and full:

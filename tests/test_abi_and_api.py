@@ -79,7 +79,18 @@ def test_argument_validation_without_a_gpu():
     rd.flags = 0
     # per segment (8 segments of 8 samples at S=64): (n_colour+3) summary floats + one float4 per sample slot
     assert lib.voxe_saved_floats(rd, 4096) == (6 + 4 * 8) * 8 * 4096
-    assert lib.voxe_set_tuning(3, 5, 0) == 1 and lib.voxe_set_tuning(0, 0, 0) == 0
+    assert lib.voxe_set_tuning(3, 33, 0) == 1 and lib.voxe_set_tuning(3, 5, 70) == 1 and lib.voxe_set_tuning(0, 0, 0) == 0
+    # the collective's descriptor checks (no launch without a GPU)
+    peers = nat.VoxePeerDesc()
+    peers.world_size, peers.rank = 2, 2
+    assert lib.voxe_allreduce_grads_peer(peers, 1024, None, None) == 1 and b"rank" in lib.voxe_last_error()
+    peers.rank = 0
+    assert lib.voxe_allreduce_grads_peer(peers, 1024, None, None) == 1 and b"NULL buffer" in lib.voxe_last_error()
+    assert lib.voxe_allreduce_grads_peer(peers, 1022, None, None) == 1 and b"multiple of 4" in lib.voxe_last_error()
+    assert lib.voxe_allreduce_grads(None, None, 16, None) == 1
+    assert lib.voxe_touched_bytes(gd) == 5 * 5 * 5 and lib.voxe_consume_grad(gd, None, None, None, None, 0, None) == 1
+    dims_in, dims_out = (ctypes.c_int32 * 3)(4, 4, 4), (ctypes.c_int32 * 3)(0, 4, 4)
+    assert lib.voxe_resample_grid(None, dims_in, 3, None, dims_out, None) == 1
     with pytest.raises(NotImplementedError):
         nat.check(2, "x")
     with pytest.raises(nat.NativeLibraryError):

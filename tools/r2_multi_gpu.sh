@@ -17,6 +17,15 @@ for what in "$@"; do
     nccl)
       run 400 $port --steps 40 --warmup 5 --device-only --collective nccl > gpurun_out/${tag}_bench_nccl_n$n.json 2> gpurun_out/${tag}_bench_nccl_n$n.err
       echo "bench nccl rc=$?"; tail -3 gpurun_out/${tag}_bench_nccl_n$n.err; timeout 60 python tools/show_bench.py gpurun_out/${tag}_bench_nccl_n$n.json ${tag}_nccl_n$n < /dev/null ;;
+    arblocks)
+      for b in 8 16 32 64 128; do
+        echo "VOXE_ALLREDUCE_BLOCKS=$b"
+        VOXE_ALLREDUCE_BLOCKS=$b run 200 $((port + b)) --check 2>/dev/null | python -c "
+import json,sys
+for ln in sys.stdin:
+    if ln.startswith('{'):
+        d=json.loads(ln)['collectives']; print({k[:40]: v.get('us') for k,v in d.items()})"
+      done ;;
     p2p)
       run 400 $port --steps 40 --warmup 5 --device-only --collective peer-p2p > gpurun_out/${tag}_bench_p2p_n$n.json 2> gpurun_out/${tag}_bench_p2p_n$n.err
       echo "bench p2p rc=$?"; tail -3 gpurun_out/${tag}_bench_p2p_n$n.err; timeout 60 python tools/show_bench.py gpurun_out/${tag}_bench_p2p_n$n.json ${tag}_p2p_n$n < /dev/null ;;

@@ -15,6 +15,7 @@
 //     library has no link-time dependency on it), for hosts whose volumes are not peer-mapped.
 #include <cuda_runtime.h>
 #include <dlfcn.h>
+#include <stdlib.h>
 #include <stdint.h>
 
 #include "voxe.h"
@@ -159,7 +160,12 @@ cudaError_t launch_allreduce_peer(const VoxePeerDesc& d, int64_t n_floats, unsig
   // enough CTAs to keep ~1.5 MB of 16-byte requests in flight per direction, few enough that CTA b of every rank is
   // resident at the same time whatever else runs (one CTA per SM at most, see __launch_bounds__)
   const long long want = (p.n_vec + (long long)kThreads * 16 - 1) / ((long long)kThreads * 16);
-  const int blocks = (int)(want < 1 ? 1 : (want > kBlocks ? kBlocks : want));
+  static const int block_cap = [] {  // tuning runs: VOXE_ALLREDUCE_BLOCKS caps the CTA count (must agree on every rank)
+    const char* v = getenv("VOXE_ALLREDUCE_BLOCKS");
+    const int n = v ? atoi(v) : 0;
+    return (n >= 1 && n <= kBlocks) ? n : kBlocks;
+  }();
+  const int blocks = (int)(want < 1 ? 1 : (want > block_cap ? block_cap : want));
   if (p.mc != nullptr) allreduce_peer_kernel<true><<<blocks, kThreads, 0, stream>>>(p, fail_flag);
   else allreduce_peer_kernel<false><<<blocks, kThreads, 0, stream>>>(p, fail_flag);
   return cudaGetLastError();

@@ -217,3 +217,50 @@ class PeerGradVolume:
         accumulator.buffer = self.buffer
         accumulator.touched = None
         accumulator.dirty = False
+
+
+class PeerGradients:
+    """Dense ``.grad`` tensors of a replicated grid, laid out back to back in ONE peer-mapped buffer, so that the step's
+    collective is a single in-place launch of the library's all-reduce kernel on the very memory autograd accumulates into --
+    no flat staging copy, no second collective for the second parameter.
+
+        grads = PeerGradients([grid.densities, grid.features])      # once, collectively, on every rank
+        for step in ...:
+            grads.zero()                                             # instead of optimizer.zero_grad(): keeps the views
+            loss.backward()                                          # the render's node adds into p.grad (these views)
+            grads.allreduce()                                        # ONE collective: p.grad = sum over ranks
+            optimizer.step()
+
+    ``optimizer.zero_grad(set_to_none=False)`` keeps the views as well; ``set_to_none=True`` (torch's default) drops them --
+    call :meth:`attach` again afterwards, or use :meth:`zero`."""
+
+    def __init__(self, params: Sequence[Tensor], group: Optional[dist.ProcessGroup] = None, multicast: Optional[bool] = None) -> None:
+        self.params = list(params)
+        numel = sum(p.numel() for p in self.params)
+        padded = (numel + 3) // 4 * 4  # whole 16-byte vectors
+        rank, world = world_info(group)
+        use_multicast = (world > 2) if multicast is None else multicast
+        self.volume = PeerGradVolume(padded, self.params[0].device, group=group, multicast=use_multicast)
+        self.views: List[Tensor] = []
+        offset = 0
+        for p in self.params:
+            self.views.append(self.volume.buffer[offset : offset + p.numel()].view(p.shape))
+            offset += p.numel()
+        self.attach()
+
+    def attach(self) -> None:
+        for p, v in zip(self.params, self.views):
+            if p.grad is not v:
+                if p.grad is not None:
+                    v.copy_(p.grad)
+                p.grad = v
+
+    def zero(self) -> None:
+        self.attach()
+        self.volume.buffer.zero_()
+
+    def allreduce(self) -> None:
+        for p, v in zip(self.params, self.views):
+            if p.grad is not v:
+                raise RuntimeError("a parameter's .grad is no longer the peer-mapped view (zero_grad(set_to_none=True)?); call attach() / zero()")
+        self.volume.allreduce()
