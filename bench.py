@@ -483,7 +483,7 @@ class DeviceBench:
     def scatter_stats(self, pose=0):
         """(in-grid samples the backward processed, samples whose 8-corner scatter it issued) for one frame, counted by the
         kernel itself (VoxeRenderDesc.stats); run once, eagerly, outside every timed region."""
-        counters = torch.zeros(2, dtype=torch.int64, device=self.device)
+        counters = torch.zeros(4, dtype=torch.int64, device=self.device)
         self.rd.stats = counters.data_ptr()
         try:
             for b0, b1 in self.batches:
@@ -493,7 +493,11 @@ class DeviceBench:
         finally:
             self.rd.stats = None
         self.packed_grad.zero_()
-        n_in, n_scatter = (int(v) for v in counters.tolist())
+        n_in, n_scatter, cell_leaders, corner_leaders = (int(v) for v in counters.tolist())
+        # intra-warp duplicates among the scattering lanes of a warp instruction (8 neighbouring rays x 4 depth ranges)
+        self.merge_stats = {"scattering_samples": n_scatter, "distinct_cells_per_warp_instruction": cell_leaders,
+                            "corner_reds": 8 * n_scatter, "distinct_voxels_per_warp_instruction": corner_leaders,
+                            "reds_after_perfect_intra_warp_merge": round(corner_leaders / max(1, 8 * n_scatter), 4)}
         return n_in, n_scatter
 
     def unpack(self):
@@ -1426,6 +1430,7 @@ def run_ours(args):
                             f"{MOVED_GATHER // 8} B RED payload; per ray: rays + dL/dcolour + segment summaries; fractions counted by the kernel "
                             "(VoxeRenderDesc.stats)",
             "scatter_fraction": None if frac_scatter is None else round(frac_scatter, 4),
+            "intra_warp_duplicates": getattr(bench, "merge_stats", None),
             # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture (the grid is
             # L2-resident at 160^3, hence far below the algorithmic bytes)
             "traffic": None if not cap else cap.get("dram_bytes"),
@@ -1452,6 +1457,7 @@ def run_ours(args):
             softplus["bwd_kernel"] = {"us_per_launch": round(t_bwd, 2), "scatter_fraction": round(t_frac, 4), "algorithmic_bytes_per_launch": round(t_bytes),
                                       "achieved": round(gbs(t_bytes, t_bwd), 1), "frac": round(gbs(t_bytes, t_bwd) / peak, 4)}
             softplus["fwd_kernel"] = {"us_per_launch": round(t_fwd, 2)}
+            softplus["bwd_kernel"]["intra_warp_duplicates"] = getattr(twin, "merge_stats", None)
     if world > 1:
         dist.barrier()
 

@@ -101,9 +101,11 @@ typedef struct VoxeRenderDesc {
   const int64_t* rng_seed_dev;   /* NULL, or DEVICE pointers to the seed and the offset of a generator whose state is  */
   const int64_t* rng_offset_dev; /* registered with a CUDA graph (torch's PhiloxCudaState under capture): the kernels   */
   uint64_t rng_offset_intragraph;/* then use (*rng_seed_dev, *rng_offset_dev + rng_offset_intragraph), re-read on replay */
-  uint64_t* stats;        /* NULL, or two DEVICE counters the backward adds to (measurement runs): [0] += in-grid     */
+  uint64_t* stats;        /* NULL, or four DEVICE counters the backward adds to (measurement runs): [0] += in-grid    */
                           /* samples it processed, [1] += samples whose 8-corner scatter it issued (a sample whose    */
-                          /* gradient is exactly zero -- e.g. ReLU at a non-positive density -- scatters nothing)     */
+                          /* gradient is exactly zero -- e.g. ReLU at a non-positive density -- scatters nothing),    */
+                          /* [2] += scattering samples whose cell no lower lane of the same warp instruction hits,    */
+                          /* [3] += corner REDs whose voxel no lower lane hits (what a perfect intra-warp merge keeps) */
 } VoxeRenderDesc;
 
 VOXE_API int voxe_abi_version(void);

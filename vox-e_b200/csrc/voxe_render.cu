@@ -446,7 +446,7 @@ __global__ void __launch_bounds__(Bounds<REGCAP>::kThreads, Bounds<REGCAP>::kMin
   sh_basis<DEG>(rc.d[0] * inv, rc.d[1] * inv, rc.d[2] * inv, (p.flags & kDiffuse) != 0, Y);
   float prefix = 0.f;  // sum of w*q over this segment's samples up to and including the current one
   int stage_buf = 0;
-  unsigned n_in = 0, n_scatter = 0;  // p.stats only
+  unsigned n_in = 0, n_scatter = 0, n_cell_leader = 0, n_corner_leader = 0;  // p.stats only
 
   // The sample vectors are fetched TWO iterations ahead of their use: with ReLU every second iteration is a short one
   // (no scatter), and ncu showed the move out of a one-ahead prefetch as the kernel's top stall (long scoreboard).
@@ -501,6 +501,15 @@ __global__ void __launch_bounds__(Bounds<REGCAP>::kThreads, Bounds<REGCAP>::kMin
     Corners c;
     make_corners(p, px, py, pz, c);
     if (p.touched != nullptr) p.touched[c.idx[0] >> 3] = (unsigned char)p.touch_tag;  // brick of corner 0 (8 slots per brick)
+    if (p.stats != nullptr) {
+      // measurement only: how many of the lanes that scatter in this warp instruction hit a cell / a voxel no lower lane
+      // hits -- the number of REDs a perfect intra-warp merge (match.any + shuffle reduction) would still issue
+      const unsigned active = __activemask();
+      const int lane_id = threadIdx.x & 31;
+      n_cell_leader += (__ffs(__match_any_sync(active, c.idx[0])) - 1 == lane_id);
+#pragma unroll
+      for (int qn = 0; qn < 8; ++qn) n_corner_leader += (__ffs(__match_any_sync(active, c.idx[qn])) - 1 == lane_id);
+    }
     const unsigned signs = SP::pre_abs(p.preact) ? corner_signs<DEG, NCOL>(p, c) : 0u;
     float gfe[LT::CV * 4];
 #pragma unroll
@@ -536,6 +545,8 @@ __global__ void __launch_bounds__(Bounds<REGCAP>::kThreads, Bounds<REGCAP>::kMin
   if (p.stats != nullptr) {  // measurement runs only (bench.py bills the bytes the kernel really moves)
     atomicAdd(p.stats, (unsigned long long)n_in);
     atomicAdd(p.stats + 1, (unsigned long long)n_scatter);
+    atomicAdd(p.stats + 2, (unsigned long long)n_cell_leader);
+    atomicAdd(p.stats + 3, (unsigned long long)n_corner_leader);
   }
 }
 
