@@ -1146,9 +1146,12 @@ def run_check(args):
 
     lib = nat.load_library()
     if world > 1:
-        for name, multicast in (("voxe_allreduce_grads_peer (multimem)", True), ("voxe_allreduce_grads_peer (peer loads/stores)", False)):
+        variants = [("voxe_allreduce_grads_peer (multimem)", True, 8), ("voxe_allreduce_grads_peer (peer loads/stores)", False, 0)]
+        if args.hybrid:  # tuning: split the CTAs of a launch between the two paths (measured at N = 8: no gain, 209-211 us)
+            variants += [(f"voxe_allreduce_grads_peer (hybrid: {k} of 8 CTAs multimem)", True, k) for k in (6, 4)]
+        for name, multicast, mc_share in variants:
             try:
-                vol = PeerGradVolume(full.numel(), device, multicast=multicast)
+                vol = PeerGradVolume(full.numel(), device, multicast=multicast, multicast_share=mc_share or None)
                 if multicast and not vol.multicast:
                     results[name] = {"skipped": "no multicast mapping on this box"}
                     continue
@@ -1170,6 +1173,8 @@ def run_check(args):
                 torch.cuda.synchronize(device)
                 results[name]["us"] = round(1e3 * e0.elapsed_time(e1) / 10, 1)
                 results[name]["bytes"] = full.numel() * 4
+                if rank == 0:
+                    print(f"[check] {name}: {results[name]}", file=sys.stderr, flush=True)
                 del vol
             except Exception as exc:  # noqa: BLE001
                 results[name] = {"error": str(exc)[:300]}
@@ -1577,6 +1582,7 @@ def main():
     ap.add_argument("--device-only", action="store_true", help="comparison runs: skip the e2e / baseline / side legs (not the driver's line)")
     ap.add_argument("--ncu", action="store_true", help="profiler mode: run --steps eager frames and exit")
     ap.add_argument("--check", action="store_true", help="rank-sum check of the CUDA path's gradients through every collective; not a bench line")
+    ap.add_argument("--hybrid", action="store_true", help="--check: also time launches split between the multicast and the plain peer path")
     ap.add_argument("--parity", action="store_true", help="run the in-run oracle check for workloads other than cfg2 as well")
     ap.add_argument("--workload", choices=["cfg2", "cfg3", "cfg4", "cfg5"], default="cfg2",
                     help="cfg2 is the headline (the line the driver reads); the others are recorded in DESIGN.md / profiles/")

@@ -309,7 +309,7 @@ VOXE_API int voxe_sample_rays(const VoxeSamplerDesc* sampler, const float* poses
  *   buffers[k]  rank k's gradient volume (buffers[rank] is the local one), 16-byte aligned, same size everywhere
  *   signals[k]  rank k's signal pad: VOXE_SIGNAL_WORDS uint32, zeroed once at allocation, used only by this call
  *   multicast   NVLS multicast mapping of the volumes (multimem.ld_reduce / multimem.st: the switch adds and
- *               replicates), or NULL: plain peer loads and stores
+ *               replicates), or NULL: plain peer loads and stores; multicast_share splits a launch between the two
  *   fail_flag   NULL, or a device uint32 that is OR-ed with 1 when a peer did not arrive within ~2 s (the kernel then
  *               gives up instead of hanging the GPU; the volume contents are undefined). */
 #define VOXE_MAX_PEERS 16
@@ -319,6 +319,8 @@ typedef struct VoxePeerDesc {
   float* buffers[VOXE_MAX_PEERS];
   uint32_t* signals[VOXE_MAX_PEERS];
   float* multicast;
+  int32_t multicast_share;   /* 1..8: of every 8 CTAs, how many take the multicast path while the others use plain peer  */
+                             /* loads / stores (the two are bound by different resources); 0 or 8: all (with `multicast`) */
 } VoxePeerDesc;
 VOXE_API int voxe_allreduce_grads_peer(const VoxePeerDesc* peers, int64_t n_floats, uint32_t* fail_flag, voxe_stream_t stream);
 

@@ -34,6 +34,7 @@ struct PeerParams {
   uint32_t* sig[kMaxPeers];
   float4* mc;
   int world, rank;
+  int mc_share;  // of every 8 consecutive CTAs, how many take the multicast path (the others: plain peer loads / stores)
   long long n_vec;
 };
 
@@ -86,8 +87,11 @@ __device__ __forceinline__ void multimem_st(float4* mc, const float4& v) {
   asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(mc), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
-template <bool MULTICAST>
+// The two paths are bound by different resources -- the multicast path by the switch's reduction rate (~330 GB/s per GPU
+// whatever the rank or CTA count), the plain path by the links (it moves twice the bytes) -- so a launch may split its CTAs
+// between them (PeerParams::mc_share).
 __global__ void __launch_bounds__(kThreads, 1) allreduce_peer_kernel(const __grid_constant__ PeerParams p, unsigned* fail_flag) {
+  const bool MULTICAST = p.mc != nullptr && (int)(blockIdx.x & 7) < p.mc_share;
   __shared__ unsigned s_fail;
   if (threadIdx.x == 0) s_fail = 0u;
   // this CTA's slice of the volume, and this rank's part of it (16-byte vectors)
@@ -99,7 +103,7 @@ __global__ void __launch_bounds__(kThreads, 1) allreduce_peer_kernel(const __gri
   // phase 0: the peers' backward kernels have finished (their streams reached this launch)
   bool ok = peer_barrier(p, 0, &s_fail);
   if (ok) {
-    if constexpr (MULTICAST) {
+    if (MULTICAST) {
       constexpr int U = 8;  // independent 16-byte requests per thread in flight (a round trip through the switch is ~2 us)
       for (long long i = r0 + threadIdx.x; i < r1; i += (long long)kThreads * U) {
         float4 acc[U];
@@ -166,8 +170,8 @@ cudaError_t launch_allreduce_peer(const VoxePeerDesc& d, int64_t n_floats, unsig
     return (n >= 1 && n <= kBlocks) ? n : kBlocks;
   }();
   const int blocks = (int)(want < 1 ? 1 : (want > block_cap ? block_cap : want));
-  if (p.mc != nullptr) allreduce_peer_kernel<true><<<blocks, kThreads, 0, stream>>>(p, fail_flag);
-  else allreduce_peer_kernel<false><<<blocks, kThreads, 0, stream>>>(p, fail_flag);
+  p.mc_share = p.mc == nullptr ? 0 : (d.multicast_share >= 1 && d.multicast_share <= 8 ? d.multicast_share : 8);
+  allreduce_peer_kernel<<<blocks, kThreads, 0, stream>>>(p, fail_flag);
   return cudaGetLastError();
 }
 

@@ -266,6 +266,15 @@ __device__ __forceinline__ void red_add_v4(float4* addr, float a, float b, float
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
+// Programmatic dependent launch (sm_90+): a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may
+// have its CTAs made resident while the previous kernel of the stream is still draining; pdl_wait() blocks until that
+// kernel has completed and its writes are visible (a no-op without the attribute), pdl_launch_dependents() tells the
+// scheduler that the NEXT kernel's CTAs may be placed as soon as every CTA of this grid has got here or exited.  The
+// render kernels of a training loop are a chain of short launches (fwd -> bwd -> hand-over -> fwd ...), each with ~2-3 us
+// of launch ramp on an otherwise idle GPU; this overlaps the ramp of one with the tail of the previous.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // Everything a thread needs to know about its ray.
 struct RayCtx {
   float o[3], d[3];

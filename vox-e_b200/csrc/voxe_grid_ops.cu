@@ -120,6 +120,7 @@ __global__ void __launch_bounds__(256) consume_touched_kernel(float4* __restrict
                                                               float* __restrict__ d_feat,
                                                               const unsigned char* __restrict__ touched, int tag,
                                                               unsigned n_bricks, int F, int CV, BrickDims d) {
+  asm volatile("griddepcontrol.wait;" ::: "memory");  // chained behind the backward kernel (launch_chained): its scatter is complete from here
   const unsigned brick = blockIdx.x * blockDim.x + threadIdx.x;
   if (brick >= n_bricks) return;
   const unsigned bz = brick % (unsigned)d.BZ, t = brick / (unsigned)d.BZ;
@@ -294,9 +295,9 @@ cudaError_t launch_consume_grad(float* packed_grad, float* d_densities, float* d
   const int threads = 256;
   if (touched != nullptr) {
     const int64_t n_bricks = packed_voxel_slots(dims) / 8;  // < 2^28 (check_grid bounds the vector count by 2^31)
-    consume_touched_kernel<<<(unsigned)((n_bricks + threads - 1) / threads), threads, 0, stream>>>(
-        reinterpret_cast<float4*>(packed_grad), d_densities, d_features, touched, tag, (unsigned)n_bricks, n_features, CV, brick_dims(dims));
-    return cudaGetLastError();
+    return launch_chained(consume_touched_kernel, dim3((unsigned)((n_bricks + threads - 1) / threads)), dim3(threads), 0, stream,
+                          reinterpret_cast<float4*>(packed_grad), d_densities, d_features, touched, tag, (unsigned)n_bricks, n_features,
+                          CV, brick_dims(dims));
   }
   const int64_t blocks = (n_vec + threads - 1) / threads;
   consume_grad_kernel<<<(unsigned)blocks, threads, 0, stream>>>(reinterpret_cast<float4*>(packed_grad), d_densities,

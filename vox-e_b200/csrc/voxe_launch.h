@@ -2,10 +2,39 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "voxe.h"
 
 namespace voxe {
+
+// Launch a kernel of a chain of short dependent launches (fwd -> bwd -> hand-over -> fwd ...) with the
+// programmatic-serialization attribute, so that its CTAs may become resident while the previous kernel of the stream
+// drains (the kernel itself blocks in griddepcontrol.wait until that kernel has completed; see pdl_wait in
+// voxe_device.cuh).  VOXE_PDL=0 launches plainly (A/B runs).  Works under stream capture (the edge becomes a programmatic
+// dependency of the graph).
+inline bool pdl_enabled() {
+  static const bool on = [] {
+    const char* v = getenv("VOXE_PDL");
+    return !(v != nullptr && v[0] == '0');
+  }();
+  return on;
+}
+
+template <class K, class... Args>
+cudaError_t launch_chained(K kernel, dim3 grid, dim3 block, size_t smem, cudaStream_t stream, const Args&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, args...);
+}
 
 struct KParams;
 struct CameraParams;

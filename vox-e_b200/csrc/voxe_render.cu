@@ -24,6 +24,8 @@
 //   vector REDs (red.global.add.v4.f32 -> REDG.E.ADD.F32x4).  The workspace is 16 bytes per sample, against the ~140
 //   bytes per sample autograd keeps for the reference.
 #include "voxe_device.cuh"
+#include <stdlib.h>
+
 #include "voxe_launch.h"
 
 #ifndef VOXE_UNROLL
@@ -215,6 +217,7 @@ __global__ void __launch_bounds__(Bounds<REGCAP>::kThreads, Bounds<REGCAP>::kMin
   const int group = ray_group(p);
   const int ray = group * rpc + r_in;
   const bool active = (seg < nseg) && (ray < p.R);
+  pdl_wait();  // everything below may read what the previous kernel of the stream wrote (rays, the packed volume, ...)
 
   float Tl = 1.f, V[NV];
 #pragma unroll
@@ -271,6 +274,7 @@ __global__ void __launch_bounds__(Bounds<REGCAP>::kThreads, Bounds<REGCAP>::kMin
       Tl *= (1.0f - alpha);
     }
   }
+  pdl_launch_dependents();  // the sample loop is over: the next kernel's CTAs may take the slots this grid frees from here on
   if (seg < nseg) {
     sT[seg * stride + r_in] = Tl;
 #pragma unroll
@@ -348,6 +352,7 @@ __global__ void __launch_bounds__(Bounds<REGCAP>::kThreads, Bounds<REGCAP>::kMin
   const int group = ray_group(p);
   const int ray = group * rpc + r_in;
   const bool active = (seg < nseg) && (ray < p.R);
+  pdl_wait();  // the forward's workspace, the upstream gradients
 
   // load the forward's segment summaries (coalesced over rays) and transpose through shared memory
   if (seg < nseg) {
@@ -418,6 +423,9 @@ __global__ void __launch_bounds__(Bounds<REGCAP>::kThreads, Bounds<REGCAP>::kMin
     }
   }
   __syncthreads();
+  // Unlike the forward, the backward lets the next kernel's CTAs in from here: its threads return one by one as their
+  // segments finish (there is no common point after the sample loop), and the hand-over kernel that follows is tiny.
+  pdl_launch_dependents();
   if (!active) return;
 
   // stream over this thread's samples, front to back
@@ -648,16 +656,9 @@ cudaError_t launch_pair(const KParams& p, bool backward, cudaStream_t stream) {
   size_t smem = sizeof(float) * ((size_t)(1 + LT::NV) * p.nseg * (p.rpc + 1) + (backward ? 2 * p.rpc : 0));
   if (backward && LT::CV > 1)
     smem = sizeof(float) * bwd_stage_offset_floats(LT::NV, p.nseg, p.rpc) + sizeof(float4) * 2 * (size_t)threads * BulkStage<LT::CV>::kSlot;
-  if (backward) {
-    auto k = render_bwd_kernel<DEG, NCOL, REGCAP, SP>;
-    if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k<<<blocks, threads, smem, stream>>>(p);
-  } else {
-    auto k = render_fwd_kernel<DEG, NCOL, REGCAP, SP>;
-    if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k<<<blocks, threads, smem, stream>>>(p);
-  }
-  return cudaGetLastError();
+  auto k = backward ? render_bwd_kernel<DEG, NCOL, REGCAP, SP> : render_fwd_kernel<DEG, NCOL, REGCAP, SP>;
+  if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  return launch_chained(k, dim3(blocks), dim3(threads), smem, stream, p);
 }
 
 template <int REGCAP>

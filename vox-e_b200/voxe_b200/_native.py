@@ -77,7 +77,7 @@ MAX_PEERS, SIGNAL_WORDS, NCCL_UNIQUE_ID_BYTES = 16, 4096, 128
 
 class VoxePeerDesc(ctypes.Structure):
     _fields_ = [("world_size", ctypes.c_int32), ("rank", ctypes.c_int32), ("buffers", ctypes.c_void_p * MAX_PEERS),
-                ("signals", ctypes.c_void_p * MAX_PEERS), ("multicast", ctypes.c_void_p)]
+                ("signals", ctypes.c_void_p * MAX_PEERS), ("multicast", ctypes.c_void_p), ("multicast_share", ctypes.c_int32)]
 
 
 class VoxeAdamDesc(ctypes.Structure):

@@ -157,6 +157,10 @@ class VoxelGradAllReducer:
             offset += n
 
 
+# Share of a launch's CTAs (out of 8) that take the multicast path when a multicast mapping exists (see csrc/voxe_collective.cu).
+DEFAULT_MULTICAST_SHARE = 8
+
+
 class PeerGradVolume:
     """A packed gradient volume that every rank of the group maps into its address space, reduced in place by the
     library's own kernel (``voxe_allreduce_grads_peer``: two-shot over NVLink peer memory, through the NVSwitch's
@@ -166,7 +170,8 @@ class PeerGradVolume:
     maps the peers; the exchange itself is ``csrc/voxe_collective.cu``.  ``buffer`` is an ordinary fp32 CUDA tensor; hand
     it to the backward kernels as their gradient volume (``adopt``) and call ``allreduce()`` once per optimiser step."""
 
-    def __init__(self, n_floats: int, device: torch.device, group: Optional[dist.ProcessGroup] = None, multicast: bool = True) -> None:
+    def __init__(self, n_floats: int, device: torch.device, group: Optional[dist.ProcessGroup] = None, multicast: bool = True,
+                 multicast_share: Optional[int] = None) -> None:
         import ctypes
 
         import torch.distributed._symmetric_memory as symm_mem
@@ -197,6 +202,9 @@ class PeerGradVolume:
         mc = int(h_buf.multicast_ptr) if multicast else 0
         desc.multicast = mc if mc else None
         self.multicast = bool(mc)
+        # of every 8 CTAs, how many go through the switch's multicast reduction (the rest: plain peer loads / stores)
+        self.multicast_share = (DEFAULT_MULTICAST_SHARE if multicast_share is None else int(multicast_share)) if mc else 0
+        desc.multicast_share = self.multicast_share
         self._desc, self._handles = desc, (h_buf, h_sig)
         torch.cuda.synchronize(device)
         dist.barrier(group)  # every rank's zero-fill of its signal pad is done before anybody's first launch
