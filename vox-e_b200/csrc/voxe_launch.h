@@ -8,15 +8,17 @@
 
 namespace voxe {
 
-// Launch a kernel of a chain of short dependent launches (fwd -> bwd -> hand-over -> fwd ...) with the
+// Launch a kernel of a chain of short dependent launches (fwd -> bwd -> hand-over -> fwd ...), optionally with the
 // programmatic-serialization attribute, so that its CTAs may become resident while the previous kernel of the stream
 // drains (the kernel itself blocks in griddepcontrol.wait until that kernel has completed; see pdl_wait in
-// voxe_device.cuh).  VOXE_PDL=0 launches plainly (A/B runs).  Works under stream capture (the edge becomes a programmatic
-// dependency of the graph).
+// voxe_device.cuh).  Opt-in (VOXE_PDL=1): measured on the benchmark frame it moves nothing beyond run-to-run noise --
+// pipelined frame 0.905 -> 0.893 ms, captured API frame 2.38 -> 2.32 ms, strictly serialised frame 1.54 -> 1.59 ms
+// (profiles/r2_pdl_ab.txt) -- the ~2 us launch ramp it hides is not where a 15-25 us launch loses its time.  Works under
+// stream capture (the edge becomes a programmatic dependency of the graph).
 inline bool pdl_enabled() {
   static const bool on = [] {
     const char* v = getenv("VOXE_PDL");
-    return !(v != nullptr && v[0] == '0');
+    return v != nullptr && v[0] == '1';
   }();
   return on;
 }

@@ -60,22 +60,30 @@ __device__ __forceinline__ float gather_sample(const KParams& p, const Corners& 
   for (int k = 0; k < LT::CV * 4; ++k) fe[k] = 0.f;
   float sig = 0.f;
   signs = 0u;
-  float4 v[8][LT::CV];
+  // Corners are gathered kGroup at a time: all loads of a group are issued before its first multiply-add.  Single-vector
+  // voxels (SH-0) take all 8 corners at once (8 float4 in flight); multi-vector voxels (SH >= 1: CV = 4 / 7 / 13 vectors
+  // per corner) take them in pairs -- 8 x CV vectors do not fit the register file next to the CV * 4 accumulators, and
+  // letting the compiler find that out cost 64-88 bytes of local-memory spills per thread at 128 registers.
+  constexpr int kGroup = LT::CV == 1 ? 8 : (LT::CV <= 4 ? 4 : 2);
+  float4 v[8][LT::CV];  // only kGroup rows are live at a time
 #pragma unroll
-  for (int q = 0; q < 8; ++q) {
-    const float4* src = p.grid + (size_t)c.idx[q] * LT::CV;
+  for (int q0 = 0; q0 < 8; q0 += kGroup) {
 #pragma unroll
-    for (int j = 0; j < LT::CV; ++j) v[q][j] = __ldg(src + j);
-  }
+    for (int q = q0; q < q0 + kGroup; ++q) {
+      const float4* src = p.grid + (size_t)c.idx[q] * LT::CV;
 #pragma unroll
-  for (int q = 0; q < 8; ++q) {
-    const float w = c.w[q];
+      for (int j = 0; j < LT::CV; ++j) v[q][j] = __ldg(src + j);
+    }
 #pragma unroll
-    for (int j = 0; j < LT::CV; ++j) {
-      fe[4 * j + 0] = fmaf(w, v[q][j].x, fe[4 * j + 0]);
-      fe[4 * j + 1] = fmaf(w, v[q][j].y, fe[4 * j + 1]);
-      fe[4 * j + 2] = fmaf(w, v[q][j].z, fe[4 * j + 2]);
-      fe[4 * j + 3] = fmaf(w, v[q][j].w, fe[4 * j + 3]);
+    for (int q = q0; q < q0 + kGroup; ++q) {
+      const float w = c.w[q];
+#pragma unroll
+      for (int j = 0; j < LT::CV; ++j) {
+        fe[4 * j + 0] = fmaf(w, v[q][j].x, fe[4 * j + 0]);
+        fe[4 * j + 1] = fmaf(w, v[q][j].y, fe[4 * j + 1]);
+        fe[4 * j + 2] = fmaf(w, v[q][j].z, fe[4 * j + 2]);
+        fe[4 * j + 3] = fmaf(w, v[q][j].w, fe[4 * j + 3]);
+      }
     }
   }
   // voxels.py:303-305: pre(density * scale) is applied at the voxels, then interpolated
@@ -241,7 +249,9 @@ __global__ void __launch_bounds__(Bounds<REGCAP>::kThreads, Bounds<REGCAP>::kMin
     // the dependent-instruction latency of one sample; unrolled by two, the loads and arithmetic of two consecutive
     // samples interleave.  Samples outside the box are rare here (thread_samples) and are masked, not skipped: their
     // corner addresses are clamped into the volume and their sigma / colour are forced to 0 (process.py:80-91).
-#pragma unroll(kSampleUnroll)
+    // Multi-vector voxels are not unrolled: two samples' accumulators and corner vectors do not fit 128 registers.
+    constexpr int kFwdUnroll = LT::CV == 1 ? kSampleUnroll : 1;
+#pragma unroll(kFwdUnroll)
     for (int i = i0; i < i1; ++i, zw.advance<SP>(p, rc, u_row, i - 1)) {
       const float zi = zw.cur;
       const float px = __fadd_rn(rc.o[0], __fmul_rn(rc.d[0], zi));   // sample.py:67: o + d * z (mul, then add)
