@@ -1097,10 +1097,9 @@ def make_peer_volume_factory(device, world, collective):
         return None
     from voxe_b200.dist import PeerGradVolume
 
-    # two ranks exchange as many bytes with plain peer loads / stores as through the switch's multicast reduction, and the
-    # plain path has the lower latency (measured at N = 2, 68 MB: 127 us against 205 us); from three ranks on the switch
-    # halves the bytes each link carries
-    multicast = collective == "peer" and world > 2
+    # measured, 68 MB (profiles/r2_check_n*.json): plain peer loads / stores 131 / 181 / 210-214 us at N = 2 / 4 / 8, the
+    # switch's multicast reduction 210 / 196 / 208 us -- the plain path up to four ranks, multimem above
+    multicast = collective == "peer" and world > 4
     return lambda n_floats: PeerGradVolume(n_floats, device, multicast=multicast)
 
 

@@ -247,7 +247,7 @@ class PeerGradients:
         numel = sum(p.numel() for p in self.params)
         padded = (numel + 3) // 4 * 4  # whole 16-byte vectors
         rank, world = world_info(group)
-        use_multicast = (world > 2) if multicast is None else multicast
+        use_multicast = (world > 4) if multicast is None else multicast  # measured crossover: see PeerGradVolume / DESIGN.md section 7
         self.volume = PeerGradVolume(padded, self.params[0].device, group=group, multicast=use_multicast)
         self.views: List[Tensor] = []
         offset = 0
