@@ -1221,6 +1221,24 @@ def run_check(args):
         dist.destroy_process_group()
 
 
+def rank_cpu_slice(local, local_world):
+    """This rank's share of the CPUs the process may run on, in units of physical cores (sysfs thread_siblings_list)."""
+    allowed = sorted(os.sched_getaffinity(0))
+    cores = {}
+    for cpu in allowed:
+        try:
+            sib = Path(f"/sys/devices/system/cpu/cpu{cpu}/topology/thread_siblings_list").read_text().strip()
+        except OSError:
+            sib = str(cpu)
+        cores.setdefault(sib, []).append(cpu)
+    groups = sorted(cores.values(), key=lambda g: g[0])
+    per = len(groups) // max(1, local_world)
+    if per >= 1:
+        return sorted(c for g in groups[local * per:(local + 1) * per] for c in g)
+    per = len(allowed) // max(1, local_world)  # fewer cores than ranks: fall back to logical CPUs
+    return allowed[local * per:(local + 1) * per] if per >= 1 else None
+
+
 def run_ours(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -1233,12 +1251,11 @@ def run_ours(args):
     pinned_cpus = None
     if world > 1 and not args.no_pin and hasattr(os, "sched_setaffinity"):
         # one rank per GPU on a shared host: give every rank its own slice of the host's CPUs (what numactl / taskset
-        # would do), so that eight Python loops and their NCCL helper threads do not migrate over each other
-        cpus = sorted(os.sched_getaffinity(0))
-        local_world = int(os.environ.get("LOCAL_WORLD_SIZE", world))
-        per = len(cpus) // max(1, local_world)
-        if per >= 1:
-            pinned_cpus = cpus[local * per:(local + 1) * per]
+        # would do), so that eight Python loops, their autograd worker threads and NCCL helper threads do not migrate over
+        # each other.  Slices are made of whole physical cores (both hyper-threads of a core go to the same rank): with
+        # contiguous logical ids two ranks would share every core they own through its sibling thread.
+        pinned_cpus = rank_cpu_slice(local, int(os.environ.get("LOCAL_WORLD_SIZE", world)))
+        if pinned_cpus:
             os.sched_setaffinity(0, pinned_cpus)
     if world > 1:
         import torch.distributed as dist
