@@ -1239,6 +1239,18 @@ def rank_cpu_slice(local, local_world):
     return allowed[local * per:(local + 1) * per] if per >= 1 else None
 
 
+def set_process_affinity(cpus):
+    """sched_setaffinity for EVERY thread of this process (torch's autograd worker threads exist already and keep their
+    own masks otherwise).  Returns the previous mask of the main thread."""
+    previous = os.sched_getaffinity(0)
+    for tid in os.listdir("/proc/self/task"):
+        try:
+            os.sched_setaffinity(int(tid), cpus)
+        except OSError:
+            pass
+    return previous
+
+
 def run_ours(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -1255,6 +1267,8 @@ def run_ours(args):
         # each other.  Slices are made of whole physical cores (both hyper-threads of a core go to the same rank): with
         # contiguous logical ids two ranks would share every core they own through its sibling thread.
         pinned_cpus = rank_cpu_slice(local, int(os.environ.get("LOCAL_WORLD_SIZE", world)))
+        if pinned_cpus and args.cpus_per_rank > 0:
+            pinned_cpus = pinned_cpus[:args.cpus_per_rank]
         if pinned_cpus:
             os.sched_setaffinity(0, pinned_cpus)
     if world > 1:
@@ -1496,12 +1510,24 @@ def run_ours(args):
             "whole_frame_call": (dict(whole_frame=True, peer_volume=peer_factory), "not the headline workload: the same frame as ONE render_rays(160000 rays) + ONE backward() "
                                                          "(the SDS edit loop's calling pattern)"),
         }
+        if world == 1 and hasattr(os, "sched_setaffinity"):
+            variants["single_cpu_affinity"] = (dict(), "the headline loop (default engine) with the whole process pinned to ONE CPU, as `taskset -c N` "
+                                                       "would: the hand-off between the Python thread and torch's autograd worker thread then stays "
+                                                       "on one core (on these virtualised hosts a cross-core wake-up costs ~8 us per hop)")
         for name, (kw, note) in variants.items():
+            previous = None
             try:
+                if name == "single_cpu_affinity":
+                    previous = set_process_affinity({sorted(os.sched_getaffinity(0))[0]})
                 r = e2e_leg(device, rank, world, n_e2e, w_e2e, dist, **kw)
                 e2e[name] = {"value": r["value"], "ms_per_step": r["ms_per_step"], "note": note}
             except Exception as exc:  # noqa: BLE001 -- a variant that cannot run is reported, the headline stands
                 e2e[name] = {"error": str(exc)[:300], "note": note}
+            finally:
+                if previous is not None:
+                    set_process_affinity(previous)
+        e2e["host_affinity"] = ("unpinned (the process may run on every CPU of the host)" if not pinned_cpus
+                                else f"every rank pinned to {len(pinned_cpus)} CPU(s) of its own slice of the host (os.sched_setaffinity)")
         e2e["collective"] = None if world == 1 else (
             "one per frame: voxe_allreduce_grads_peer in place on the peer-mapped buffer both .grad tensors are views of (voxe_b200.dist.PeerGradients)"
             if peer_factory is not None else "one per frame: VoxelGradAllReducer (flat staging buffer of both dense gradients, ncclAllReduce)")
@@ -1610,6 +1636,10 @@ def main():
                     help="stratified jitter of the device leg: generated inside the kernels (counter-based hash) or torch-drawn [R,S] buffers")
     ap.add_argument("--sweep", type=str, default="", help="tuning sweep: 'L,rpc,cap;L,rpc,cap;...'")
     ap.add_argument("--tune", type=str, default="", help="L,rpc,regcap launch-shape override for tuning runs")
+    ap.add_argument("--cpus-per-rank", type=int, default=1,
+                    help="N > 1: CPUs of its slice a rank is pinned to (0 = the whole slice).  Default 1: on these (virtualised) hosts the "
+                         "hand-off between the Python thread and torch's autograd worker thread costs ~8 us per hop across cores and "
+                         "degrades when eight ranks do it at once (5.1 ms per frame at N = 8 on 4-CPU slices, 3.1 ms on one CPU)")
     ap.add_argument("--no-pin", action="store_true", help="N > 1: do not pin each rank to its own slice of the host CPUs")
     ap.add_argument("--batch", type=int, default=0, help="rays per launch override (tuning / ray-batch sweeps; not a bench line)")
     args = ap.parse_args()

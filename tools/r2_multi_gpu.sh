@@ -26,6 +26,9 @@ for ln in sys.stdin:
     if ln.startswith('{'):
         d=json.loads(ln)['collectives']; print({k[:40]: v.get('us') for k,v in d.items()})"
       done ;;
+    onecpu)
+      run 400 $port --steps 10 --warmup 3 --e2e-steps 6 --cpus-per-rank 1 > gpurun_out/${tag}_bench_onecpu_n$n.json 2> gpurun_out/${tag}_bench_onecpu_n$n.err
+      echo "bench onecpu rc=$?"; tail -3 gpurun_out/${tag}_bench_onecpu_n$n.err; timeout 60 python tools/show_bench.py gpurun_out/${tag}_bench_onecpu_n$n.json ${tag}_onecpu_n$n < /dev/null ;;
     p2p)
       run 400 $port --steps 40 --warmup 5 --device-only --collective peer-p2p > gpurun_out/${tag}_bench_p2p_n$n.json 2> gpurun_out/${tag}_bench_p2p_n$n.err
       echo "bench p2p rc=$?"; tail -3 gpurun_out/${tag}_bench_p2p_n$n.err; timeout 60 python tools/show_bench.py gpurun_out/${tag}_bench_p2p_n$n.json ${tag}_p2p_n$n < /dev/null ;;
