@@ -433,6 +433,13 @@ class DeviceBench:
         if WL["name"].startswith("cfg5"):  # one 65536-ray batch through the middle of each frame
             lo = (WL["height"] // 2 - 32) * WL["width"]
             self.rays = [(o[lo:lo + WL["batch"]].contiguous(), d[lo:lo + WL["batch"]].contiguous()) for o, d in self.rays]
+        if WL.get("shuffle_rays") and share is None:
+            # measurement variant: the frame's rays in random order, as the reconstruction loop's batches are
+            # (sample_random_rays_and_pixels_synchronously, misc.py:126-138 upstream): no two neighbouring rays of a batch are
+            # neighbouring pixels
+            gp = torch.Generator(device=device).manual_seed(11)
+            perms = [torch.randperm(o.shape[0], device=device, generator=gp) for o, _ in self.rays]
+            self.rays = [(o[pm].contiguous(), d[pm].contiguous()) for (o, d), pm in zip(self.rays, perms)]
         self.R = self.rays[0][0].shape[0]
         g = torch.Generator().manual_seed(7)
         self.G = torch.randn(self.R, 3, generator=g).to(device)
@@ -1641,11 +1648,16 @@ def main():
                          "hand-off between the Python thread and torch's autograd worker thread costs ~8 us per hop across cores and "
                          "degrades when eight ranks do it at once (5.1 ms per frame at N = 8 on 4-CPU slices, 3.1 ms on one CPU)")
     ap.add_argument("--no-pin", action="store_true", help="N > 1: do not pin each rank to its own slice of the host CPUs")
+    ap.add_argument("--shuffle-rays", action="store_true",
+                    help="measurement variant: every frame's rays in random order (incoherent batches, as random training batches are)")
     ap.add_argument("--batch", type=int, default=0, help="rays per launch override (tuning / ray-batch sweeps; not a bench line)")
     args = ap.parse_args()
     select_workload(args.workload)
     if args.batch > 0:
         WL["batch"] = args.batch
+    if args.shuffle_rays:
+        WL["shuffle_rays"] = True
+        WL["name"] += " [rays of every frame shuffled]"
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
     if args.tune:
