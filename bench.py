@@ -1218,7 +1218,52 @@ def run_check(args):
         record("torch.distributed.all_reduce (NCCL)", buf)
     else:
         record("single rank (no collective)", share)
-    # the API path: render_rays + backward on each rank's share, one collective, compared with the unsharded dense gradients
+    # the API path: VolumetricModel.render_rays + backward() on each rank's share of the batches, ONE collective on the
+    # peer-mapped buffer both .grad tensors are views of (PeerGradients), compared on every rank with the dense gradients of
+    # an unsharded API render of the whole frame
+    api = {}
+    try:
+        from thre3d_atom.modules.volumetric_model import VolumetricModel
+        from thre3d_atom.rendering.volumetric.render_interface import Rays
+        from thre3d_atom.thre3d_reprs.renderers import SHVoxGridRenderConfig, render_sh_voxel_grid
+        from thre3d_atom.thre3d_reprs.voxels import VoxelGrid, VoxelSize
+        from thre3d_atom.utils.imaging_utils import CameraBounds
+        from voxe_b200.dist import PeerGradients
+
+        grid = VoxelGrid(bench.dens.clone(), bench.feat.clone(), VoxelSize(*(w / n for w, n in zip(WL["world"], WL["dims"]))),
+                         density_preactivation=torch.nn.Identity(), density_postactivation=torch.nn.ReLU(),
+                         expected_density_scale=WL["density_scale"], tunable=True)
+        vm = VolumetricModel(grid, render_sh_voxel_grid,
+                             SHVoxGridRenderConfig(num_samples_per_ray=WL["S"], camera_bounds=CameraBounds(WL["near"], WL["far"]), white_bkgd=True,
+                                                   perturb_sampled_points=False), device=device)
+        o, d = bench.rays[pose]
+
+        def api_grads(batches):
+            for b0, b1 in batches:
+                vm.render_rays(Rays(o[b0:b1], d[b0:b1])).colour.backward(bench.G[b0:b1])
+            torch.cuda.synchronize(device)
+
+        grid.densities.grad = grid.features.grad = None
+        api_grads(bench.batches)
+        want_d, want_f = grid.densities.grad.clone(), grid.features.grad.clone()
+        if world > 1:
+            grads = PeerGradients([grid.densities, grid.features])
+            grads.zero()
+            api_grads(bench.batches[rank::world])
+            grads.allreduce()
+            torch.cuda.synchronize(device)
+            assert not grads.volume.failed(), "a peer did not arrive"
+        errs = []
+        for got, want in ((grid.densities.grad, want_d), (grid.features.grad, want_f)):
+            t = torch.tensor([float((got - want).abs().max()) / float(want.abs().max())], device=device)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            errs.append(float(t.item()))
+        api = {"d_densities_max_abs_over_inf": errs[0], "d_features_max_abs_over_inf": errs[1], "ok": max(errs) <= 1e-5,
+               "path": "render_rays + backward per batch on each rank's share, PeerGradients.allreduce(), against the unsharded API gradients"}
+    except Exception as exc:  # noqa: BLE001
+        api = {"error": str(exc)[:300]}
+    results["API path (VolumetricModel + PeerGradients)"] = api
     if rank == 0:
         ok = all(r.get("ok", True) and "error" not in r for r in results.values())
         print(json.dumps({"check": "rank-sum of render_bwd_kernel gradients", "n_gpus": world, "frame": f"pose {pose}, {len(bench.batches)} batches dealt round-robin",
