@@ -605,7 +605,7 @@ class DeviceBench:
 
 
 def e2e_leg(device, rank, world, steps, warmup, dist, deferred=False, engine_threads=True, whole_frame=False, graph=False,
-            peer_volume=None):
+            peer_volume=None, frame_backward=False):
     """The frame through the public API, inputs starting in pinned host memory.
 
     engine_threads  True: torch's default autograd engine (a device worker thread runs every backward()); False: the stock
@@ -670,13 +670,19 @@ def e2e_leg(device, rank, world, steps, warmup, dist, deferred=False, engine_thr
 
     def render_frame(o, d, gc):
         """The API calls of one frame on device-resident inputs: per batch render_rays -> backward."""
-        colours = []
-        for o_b, d_b, g_b in zip(o.split(B), d.split(B), gc.split(B)):  # 4096-ray batches (views, no copies)
+        colours, roots = [], []
+        g_batches = gc.split(B)
+        for o_b, d_b, g_b in zip(o.split(B), d.split(B), g_batches):  # 4096-ray batches (views, no copies)
             out = vm.render_rays(Rays(o_b, d_b))
             # loss = <colour, G>: the upstream gradient is handed to autograd directly, as the SDS step does
             # (thre3d_reprs/sd.py:20-34 SpecifyGradient)
-            out.colour.backward(g_b)
+            if frame_backward:
+                roots.append(out.colour)
+            else:
+                out.colour.backward(g_b)
             colours.append(out.colour.detach())
+        if frame_backward:  # one engine invocation for the frame's 40 render nodes: the loss of a frame is the sum over its batches
+            torch.autograd.backward(roots, grad_tensors=list(g_batches))
         colour = torch.cat(colours)
         return colour, (colour * gc).sum()
 
@@ -1301,18 +1307,6 @@ def rank_cpu_slice(local, local_world):
     return allowed[local * per:(local + 1) * per] if per >= 1 else None
 
 
-def set_process_affinity(cpus):
-    """sched_setaffinity for EVERY thread of this process (torch's autograd worker threads exist already and keep their
-    own masks otherwise).  Returns the previous mask of the main thread."""
-    previous = os.sched_getaffinity(0)
-    for tid in os.listdir("/proc/self/task"):
-        try:
-            os.sched_setaffinity(int(tid), cpus)
-        except OSError:
-            pass
-    return previous
-
-
 def run_ours(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -1571,27 +1565,20 @@ def run_ours(args):
                                              "H2D of the frame's inputs and D2H of its results stay in the timed region)"),
             "calling_thread_engine": (dict(engine_threads=False, peer_volume=peer_factory), "same loop under torch.autograd.set_multithreading_enabled(False): backward() "
                                                                   "runs on the calling thread (a caller-side switch)"),
+            "frame_backward": (dict(frame_backward=True, peer_volume=peer_factory),
+                               "40 x render_rays(4096 rays), then ONE torch.autograd.backward over the 40 outputs (the frame's loss is the sum over "
+                               "its batches): every batch is still rendered and differentiated, the autograd engine is entered once per frame"),
             "deferred_grads": (dict(deferred=True, peer_volume=peer_factory), "same loop with VoxelGrid.accumulate_render_gradients(): gradients "
                                                                               "materialised once per frame"),
             "whole_frame_call": (dict(whole_frame=True, peer_volume=peer_factory), "not the headline workload: the same frame as ONE render_rays(160000 rays) + ONE backward() "
                                                          "(the SDS edit loop's calling pattern)"),
         }
-        if world == 1 and hasattr(os, "sched_setaffinity"):
-            variants["single_cpu_affinity"] = (dict(), "the headline loop (default engine) with the whole process pinned to ONE CPU, as `taskset -c N` "
-                                                       "would: the hand-off between the Python thread and torch's autograd worker thread then stays "
-                                                       "on one core (on these virtualised hosts a cross-core wake-up costs ~8 us per hop)")
         for name, (kw, note) in variants.items():
-            previous = None
             try:
-                if name == "single_cpu_affinity":
-                    previous = set_process_affinity({sorted(os.sched_getaffinity(0))[0]})
                 r = e2e_leg(device, rank, world, n_e2e, w_e2e, dist, **kw)
                 e2e[name] = {"value": r["value"], "ms_per_step": r["ms_per_step"], "note": note}
             except Exception as exc:  # noqa: BLE001 -- a variant that cannot run is reported, the headline stands
                 e2e[name] = {"error": str(exc)[:300], "note": note}
-            finally:
-                if previous is not None:
-                    set_process_affinity(previous)
         e2e["host_affinity"] = ("unpinned (the process may run on every CPU of the host)" if not pinned_cpus
                                 else f"every rank pinned to {len(pinned_cpus)} CPU(s) of its own slice of the host (os.sched_setaffinity)")
         e2e["collective"] = None if world == 1 else (
