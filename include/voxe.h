@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define VOXE_ABI_VERSION 12
+#define VOXE_ABI_VERSION 13
 
 #if defined(__GNUC__)
 #define VOXE_API __attribute__((visibility("default")))
@@ -242,6 +242,17 @@ VOXE_API int voxe_adam_step(const VoxeGridDesc* grid, const VoxeAdamDesc* adam, 
  * without the concatenate / permute / slice copies around it: call it once per tensor (features, densities, attn). */
 VOXE_API int voxe_resample_grid(const float* grid_in, const int32_t in_dims[3], int32_t channels, float* grid_out,
                                 const int32_t out_dims[3], voxe_stream_t stream);
+
+/* Stand-alone point queries: VoxelGrid.forward / forward_attn (thre3d_atom/thre3d_reprs/voxels.py:287-345, 347-406) outside
+ * the ray-marcher.  `points` [N,3] world coordinates, anywhere (zeros padding outside the grid, NO inside mask -- that one
+ * belongs to the renderer); `out` [N, n_features + 1] = (interpolated features, post(interpolated pre(density * scale))),
+ * read from the packed volume the render kernels use (pack the attention grid as `features` for forward_attn).
+ * voxe_query_points_bwd adds the gradient of sum(out * g_out) to the packed gradient volume (convert with
+ * voxe_unpack_grad); points receive no gradient (the reference's callers never differentiate them). */
+VOXE_API int voxe_query_points(const VoxeGridDesc* grid, const float* packed, const float* points, float* out, int64_t num_points,
+                               voxe_stream_t stream);
+VOXE_API int voxe_query_points_bwd(const VoxeGridDesc* grid, const float* packed, const float* points, const float* g_out,
+                                   float* packed_grad, int64_t num_points, voxe_stream_t stream);
 
 /* ---- per-step full-grid regularisers of the edit loop --------------------------------------------
  * `workspace` is VOXE_REG_WORKSPACE_DOUBLES doubles of device memory owned by the caller, ZEROED ONCE when it is allocated

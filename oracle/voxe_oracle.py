@@ -222,6 +222,18 @@ def trilinear_fetch(vol: Tensor, pts: Tensor, aabb, dtype) -> Tensor:
     return out
 
 
+def query_points_oracle(densities: Tensor, features: Tensor, grid: OracleGrid, points: Tensor, dtype=torch.float64) -> Tensor:
+    """VoxelGrid.forward / forward_attn (voxels.py:287-345, 347-406): [N, F + 1] = (interpolated features, post(interpolated
+    pre(densities * scale))) at world-space ``points`` [N,3] -- anywhere, zeros padding, no inside mask.  Pass the attention
+    grid [X,Y,Z,1] as ``features`` for forward_attn.  Differentiable w.r.t. both grid tensors."""
+    densities, features = densities.to(dtype), features.to(dtype)
+    aabb = aabb_of(tuple(features.shape[:3]), grid)
+    pts = points.to(torch.float32).to(dtype)
+    pre = _activate(densities * grid.density_scale, grid.preact)  # on the voxels, then interpolated (voxels.py:303-305)
+    sigma = _activate(trilinear_fetch(pre, pts, aabb, dtype), grid.postact)
+    return torch.cat([trilinear_fetch(features, pts, aabb, dtype), sigma], dim=-1)
+
+
 def render_oracle(
     densities: Tensor,
     features: Tensor,

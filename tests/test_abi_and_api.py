@@ -126,8 +126,8 @@ def test_render_refuses_cpu_tensors_and_unfused_callables():
     bad = VoxelGrid(torch.zeros(4, 4, 4, 1), torch.zeros(4, 4, 4, 3), VoxelSize(1, 1, 1), density_postactivation=torch.nn.Tanh())
     with pytest.raises(NotImplementedError):
         render_sh_voxel_grid(bad, rays, cfg)
-    with pytest.raises(NotImplementedError):
-        grid(torch.zeros(3, 3))  # stand-alone point queries are fused into the kernels
+    with pytest.raises(RuntimeError, match="CUDA only"):
+        grid(torch.zeros(3, 3))  # the stand-alone point query is a CUDA kernel too
 
 
 def test_value_types_keep_the_reference_contract():

@@ -127,10 +127,7 @@ int pick_shape(int S, int sh_degree, int64_t R, bool backward, int& L, int& nseg
   return VOXE_OK;
 }
 
-int fill_params(const VoxeGridDesc* g, const VoxeRenderDesc* r, int64_t R, bool backward, voxe::KParams& p, int& regcap) {
-  std::memset(&p, 0, sizeof(p));
-  p.R = (int)R;
-  p.S = r->num_samples;
+void fill_grid(const VoxeGridDesc* g, voxe::KParams& p) {
   p.X = g->dims[0];
   p.Y = g->dims[1];
   p.Z = g->dims[2];
@@ -143,9 +140,18 @@ int fill_params(const VoxeGridDesc* g, const VoxeRenderDesc* r, int64_t R, bool 
     p.ua[a] = (float)(0.5 * (double)g->norm_scale[a] * g->dims[a]);
     p.ub[a] = (float)(0.5 * (((double)g->norm_bias[a] + 1.0) * g->dims[a] - 1.0) + 1.0);  // +1: zero apron
   }
+  p.dscale = g->density_scale;
+  p.preact = g->preact;
+  p.postact = g->postact;
+}
+
+int fill_params(const VoxeGridDesc* g, const VoxeRenderDesc* r, int64_t R, bool backward, voxe::KParams& p, int& regcap) {
+  std::memset(&p, 0, sizeof(p));
+  fill_grid(g, p);
+  p.R = (int)R;
+  p.S = r->num_samples;
   p.near = r->near;
   p.far = r->far;
-  p.dscale = g->density_scale;
   p.noise_std = r->noise_std;
   p.rng_seed = r->rng_seed;
   p.rng_offset = r->rng_offset;
@@ -156,8 +162,6 @@ int fill_params(const VoxeGridDesc* g, const VoxeRenderDesc* r, int64_t R, bool 
   }
   p.lin_step = 1.0f / (float)(r->num_samples - 1);
   p.flags = r->flags;
-  p.preact = g->preact;
-  p.postact = g->postact;
   if (int rc = pick_shape(p.S, r->sh_degree, R, backward, p.L, p.nseg, p.rpc, regcap)) return rc;
   // CTA -> ray-group rotation (see ray_group in voxe_render.cu), off by default: on the benchmark frames the work per
   // group varies by +-8 % only and rotating the rounds changed nothing (profiles/r2_shape_sweeps.txt); kept as a tuning
@@ -294,6 +298,34 @@ int voxe_resample_grid(const float* grid_in, const int32_t in_dims[3], int32_t c
   if (e != cudaSuccess) return cuda_fail(e, "voxe_resample_grid launch");
   g_launches.fetch_add(1);
   return VOXE_OK;
+}
+
+static int query_points(const VoxeGridDesc* grid, const float* packed, const float* points, float* out, const float* g_out,
+                        float* packed_grad, int64_t n, voxe_stream_t stream, const char* what) {
+  if (int rc = check_grid(grid)) return rc;
+  if (n < 0) return fail(VOXE_ERR_INVALID_ARGUMENT, "%s: num_points must be >= 0", what);
+  if (n == 0) return VOXE_OK;
+  if (!packed || !points || (!out && !g_out) || (g_out && !packed_grad)) return fail(VOXE_ERR_INVALID_ARGUMENT, "%s: NULL buffer", what);
+  voxe::KParams p;
+  std::memset(&p, 0, sizeof(p));
+  fill_grid(grid, p);
+  p.grid = reinterpret_cast<const float4*>(packed);
+  p.grad = reinterpret_cast<float4*>(packed_grad);
+  cudaError_t e = voxe::launch_query_points(p, points, out, g_out, (long long)n, grid->channels / 4, grid->n_features, (cudaStream_t)stream);
+  if (e != cudaSuccess) return cuda_fail(e, what);
+  g_launches.fetch_add(1);
+  return VOXE_OK;
+}
+
+int voxe_query_points(const VoxeGridDesc* grid, const float* packed, const float* points, float* out, int64_t num_points,
+                      voxe_stream_t stream) {
+  return query_points(grid, packed, points, out, nullptr, nullptr, num_points, stream, "voxe_query_points");
+}
+
+int voxe_query_points_bwd(const VoxeGridDesc* grid, const float* packed, const float* points, const float* g_out,
+                          float* packed_grad, int64_t num_points, voxe_stream_t stream) {
+  if (!g_out) return fail(VOXE_ERR_INVALID_ARGUMENT, "voxe_query_points_bwd: NULL g_out");
+  return query_points(grid, packed, points, nullptr, g_out, packed_grad, num_points, stream, "voxe_query_points_bwd");
 }
 
 int voxe_tv_regularizer(const float* grid, const int32_t dims[3], int32_t channels, int32_t relu, double* workspace,

@@ -65,6 +65,10 @@ int64_t packed_bricks(const int dims[3]);  // 2x2x2 bricks of the packed volume 
 cudaError_t launch_resample_grid(const float* in, const int in_dims[3], int channels, float* out, const int out_dims[3],
                                  cudaStream_t stream);
 
+// stand-alone point queries (voxe_query.cu); g_out == nullptr: forward into `out`, else backward into p.grad
+cudaError_t launch_query_points(const KParams& p, const float* points, float* out, const float* g_out, long long n, int cv,
+                                int n_features, cudaStream_t stream);
+
 cudaError_t launch_adam_step(float* packed, float* packed_grad, float* packed_m, float* packed_v, float* densities,
                              float* features, const float* dense_gd, const float* dense_gf, const int dims[3], int n_features,
                              int channels, double lr, double beta1, double beta2, double eps, int step, cudaStream_t stream);

@@ -6,7 +6,8 @@ AABB, config dictionaries for checkpoints, ``test_inside_volume`` and the rescal
 
 What differs is where the arithmetic lives.  The reference's ``forward`` (voxels.py:287-342) runs two ``grid_sample``
 calls plus a full-grid ``densities * scale`` pass per call; here the grid only *describes* itself to the kernels
-(:meth:`fused_spec`, :meth:`packed_cache`) and the trilinear fetch happens inside ``voxe_render_fwd/bwd``.  Density
+(:meth:`fused_spec`, :meth:`packed_cache`) and the trilinear fetch happens inside ``voxe_render_fwd/bwd`` (or, for a stand-alone ``grid(points)`` query, inside
+``voxe_query_points``).  Density
 activations must therefore come from the closed set the kernels fuse -- pre in {Identity, abs}, post in {Identity,
 ReLU, Softplus(beta=1, threshold=20)} -- and feature activations must be Identity (true for every script in the
 reference); anything else raises ``NotImplementedError`` at render time rather than taking a slow path.
@@ -299,18 +300,30 @@ class VoxelGrid(Module):
             self._grad_accumulator.materialize(self.fused_spec(), self._densities, self._features)
 
     def forward(self, points: Tensor, viewdirs: Optional[Tensor] = None) -> Tensor:
-        """Point queries are not a separate operation here: sampling, interpolation and compositing are one kernel,
-        entered through ``render_sh_voxel_grid`` / ``VolumetricModel.render_rays``."""
-        raise NotImplementedError(
-            "VoxelGrid.forward(points) is fused into the ray-marching kernels of voxe_b200; render through "
-            "thre3d_atom.thre3d_reprs.renderers.render_sh_voxel_grid (no stand-alone point-query path is provided)"
-        )
+        """Features / radiance and density at ``points`` [N, 3] -> [N, F + 1] (voxels.py:287-345 upstream): one
+        ``voxe_query_points`` launch over the packed volume instead of two ``grid_sample`` calls and a full-grid
+        ``densities * scale`` pass.  The renderers do not come through here -- sampling, interpolation and compositing are
+        one kernel there -- this is the stand-alone query of the reference's API."""
+        from voxe_b200.render_function import query_points
+
+        out = query_points(self.fused_spec(), self._densities, self._features, points, cache=self._packed)
+        return self._with_radiance(out, viewdirs)
 
     def forward_attn(self, points: Tensor, viewdirs: Optional[Tensor] = None, orig_densities=False) -> Tensor:
-        raise NotImplementedError(
-            "VoxelGrid.forward_attn(points) is fused into the ray-marching kernels of voxe_b200; render through "
-            "thre3d_atom.thre3d_reprs.renderers.render_sh_voxel_grid_attn"
-        )
+        """[N, 2] = (interpolated attention value, density) at ``points`` (voxels.py:347-406 upstream); ``orig_densities``
+        reads the densities kept by ``update_orig_densities``."""
+        from voxe_b200.render_function import query_points
+
+        densities = self.orig_densities if orig_densities else self._densities
+        out = query_points(self.fused_spec(n_features=1), densities, self.attn, points, cache=self._packed_attn)
+        return self._with_radiance(out, viewdirs)
+
+    def _with_radiance(self, out: Tensor, viewdirs: Optional[Tensor]) -> Tensor:
+        if self._radiance_transfer_function is None or viewdirs is None:
+            return out
+        # voxels.py:336-340: a user-supplied callable (None in every script of the reference), applied to the features
+        radiance = self._radiance_transfer_function(out[:, :-1], viewdirs)
+        return torch.cat([radiance, out[:, -1:]], dim=-1)
 
 
 def _resample(tensor: Tensor, output_size: Tuple[int, int, int], mode: str) -> Tensor:

@@ -16,7 +16,7 @@ _lock = threading.Lock()
 _lib: Optional[ctypes.CDLL] = None
 
 # ---- enums of include/voxe.h -------------------------------------------------------------------------------
-ABI_VERSION = 12
+ABI_VERSION = 13
 PREACT_IDENTITY, PREACT_ABS = 0, 1
 POSTACT_IDENTITY, POSTACT_RELU, POSTACT_SOFTPLUS = 0, 1, 2
 FLAG_PERTURB, FLAG_AABB_SAMPLING, FLAG_DISPARITY_SAMPLING = 1, 2, 4
@@ -106,6 +106,8 @@ EXPORTS = {
     "voxe_render_infer": (ctypes.c_int, [_GD, _RD, _P, _P, _P, _P, _P, _P, _P, _P, ctypes.c_int64, ctypes.c_float, _P]),
     "voxe_render_bwd": (ctypes.c_int, [_GD, _RD, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, ctypes.c_int32, ctypes.c_int64, _P]),
     "voxe_resample_grid": (ctypes.c_int, [_P, ctypes.POINTER(ctypes.c_int32 * 3), ctypes.c_int32, _P, ctypes.POINTER(ctypes.c_int32 * 3), _P]),
+    "voxe_query_points": (ctypes.c_int, [ctypes.POINTER(VoxeGridDesc), _P, _P, _P, ctypes.c_int64, _P]),
+    "voxe_query_points_bwd": (ctypes.c_int, [ctypes.POINTER(VoxeGridDesc), _P, _P, _P, _P, ctypes.c_int64, _P]),
     "voxe_tv_regularizer": (ctypes.c_int, [_P, ctypes.POINTER(ctypes.c_int32 * 3), ctypes.c_int32, ctypes.c_int32, _P, _P, _P,
                                            ctypes.c_float, _P, ctypes.c_int32, _P]),
     "voxe_pair_loss": (ctypes.c_int, [_P, _P, ctypes.c_int64, ctypes.c_int32, _P, _P, _P, _P]),

@@ -440,3 +440,53 @@ def fused_render_attn(*args, **kwargs):
     """Attention-grid twin (renderers.py:108-163): same kernels with VOXE_FLAG_ATTN set in the render spec and the
     1-channel attention volume passed as ``features``."""
     return fused_render(*args, **kwargs)
+
+
+class _PointQuery(torch.autograd.Function):
+    """``voxe_query_points`` / ``voxe_query_points_bwd`` under autograd (differentiable w.r.t. the two grid tensors)."""
+
+    @staticmethod
+    def forward(ctx, densities: Tensor, features: Tensor, points: Tensor, gspec: FusedGridSpec, packed: Tensor) -> Tensor:
+        dev = densities.device
+        lib = nat.load_library()
+        n = points.shape[0]
+        out = torch.empty((n, gspec.n_features + 1), dtype=torch.float32, device=dev)
+        if n:
+            with torch.cuda.device(dev):
+                nat.check(lib.voxe_query_points(gspec.to_native(), packed.data_ptr(), points.data_ptr(), out.data_ptr(), n, _stream_ptr(dev)),
+                          "voxe_query_points")
+        # saved (not just referenced): a live graph must keep PackedVolumeCache from repacking this buffer in place
+        ctx.save_for_backward(points, packed)
+        ctx.gspec, ctx.shapes = gspec, (densities.shape, features.shape)
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out: Tensor):
+        points, packed = ctx.saved_tensors
+        gspec, (dshape, fshape) = ctx.gspec, ctx.shapes
+        dev = packed.device
+        lib = nat.load_library()
+        need_d, need_f = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        g_d = torch.empty(dshape, dtype=torch.float32, device=dev) if need_d else None
+        g_f = torch.empty(fshape, dtype=torch.float32, device=dev) if need_f else None
+        volume = torch.zeros_like(packed)
+        gd = gspec.to_native()
+        with torch.cuda.device(dev):
+            s = _stream_ptr(dev)
+            if points.shape[0]:
+                nat.check(lib.voxe_query_points_bwd(gd, packed.data_ptr(), points.data_ptr(), g_out.float().contiguous().data_ptr(),
+                                                    volume.data_ptr(), points.shape[0], s), "voxe_query_points_bwd")
+            nat.check(lib.voxe_unpack_grad(gd, volume.data_ptr(), _ptr(g_d), _ptr(g_f), 0, s), "voxe_unpack_grad")
+        return g_d, g_f, None, None, None
+
+
+def query_points(gspec: FusedGridSpec, densities: Tensor, features: Tensor, points: Tensor,
+                 cache: Optional[PackedVolumeCache] = None) -> Tensor:
+    """Stand-alone point query (voxels.py:287-345 upstream): ``[N, F + 1]`` = interpolated features and post-activated
+    interpolated density at ``points`` [N, 3] (world coordinates, anywhere: zeros padding, no inside mask)."""
+    assert points.dim() == 2 and points.shape[-1] == 3, f"points should be of shape [N x 3] as opposed to ({tuple(points.shape)})"
+    _require_cuda(densities, features)
+    if points.device != densities.device:
+        raise RuntimeError(f"all render inputs must live on one device (got {points.device} and {densities.device})")
+    packed = (cache or PackedVolumeCache()).get(gspec, densities, features)
+    return _PointQuery.apply(densities, features, points.detach().float().contiguous(), gspec, packed)
