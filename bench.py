@@ -385,7 +385,7 @@ class DeviceBench:
     N_GRID_COPIES = 3  # rotating copies: 3 x 65.5 MB of grid + 65.5 MB of gradients >> 126 MB L2
 
     def __init__(self, device, rank, world, count_s_in=True, n_lanes=1, kernel_jitter=True, postact=None, peer_volume=None,
-                 share=None):
+                 share=None, sparse=False):
         from voxe_b200 import _native as nat
         from voxe_b200.render_function import FusedGridSpec, FusedRenderSpec, pack_volume
 
@@ -415,6 +415,17 @@ class DeviceBench:
             self.peer_volume = None
             self.packed_grad = torch.zeros_like(self.packed[0])
         self.d_dens, self.d_feat = (share.d_dens, share.d_feat) if share is not None else (torch.empty_like(dens), torch.empty_like(feat))
+        # sparse hand-over: the backward leaves a trail of brick flags; the step's exchange (N > 1) and the conversion into
+        # dense gradients follow it instead of sweeping the whole volume (voxe_allreduce_grads_peer_sparse, voxe_consume_grad)
+        self.sparse, self.tag = bool(sparse), 1
+        if share is not None:
+            self.sparse, self.touched = share.sparse, share.touched
+        elif not self.sparse:
+            self.touched = None
+        elif self.peer_volume is not None:
+            self.touched = self.peer_volume.enable_sparse(self.gspec)
+        else:
+            self.touched = torch.zeros(int(self.lib.voxe_touched_bytes(self.gd)), dtype=torch.uint8, device=device)
         if WL.get("random_views"):
             # cfg 4 as BASELINE.json states it: `random_views` poses from get_random_pose after np.random.seed(42)
             # (utils/imaging_utils.py:197-215 upstream), dealt round-robin over the ranks
@@ -485,20 +496,29 @@ class DeviceBench:
         self.nat.check(self.lib.voxe_render_bwd(
             self.gd, self.rd, self.packed[copy].data_ptr(), o[b0:b1].data_ptr(), d[b0:b1].data_ptr(),
             self._jitter_arg(pose, b0), None, saved.data_ptr(), self.G[b0:b1].data_ptr(), None, None, None,
-            self.packed_grad.data_ptr(), None, 0, b1 - b0, self._stream()), "voxe_render_bwd")
+            self.packed_grad.data_ptr(), self.touched.data_ptr() if self.sparse else None, self.tag if self.sparse else 0, b1 - b0,
+            self._stream()), "voxe_render_bwd")
 
     def scatter_stats(self, pose=0):
         """(in-grid samples the backward processed, samples whose 8-corner scatter it issued) for one frame, counted by the
         kernel itself (VoxeRenderDesc.stats); run once, eagerly, outside every timed region."""
         counters = torch.zeros(4, dtype=torch.int64, device=self.device)
         self.rd.stats = counters.data_ptr()
+        n_bricks = int(self.lib.voxe_touched_bytes(self.gd))
+        keep = (self.sparse, self.touched)
+        if not self.sparse:  # a private trail, just to count the bricks a frame touches
+            self.sparse, self.touched = True, torch.zeros(n_bricks, dtype=torch.uint8, device=self.device)
+        else:
+            self.touched.zero_()
         try:
             for b0, b1 in self.batches:
                 self._fwd(pose, 0, b0, b1, self.saved)
                 self._bwd(pose, 0, b0, b1, self.saved)
             torch.cuda.synchronize(self.device)
+            self.touched_fraction = round(float((self.touched[:n_bricks] == self.tag).float().mean()), 4)
         finally:
             self.rd.stats = None
+            self.sparse, self.touched = keep
         self.packed_grad.zero_()
         n_in, n_scatter, cell_leaders, corner_leaders = (int(v) for v in counters.tolist())
         # intra-warp duplicates among the scattering lanes of a warp instruction (8 neighbouring rays x 4 depth ranges)
@@ -508,6 +528,11 @@ class DeviceBench:
         return n_in, n_scatter
 
     def unpack(self):
+        """Packed gradient volume -> dense d_densities / d_features (the reference's layout)."""
+        if self.sparse:  # only the flagged bricks; what is read is zeroed, so the packed volume is all-zero again afterwards
+            self.nat.check(self.lib.voxe_consume_grad(self.gd, self.packed_grad.data_ptr(), self.d_dens.data_ptr(), self.d_feat.data_ptr(),
+                                                      self.touched.data_ptr(), self.tag, self._stream()), "voxe_consume_grad")
+            return
         self.nat.check(self.lib.voxe_unpack_grad(self.gd, self.packed_grad.data_ptr(), self.d_dens.data_ptr(), self.d_feat.data_ptr(), 0,
                                                  self._stream()), "voxe_unpack_grad")
 
@@ -529,7 +554,11 @@ class DeviceBench:
                     self._bwd(pose, copy, b0, b1, saved)
             return
         draw = WL["perturb"] and refresh_jitter and not self.kernel_jitter
-        if zero:  # one zero-fill per optimiser step (cfg 4 accumulates all of a rank's views before its one all-reduce)
+        if zero and self.sparse:  # fresh dense gradients and a fresh trail; the packed volume was left all-zero by the consume
+            self.d_dens.zero_()
+            self.d_feat.zero_()
+            self.touched.zero_()
+        elif zero:  # one zero-fill per optimiser step (cfg 4 accumulates all of a rank's views before its one all-reduce)
             self.packed_grad.zero_()
         n = self.n_lanes
         lanes = [main] + self.lane_streams[: n - 1]
@@ -1200,6 +1229,58 @@ def run_check(args):
                 del vol
             except Exception as exc:  # noqa: BLE001
                 results[name] = {"error": str(exc)[:300]}
+        # (a') the brick-wise exchange: a PART of the frame (so most bricks stay untouched), each rank's share rendered with
+        # brick flags straight into the peer volume; three rounds with fresh tags over flags that are never cleared; then the
+        # flag-guided hand-over into dense gradients, against the unpacked volume of the unsharded render
+        part = bench.batches[: max(world, len(bench.batches) // 6)]
+        full_part = render(part)
+        want_d, want_f = torch.empty_like(bench.d_dens), torch.empty_like(bench.d_feat)
+        nat.check(lib.voxe_unpack_grad(bench.gd, full_part.data_ptr(), want_d.data_ptr(), want_f.data_ptr(), 0, bench._stream()), "voxe_unpack_grad")
+        for name, multicast in (("voxe_allreduce_grads_peer_sparse (multimem)", True), ("voxe_allreduce_grads_peer_sparse (peer loads/stores)", False)):
+            keep = (bench.packed_grad, bench.sparse, bench.touched, bench.tag)
+            try:
+                vol = PeerGradVolume(full.numel(), device, multicast=multicast)
+                if multicast and not vol.multicast:
+                    results[name] = {"skipped": "no multicast mapping on this box"}
+                    continue
+                bench.packed_grad, bench.sparse, bench.touched = vol.buffer, True, vol.enable_sparse(bench.gspec)
+                for tag in (1, 2, 3):
+                    bench.tag = tag
+                    render(part[rank::world])  # zero-fills the volume first; leaves this rank's share and its flags
+                    dist.barrier()
+                    vol.allreduce_sparse(tag)
+                    torch.cuda.synchronize(device)
+                assert not vol.failed(), "a peer did not arrive"
+                err = float((vol.buffer - full_part).abs().max()) / scale
+                n_bricks = int(lib.voxe_touched_bytes(bench.gd))
+                frac = float((bench.touched[:n_bricks] == bench.tag).float().mean())
+                bench.d_dens.zero_()
+                bench.d_feat.zero_()
+                bench.unpack()  # voxe_consume_grad along the union of the flags
+                torch.cuda.synchronize(device)
+                err = max(err, float((bench.d_dens - want_d).abs().max()) / scale, float((bench.d_feat - want_f).abs().max()) / scale)
+                left = float(vol.buffer.abs().max())
+                t = torch.tensor([err, left], device=device)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                results[name] = {"max_abs_over_inf": float(t[0]), "volume_left_after_hand_over": float(t[1]), "ok": float(t[0]) <= 1e-5 and float(t[1]) == 0.0,
+                                 "flagged_brick_fraction_after_union": round(frac, 4), "frame_part": f"{len(part)} of {len(bench.batches)} batches"}
+                render(part[rank::world])
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                dist.barrier()
+                torch.cuda.synchronize(device)
+                e0.record()
+                for _ in range(10):
+                    vol.allreduce_sparse(bench.tag)
+                e1.record()
+                torch.cuda.synchronize(device)
+                results[name]["us"] = round(1e3 * e0.elapsed_time(e1) / 10, 1)
+                if rank == 0:
+                    print(f"[check] {name}: {results[name]}", file=sys.stderr, flush=True)
+                del vol
+            except Exception as exc:  # noqa: BLE001
+                results[name] = {"error": str(exc)[:300]}
+            finally:
+                bench.packed_grad, bench.sparse, bench.touched, bench.tag = keep
         # (b) the C ABI's NCCL entry point on its own communicator
         try:
             import ctypes
@@ -1351,8 +1432,13 @@ def run_ours(args):
     if world > 1 and peer_factory is None:
         collective = "ncclAllReduce via torch.distributed"
 
+    handover = args.handover or ("sparse" if args.workload == "cfg5" else "dense")
+    if handover == "sparse" and world > 1 and peer_factory is None:
+        handover = "dense"  # the brick-wise exchange is the library's own kernel; ncclAllReduce takes the whole volume
     bench = DeviceBench(device, rank, world, count_s_in=not (args.ncu or args.sweep), n_lanes=args.lanes,
-                        kernel_jitter=args.jitter == "kernel", peer_volume=peer_factory)
+                        kernel_jitter=args.jitter == "kernel", peer_volume=peer_factory, sparse=handover == "sparse")
+    if bench.sparse and world > 1:
+        collective = collective.replace("voxe_allreduce_grads_peer", "voxe_allreduce_grads_peer_sparse")
     barrier = (lambda: dist.barrier()) if world > 1 else None
 
     if args.ncu:  # profiler mode: eager launches of whole frames, nothing else (numbers printed here are NOT bench values)
@@ -1369,7 +1455,9 @@ def run_ours(args):
 
     def allreduce():
         if world > 1:
-            if bench.peer_volume is not None:
+            if bench.peer_volume is not None and bench.sparse:
+                bench.peer_volume.allreduce_sparse(bench.tag)  # flag union, then only the bricks some rank touched
+            elif bench.peer_volume is not None:
                 bench.peer_volume.allreduce()   # ONE all-reduce of the packed voxel gradients per step: the library's kernel
             else:
                 dist.all_reduce(bench.packed_grad)
@@ -1457,6 +1545,34 @@ def run_ours(args):
         parity = parity_of_timed_leg(bench, last, last % bench.N_GRID_COPIES, world)
     if world > 1:
         dist.barrier()
+
+    # where a step of the sparse hand-over spends its time: the stages of the last frames again, one at a time (every rank
+    # takes part in the exchange; rank 0 reports)
+    breakdown = None
+    if bench.sparse:
+        stages = {"zero_dense_grads_and_flags": [], "fwd_bwd": [], "allreduce_sparse": [], "consume": []}
+        for rep in range(3):
+            pose = (last + rep) % len(bench.poses)
+            marks = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+            if barrier:
+                barrier()
+            torch.cuda.synchronize(device)
+            marks[0].record()
+            bench.d_dens.zero_()
+            bench.d_feat.zero_()
+            bench.touched.zero_()
+            marks[1].record()
+            bench.frame_body(pose, 0, "both", zero=False)
+            marks[2].record()
+            allreduce()
+            marks[3].record()
+            bench.unpack()
+            marks[4].record()
+            torch.cuda.synchronize(device)
+            for name, a, b in zip(stages, marks[:-1], marks[1:]):
+                stages[name].append(a.elapsed_time(b))
+        breakdown = {k: round(1e3 * min(v), 1) for k, v in stages.items()}
+        breakdown["unit"] = "us, best of 3 eager passes on rank 0 (allreduce_sparse includes waiting for the slowest rank's backward)"
 
     # the same frame on a Softplus field (the reference scripts' default): every in-grid sample scatters
     softplus = None
@@ -1622,8 +1738,10 @@ def run_ours(args):
                     "+ unpack; total work fixed as N grows")
         else:
             step = (f"one {WL['height']}x{WL['width']} frame = {len(bench.batches)} batches x (fwd, bwd; jitter "
-                    f"{'generated in-kernel' if bench.kernel_jitter else 'drawn by torch.rand'}) + grad zero-fill + unpack"
-                    + (f" + 1 all-reduce of the packed voxel grads ({bench.packed_grad.numel() * 4 / 1e6:.0f} MB)" if world > 1 else ""))
+                    f"{'generated in-kernel' if bench.kernel_jitter else 'drawn by torch.rand'})"
+                    + (" + zero-fill of the dense gradients + brick-flag hand-over (voxe_consume_grad)" if bench.sparse else " + grad zero-fill + unpack")
+                    + ((f" + brick-wise all-reduce of the packed voxel grads (flag union, then the touched bricks of {bench.packed_grad.numel() * 4 / 1e6:.0f} MB)"
+                        if bench.sparse else f" + 1 all-reduce of the packed voxel grads ({bench.packed_grad.numel() * 4 / 1e6:.0f} MB)") if world > 1 else ""))
         line = {
             "metric": "rays/s fwd+bwd, 160^3 SH-0 grid, 400x400 render", "value": rays_per_s, "unit": "rays/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
@@ -1636,6 +1754,9 @@ def run_ours(args):
                              f"{bench.packed_grad.numel() * 4 / 1e6:.0f} MB gradient volume + per-batch workspaces > 126 MB L2; {len(bench.poses)} poses rotate",
                        "parallelism": f"ray/view data parallel x{world}", "timing": "CUDA events around K graph replays, max over ranks",
                        "collective": None if world == 1 else collective,
+                       "gradient_handover": "sparse (brick flags)" if bench.sparse else "dense",
+                       "touched_brick_fraction": getattr(bench, "touched_fraction", None),
+                       "step_breakdown": breakdown,
                        "host_cpus_per_rank": len(pinned_cpus) if pinned_cpus else "unpinned"},
             "e2e": e2e, "gpu_launches": args.steps * ((bench.kernels_per_step - 1) * (len(graphs) if random_views else 1) + 1
                                                          + (1 if bench.peer_volume is not None else 0)), "roofline": roof,
@@ -1684,6 +1805,9 @@ def main():
     ap.add_argument("--collective", choices=["peer", "peer-p2p", "nccl"], default="peer",
                     help="N > 1: voxe_allreduce_grads_peer on a peer-mapped gradient volume (multimem when the box has NVLS; peer-p2p "
                          "forces plain peer loads/stores), or ncclAllReduce through torch.distributed")
+    ap.add_argument("--handover", choices=["dense", "sparse"], default="",
+                    help="gradient hand-over of the device leg: 'dense' = zero-fill + whole-volume all-reduce + unpack; 'sparse' = follow the "
+                         "backward's brick flags (default for cfg5, whose batch touches a few percent of a 15 GB volume)")
     ap.add_argument("--lanes", type=int, default=3, help="ray batches in flight within a frame (streams)")
     ap.add_argument("--jitter", choices=["kernel", "buffer"], default="kernel",
                     help="stratified jitter of the device leg: generated inside the kernels (counter-based hash) or torch-drawn [R,S] buffers")

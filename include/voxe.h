@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define VOXE_ABI_VERSION 13
+#define VOXE_ABI_VERSION 14
 
 #if defined(__GNUC__)
 #define VOXE_API __attribute__((visibility("default")))
@@ -334,6 +334,18 @@ typedef struct VoxePeerDesc {
                              /* loads / stores (the two are bound by different resources); 0 or 8: all (with `multicast`) */
 } VoxePeerDesc;
 VOXE_API int voxe_allreduce_grads_peer(const VoxePeerDesc* peers, int64_t n_floats, uint32_t* fail_flag, voxe_stream_t stream);
+
+/* voxe_allreduce_grads_peer_sparse: the same exchange restricted to the 2x2x2 bricks that SOME rank's backward touched in
+ * this step -- for volumes of which a step writes a small part (a 65 536-ray batch through a 512^3 SH-2 grid touches a few
+ * percent of 15 GB).  `peers->buffers` are the ranks' PACKED gradient volumes of `grid` (voxe_packed_floats floats each);
+ * `touched_peers[k]` is rank k's flag array as written by voxe_render_bwd(..., touched, touch_tag, ...), peer-mapped like the
+ * volumes, 16-byte aligned and voxe_peer_touched_bytes(grid) long (voxe_touched_bytes rounded up to whole 16-byte vectors,
+ * the padding zeroed once).  Two launches on `stream`: the flag arrays are all-reduced with "some rank carries the tag"
+ * as the operator (afterwards every rank's array holds the union, so voxe_consume_grad(..., touched, touch_tag) visits
+ * exactly the bricks that hold sums), then the tagged bricks are summed over the ranks in place.  Same tag on every rank. */
+VOXE_API int64_t voxe_peer_touched_bytes(const VoxeGridDesc* grid);
+VOXE_API int voxe_allreduce_grads_peer_sparse(const VoxePeerDesc* peers, const VoxeGridDesc* grid, uint8_t* const* touched_peers,
+                                              int32_t touch_tag, uint32_t* fail_flag, voxe_stream_t stream);
 
 /* voxe_allreduce_grads: ncclAllReduce(SUM, fp32, in place) of `buf` on `nccl_comm` (an ncclComm_t) -- for hosts whose
  * volumes are not peer-mapped.  libnccl.so.2 is opened at run time (no link-time dependency); the helpers below build a

@@ -87,6 +87,8 @@ def test_argument_validation_without_a_gpu():
     peers.rank = 0
     assert lib.voxe_allreduce_grads_peer(peers, 1024, None, None) == 1 and b"NULL buffer" in lib.voxe_last_error()
     assert lib.voxe_allreduce_grads_peer(peers, 1022, None, None) == 1 and b"multiple of 4" in lib.voxe_last_error()
+    assert lib.voxe_allreduce_grads_peer_sparse(peers, gd, None, 0, None, None) == 1 and b"NULL buffer" in lib.voxe_last_error()
+    assert lib.voxe_peer_touched_bytes(gd) == 128 and lib.voxe_query_points(gd, None, None, None, 8, None) == 1
     assert lib.voxe_allreduce_grads(None, None, 16, None) == 1
     assert lib.voxe_touched_bytes(gd) == 5 * 5 * 5 and lib.voxe_consume_grad(gd, None, None, None, None, 0, None) == 1
     dims_in, dims_out = (ctypes.c_int32 * 3)(4, 4, 4), (ctypes.c_int32 * 3)(0, 4, 4)

@@ -116,7 +116,7 @@ def _scene(deg=0, dims=(24, 20, 28), n_rays=777, S=64, perturb=False, post=None,
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("deg", [0, 2])
+@pytest.mark.parametrize("deg", [0, 1, 2, 3])
 def test_touched_brick_consume_equals_the_dense_consume(deg):
     """C ABI: backward with flags + consume over flagged bricks == backward + consume over the whole volume, for several
     batches through ONE flag array (so later calls see the stale tags of earlier ones), and the volume is all-zero after."""

@@ -372,20 +372,44 @@ int voxe_pair_loss_grad(const float* a, const float* b, int64_t n, int32_t mode,
   return VOXE_OK;
 }
 
-int voxe_allreduce_grads_peer(const VoxePeerDesc* peers, int64_t n_floats, uint32_t* fail_flag, voxe_stream_t stream) {
-  if (!peers) return fail(VOXE_ERR_INVALID_ARGUMENT, "voxe_allreduce_grads_peer: NULL descriptor");
+static int check_peers(const VoxePeerDesc* peers, int64_t n_floats, const char* what) {
+  if (!peers) return fail(VOXE_ERR_INVALID_ARGUMENT, "%s: NULL descriptor", what);
   if (peers->world_size < 1 || peers->world_size > VOXE_MAX_PEERS || peers->rank < 0 || peers->rank >= peers->world_size)
-    return fail(VOXE_ERR_INVALID_ARGUMENT, "voxe_allreduce_grads_peer: world_size must be in 1..%d and rank inside it", VOXE_MAX_PEERS);
-  if (n_floats < 0 || (n_floats & 3)) return fail(VOXE_ERR_INVALID_ARGUMENT, "voxe_allreduce_grads_peer: n_floats must be a multiple of 4");
+    return fail(VOXE_ERR_INVALID_ARGUMENT, "%s: world_size must be in 1..%d and rank inside it", what, VOXE_MAX_PEERS);
+  if (n_floats < 0 || (n_floats & 3)) return fail(VOXE_ERR_INVALID_ARGUMENT, "%s: n_floats must be a multiple of 4", what);
   for (int k = 0; k < peers->world_size; ++k) {
-    if (!peers->buffers[k] || !peers->signals[k]) return fail(VOXE_ERR_INVALID_ARGUMENT, "voxe_allreduce_grads_peer: NULL buffer / signal pad of rank %d", k);
-    if (reinterpret_cast<uintptr_t>(peers->buffers[k]) & 15) return fail(VOXE_ERR_INVALID_ARGUMENT, "voxe_allreduce_grads_peer: buffers must be 16-byte aligned");
+    if (!peers->buffers[k] || !peers->signals[k]) return fail(VOXE_ERR_INVALID_ARGUMENT, "%s: NULL buffer / signal pad of rank %d", what, k);
+    if (reinterpret_cast<uintptr_t>(peers->buffers[k]) & 15) return fail(VOXE_ERR_INVALID_ARGUMENT, "%s: buffers must be 16-byte aligned", what);
   }
-  if (reinterpret_cast<uintptr_t>(peers->multicast) & 15) return fail(VOXE_ERR_INVALID_ARGUMENT, "voxe_allreduce_grads_peer: multicast mapping must be 16-byte aligned");
+  if (reinterpret_cast<uintptr_t>(peers->multicast) & 15) return fail(VOXE_ERR_INVALID_ARGUMENT, "%s: multicast mapping must be 16-byte aligned", what);
+  return VOXE_OK;
+}
+
+int voxe_allreduce_grads_peer(const VoxePeerDesc* peers, int64_t n_floats, uint32_t* fail_flag, voxe_stream_t stream) {
+  if (int rc = check_peers(peers, n_floats, "voxe_allreduce_grads_peer")) return rc;
   if (n_floats == 0 || peers->world_size == 1) return VOXE_OK;
   cudaError_t e = voxe::launch_allreduce_peer(*peers, n_floats, fail_flag, (cudaStream_t)stream);
   if (e != cudaSuccess) return cuda_fail(e, "voxe_allreduce_grads_peer launch");
   g_launches.fetch_add(1);
+  return VOXE_OK;
+}
+
+int64_t voxe_peer_touched_bytes(const VoxeGridDesc* grid) { return (voxe_touched_bytes(grid) + 15) / 16 * 16; }
+
+int voxe_allreduce_grads_peer_sparse(const VoxePeerDesc* peers, const VoxeGridDesc* grid, uint8_t* const* touched_peers,
+                                     int32_t touch_tag, uint32_t* fail_flag, voxe_stream_t stream) {
+  const char* what = "voxe_allreduce_grads_peer_sparse";
+  if (int rc = check_peers(peers, 0, what)) return rc;
+  if (int rc = check_grid(grid)) return rc;
+  if (touch_tag < 1 || touch_tag > 255) return fail(VOXE_ERR_INVALID_ARGUMENT, "%s: touch_tag must be in 1..255", what);
+  if (!touched_peers) return fail(VOXE_ERR_INVALID_ARGUMENT, "%s: NULL touched_peers", what);
+  for (int k = 0; k < peers->world_size; ++k)
+    if (!touched_peers[k] || (reinterpret_cast<uintptr_t>(touched_peers[k]) & 15))
+      return fail(VOXE_ERR_INVALID_ARGUMENT, "%s: flag array of rank %d is NULL or not 16-byte aligned", what, k);
+  if (peers->world_size == 1) return VOXE_OK;
+  cudaError_t e = voxe::launch_allreduce_peer_sparse(*peers, touched_peers, touch_tag, grid->dims, grid->channels, fail_flag, (cudaStream_t)stream);
+  if (e != cudaSuccess) return cuda_fail(e, "voxe_allreduce_grads_peer_sparse launch");
+  g_launches.fetch_add(2);
   return VOXE_OK;
 }
 

@@ -149,6 +149,154 @@ __global__ void __launch_bounds__(kThreads, 1) allreduce_peer_kernel(const __gri
   if (!ok && threadIdx.x == 0 && fail_flag != nullptr) atomicOr(fail_flag, 1u);
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Sparse variant: exchange only the 2x2x2 bricks some rank's backward touched.
+//
+// A 65 536-ray batch through a 512^3 SH-2 grid (cfg 5) writes a few percent of a 15 GB gradient volume; reducing the
+// whole volume costs ~40 ms at N = 8, several times the render itself.  The backward kernels leave a trail -- one byte
+// per brick, `tag` where a sample's corner 0 fell (voxe_render_bwd) -- so the exchange can follow it:
+//   kernel A (flags_union_kernel): an all-reduce of the FLAG arrays with "some rank has the tag" as the operator: rank r
+//     owns the r-th part of every CTA's slice, reads that part of every rank's flags (16 flags per load), and stores the
+//     union into every rank's array.  17.6 MB at 512^3.  Same per-CTA barriers as the dense kernel; because CTA b leaves
+//     only when CTA b of every peer has stored, the kernel's completion on a rank implies every peer's stores have landed.
+//   kernel B (allreduce_sparse_kernel): walks the bricks in tiles of 32 (one lane per brick), dealt round-robin over the
+//     ranks and then over the CTAs and warps -- a batch's trail is a slab of the volume, so contiguous ownership would leave
+//     most CTAs idle.  A lane tests its brick against the dilated union (a brick holds gradients if one of the 8 flags at
+//     (bx-dx, by-dy, bz-dz) carries the tag: a sample's corners reach one brick further in +x, +y, +z), the warp ballots,
+//     and all lanes together reduce the tagged bricks' vectors (multimem.ld_reduce + multimem.st, or peer loads / stores).
+// Afterwards every rank's flags hold the union, so its voxe_consume_grad visits exactly the bricks that now hold sums.
+struct SparseParams {
+  PeerParams base;
+  unsigned char* touched[kMaxPeers];
+  unsigned tagword;       // the tag in all four bytes
+  unsigned n_bricks;
+  long long n_flag_vec;   // 16-flag vectors (the arrays are padded to whole vectors)
+  int BY, BZ;
+  int vec_per_brick;      // 8 * CV
+};
+
+__device__ __forceinline__ uint4 ld_peer_u4(const uint4* p) {
+  uint4 v;
+  asm volatile("ld.global.relaxed.sys.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_peer_u4(uint4* p, const uint4& v) {
+  asm volatile("st.global.relaxed.sys.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+// bytes of `mine` replaced by the tag wherever the same byte of `theirs` is the tag
+__device__ __forceinline__ unsigned merge_tag(unsigned mine, unsigned theirs, unsigned tagword) {
+  const unsigned m = __vcmpeq4(theirs, tagword);
+  return (mine & ~m) | (tagword & m);
+}
+
+__global__ void __launch_bounds__(kThreads, 1) flags_union_kernel(const __grid_constant__ SparseParams p, unsigned* fail_flag) {
+  __shared__ unsigned s_fail;
+  if (threadIdx.x == 0) s_fail = 0u;
+  const long long per_cta = (p.n_flag_vec + gridDim.x - 1) / gridDim.x;
+  const long long c0 = blockIdx.x * per_cta, c1 = min(c0 + per_cta, p.n_flag_vec);
+  const long long per_rank = (max(c1 - c0, 0LL) + p.base.world - 1) / p.base.world;
+  const long long r0 = min(c0 + p.base.rank * per_rank, c1), r1 = min(r0 + per_rank, c1);
+  bool ok = peer_barrier(p.base, 0, &s_fail);  // the peers' backward kernels have finished
+  if (ok) {
+    for (long long i = r0 + threadIdx.x; i < r1; i += kThreads) {
+      uint4 u = ld_peer_u4(reinterpret_cast<const uint4*>(p.touched[p.base.rank]) + i);
+      for (int k = 0; k < p.base.world; ++k) {
+        if (k == p.base.rank) continue;
+        const uint4 v = ld_peer_u4(reinterpret_cast<const uint4*>(p.touched[k]) + i);
+        u.x = merge_tag(u.x, v.x, p.tagword);
+        u.y = merge_tag(u.y, v.y, p.tagword);
+        u.z = merge_tag(u.z, v.z, p.tagword);
+        u.w = merge_tag(u.w, v.w, p.tagword);
+      }
+      // a byte that is not the tag carries this rank's stale value to the peers: any value but the tag means the same
+      for (int k = 0; k < p.base.world; ++k) st_peer_u4(reinterpret_cast<uint4*>(p.touched[(p.base.rank + k) % p.base.world]) + i, u);
+    }
+    ok = peer_barrier(p.base, 1, &s_fail);
+  }
+  if (!ok && threadIdx.x == 0 && fail_flag != nullptr) atomicOr(fail_flag, 1u);
+}
+
+__device__ __forceinline__ unsigned char ld_flag(const unsigned char* p) {  // written by the peers during the previous kernel
+  unsigned v;
+  asm volatile("ld.global.relaxed.gpu.u8 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return (unsigned char)v;
+}
+
+__global__ void __launch_bounds__(kThreads, 1) allreduce_sparse_kernel(const __grid_constant__ SparseParams p, unsigned* fail_flag) {
+  __shared__ unsigned s_fail;
+  if (threadIdx.x == 0) s_fail = 0u;
+  __syncthreads();
+  const bool MULTICAST = p.base.mc != nullptr;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = kThreads / 32;
+  const unsigned char* flags = p.touched[p.base.rank];
+  const unsigned char want = (unsigned char)(p.tagword & 0xffu);
+  const unsigned n_tiles = (p.n_bricks + 31u) / 32u;
+  const int vpb = p.vec_per_brick;
+  // tile t belongs to rank t % world; a rank's tiles are dealt over its CTAs, then over the warps of a CTA
+  for (unsigned long long q = (unsigned long long)blockIdx.x + (unsigned long long)gridDim.x * warp;; q += (unsigned long long)gridDim.x * n_warps) {
+    const unsigned long long t = q * p.base.world + p.base.rank;
+    if (t >= n_tiles) break;
+    const unsigned brick = (unsigned)t * 32u + lane;
+    bool any = false;
+    if (brick < p.n_bricks) {
+      const unsigned bz = brick % (unsigned)p.BZ, r = brick / (unsigned)p.BZ;
+      const unsigned by = r % (unsigned)p.BY, bx = r / (unsigned)p.BY;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const unsigned dx = k >> 2, dy = (k >> 1) & 1, dz = k & 1;
+        if (bx >= dx && by >= dy && bz >= dz) any |= ld_flag(flags + ((bx - dx) * (unsigned)p.BY + (by - dy)) * (unsigned)p.BZ + (bz - dz)) == want;
+      }
+    }
+    const unsigned mask = __ballot_sync(0xffffffffu, any);
+    const int n = __popc(mask) * vpb;  // vectors of this tile's tagged bricks, shared out over the lanes
+    const long long tile0 = (long long)t * 32 * vpb;
+    constexpr int U = 4;
+    for (int i0 = lane; i0 < n; i0 += 32 * U) {
+      long long off[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int id = i0 + 32 * u;
+        if (id < n) {
+          const int j = id / vpb;
+          off[u] = tile0 + (long long)__fns(mask, 0u, j + 1) * vpb + (id - j * vpb);
+        } else {
+          off[u] = -1;
+        }
+      }
+      float4 acc[U];
+      if (MULTICAST) {
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+          if (off[u] >= 0) acc[u] = multimem_ld_reduce(p.base.mc + off[u]);
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+          if (off[u] >= 0) multimem_st(p.base.mc + off[u], acc[u]);
+      } else {
+#pragma unroll
+        for (int u = 0; u < U; ++u) acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int k = 0; k < p.base.world; ++k) {  // fixed rank order: the same sum on every rank and run
+          float4 v[U];
+#pragma unroll
+          for (int u = 0; u < U; ++u)
+            if (off[u] >= 0) v[u] = ld_peer(p.base.buf[k] + off[u]);
+#pragma unroll
+          for (int u = 0; u < U; ++u)
+            if (off[u] >= 0) { acc[u].x += v[u].x; acc[u].y += v[u].y; acc[u].z += v[u].z; acc[u].w += v[u].w; }
+        }
+        for (int k = 0; k < p.base.world; ++k) {
+          const int dst = (p.base.rank + k) % p.base.world;
+#pragma unroll
+          for (int u = 0; u < U; ++u)
+            if (off[u] >= 0) st_peer(p.base.buf[dst] + off[u], acc[u]);
+        }
+      }
+    }
+  }
+  // every rank has written its tiles into every volume (the peers' backward kernels were awaited by kernel A)
+  const bool ok = peer_barrier(p.base, 1, &s_fail);
+  if (!ok && threadIdx.x == 0 && fail_flag != nullptr) atomicOr(fail_flag, 1u);
+}
+
 }  // namespace
 
 cudaError_t launch_allreduce_peer(const VoxePeerDesc& d, int64_t n_floats, unsigned* fail_flag, cudaStream_t stream) {
@@ -172,6 +320,38 @@ cudaError_t launch_allreduce_peer(const VoxePeerDesc& d, int64_t n_floats, unsig
   const int blocks = (int)(want < 1 ? 1 : (want > block_cap ? block_cap : want));
   p.mc_share = p.mc == nullptr ? 0 : (d.multicast_share >= 1 && d.multicast_share <= 8 ? d.multicast_share : 8);
   allreduce_peer_kernel<<<blocks, kThreads, 0, stream>>>(p, fail_flag);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_allreduce_peer_sparse(const VoxePeerDesc& d, unsigned char* const* touched_peers, int tag, const int dims[3],
+                                         int channels, unsigned* fail_flag, cudaStream_t stream) {
+  SparseParams p{};
+  p.base.world = d.world_size;
+  p.base.rank = d.rank;
+  for (int k = 0; k < d.world_size; ++k) {
+    p.base.buf[k] = reinterpret_cast<float4*>(d.buffers[k]);
+    p.base.sig[k] = d.signals[k];
+    p.touched[k] = touched_peers[k];
+  }
+  p.base.mc = reinterpret_cast<float4*>(d.multicast);
+  p.base.mc_share = p.base.mc ? 8 : 0;
+  const int64_t bricks = packed_bricks(dims);
+  p.n_bricks = (unsigned)bricks;
+  p.n_flag_vec = (bricks + 15) / 16;
+  p.BY = (dims[1] + 3) / 2;
+  p.BZ = (dims[2] + 3) / 2;
+  p.vec_per_brick = 8 * (channels / 4);
+  p.base.n_vec = bricks * p.vec_per_brick;
+  p.tagword = (unsigned)(tag & 0xff) * 0x01010101u;
+  const long long want_a = (p.n_flag_vec + kThreads * 4 - 1) / (kThreads * 4);
+  const int blocks_a = (int)(want_a < 1 ? 1 : (want_a > kBlocks ? kBlocks : want_a));
+  flags_union_kernel<<<blocks_a, kThreads, 0, stream>>>(p, fail_flag);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  const long long tiles_per_rank = ((bricks + 31) / 32 + d.world_size - 1) / d.world_size;
+  const long long want_b = (tiles_per_rank + (kThreads / 32) - 1) / (kThreads / 32);
+  const int blocks_b = (int)(want_b < 1 ? 1 : (want_b > kBlocks ? kBlocks : want_b));
+  allreduce_sparse_kernel<<<blocks_b, kThreads, 0, stream>>>(p, fail_flag);
   return cudaGetLastError();
 }
 

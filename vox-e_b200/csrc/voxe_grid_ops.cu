@@ -159,6 +159,77 @@ __global__ void __launch_bounds__(256) consume_touched_kernel(float4* __restrict
   }
 }
 
+// Multi-vector voxels (SH degree >= 1: a brick is 8 * CV vectors, 896 bytes at SH-2): one thread per brick would walk its
+// brick in 112-byte strides while its neighbours do the same 896 bytes further on -- every load instruction touches 32
+// lines.  Here a warp takes 32 consecutive bricks, one lane per brick for the flag test, ballots, and then all lanes
+// together stream the vectors of the flagged bricks: consecutive lanes read consecutive 16-byte vectors, and the adds of a
+// voxel's channels land in one contiguous row of the dense gradient.
+__global__ void __launch_bounds__(256) consume_touched_tiles_kernel(float4* __restrict__ pg, float* __restrict__ d_dens,
+                                                                    float* __restrict__ d_feat,
+                                                                    const unsigned char* __restrict__ touched, int tag,
+                                                                    unsigned n_bricks, int F, int CV, BrickDims d) {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  const int lane = threadIdx.x & 31;
+  const unsigned tile = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const unsigned brick = tile * 32u + lane;
+  const unsigned char want = (unsigned char)tag;
+  bool any = false;
+  if (brick < n_bricks) {
+    const unsigned bz = brick % (unsigned)d.BZ, t = brick / (unsigned)d.BZ;
+    const unsigned by = t % (unsigned)d.BY, bx = t / (unsigned)d.BY;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const unsigned dx = k >> 2, dy = (k >> 1) & 1, dz = k & 1;
+      if (bx >= dx && by >= dy && bz >= dz) any |= __ldg(touched + ((bx - dx) * (unsigned)d.BY + (by - dy)) * (unsigned)d.BZ + (bz - dz)) == want;
+    }
+  }
+  const unsigned mask = __ballot_sync(0xffffffffu, any);
+  if (mask == 0u) return;
+  const int vpb = 8 * CV;
+  const int n = __popc(mask) * vpb;
+  float4* tile_base = pg + (int64_t)tile * 32 * vpb;
+  constexpr int U = 4;
+  for (int i0 = lane; i0 < n; i0 += 32 * U) {
+    float4 g[U];
+    int off[U], within[U];
+    unsigned which[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int id = i0 + 32 * u;
+      off[u] = -1;
+      if (id < n) {
+        const int j = id / vpb;
+        within[u] = id - j * vpb;
+        which[u] = __fns(mask, 0u, j + 1);
+        off[u] = (int)which[u] * vpb + within[u];
+        g[u] = tile_base[off[u]];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (off[u] < 0 || (g[u].x == 0.f && g[u].y == 0.f && g[u].z == 0.f && g[u].w == 0.f)) continue;
+      tile_base[off[u]] = make_float4(0.f, 0.f, 0.f, 0.f);
+      const unsigned b = tile * 32u + which[u];
+      const unsigned bz = b % (unsigned)d.BZ, t = b / (unsigned)d.BZ;
+      const unsigned by = t % (unsigned)d.BY, bx = t / (unsigned)d.BY;
+      const int k = within[u] / CV, j = within[u] - k * CV;  // voxel slot (x&1, y&1, z&1) of the brick, vector of the voxel
+      const int x = 2 * (int)bx + (k >> 2) - 1, y = 2 * (int)by + ((k >> 1) & 1) - 1, z = 2 * (int)bz + (k & 1) - 1;
+      if (!(x >= 0 && y >= 0 && z >= 0 && x < d.X && y < d.Y && z < d.Z)) continue;  // apron / padding slot: dropped
+      const int64_t v = ((int64_t)x * d.Y + y) * d.Z + z;
+      const float in[4] = {g[u].x, g[u].y, g[u].z, g[u].w};
+#pragma unroll
+      for (int c4 = 0; c4 < 4; ++c4) {
+        const int c = 4 * j + c4;
+        if (c < F) {
+          if (d_feat) atomicAdd(d_feat + v * F + c, in[c4]);
+        } else if (c == F) {
+          if (d_dens) atomicAdd(d_dens + v, in[c4]);
+        }
+      }
+    }
+  }
+}
+
 // Fused per-step grid pass: consume the packed gradient volume (plus optional dense gradients from torch-side losses),
 // apply one Adam step to the reference-layout parameters and their moments, refresh the packed volume and zero the
 // packed gradients -- one launch instead of zero-fill + unpack + AccumulateGrad + ~10 optimiser kernels + repack.
@@ -295,6 +366,10 @@ cudaError_t launch_consume_grad(float* packed_grad, float* d_densities, float* d
   const int threads = 256;
   if (touched != nullptr) {
     const int64_t n_bricks = packed_voxel_slots(dims) / 8;  // < 2^28 (check_grid bounds the vector count by 2^31)
+    if (CV > 1)  // one lane per brick for the flags, whole warps for the flagged bricks' vectors
+      return launch_chained(consume_touched_tiles_kernel, dim3((unsigned)((n_bricks + threads - 1) / threads)), dim3(threads), 0, stream,
+                            reinterpret_cast<float4*>(packed_grad), d_densities, d_features, touched, tag, (unsigned)n_bricks, n_features,
+                            CV, brick_dims(dims));
     return launch_chained(consume_touched_kernel, dim3((unsigned)((n_bricks + threads - 1) / threads)), dim3(threads), 0, stream,
                           reinterpret_cast<float4*>(packed_grad), d_densities, d_features, touched, tag, (unsigned)n_bricks, n_features,
                           CV, brick_dims(dims));

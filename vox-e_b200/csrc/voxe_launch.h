@@ -89,6 +89,8 @@ cudaError_t launch_sample_rays(long long n, long long k, int H, int W, int C, fl
 
 // gradient all-reduce (voxe_collective.cu)
 cudaError_t launch_allreduce_peer(const VoxePeerDesc& peers, int64_t n_floats, unsigned* fail_flag, cudaStream_t stream);
+cudaError_t launch_allreduce_peer_sparse(const VoxePeerDesc& peers, unsigned char* const* touched_peers, int tag, const int dims[3],
+                                         int channels, unsigned* fail_flag, cudaStream_t stream);
 const char* nccl_unavailable();  // nullptr when libnccl could be opened
 const char* nccl_error_string(int rc);
 int nccl_unique_id(void* out128);

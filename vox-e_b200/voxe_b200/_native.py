@@ -16,7 +16,7 @@ _lock = threading.Lock()
 _lib: Optional[ctypes.CDLL] = None
 
 # ---- enums of include/voxe.h -------------------------------------------------------------------------------
-ABI_VERSION = 13
+ABI_VERSION = 14
 PREACT_IDENTITY, PREACT_ABS = 0, 1
 POSTACT_IDENTITY, POSTACT_RELU, POSTACT_SOFTPLUS = 0, 1, 2
 FLAG_PERTURB, FLAG_AABB_SAMPLING, FLAG_DISPARITY_SAMPLING = 1, 2, 4
@@ -114,6 +114,8 @@ EXPORTS = {
     "voxe_pair_loss_grad": (ctypes.c_int, [_P, _P, ctypes.c_int64, ctypes.c_int32, _P, _P, ctypes.c_float, _P, ctypes.c_int32, _P]),
     "voxe_sample_rays": (ctypes.c_int, [ctypes.POINTER(VoxeSamplerDesc), _P, _P, _P, _P, _P, ctypes.c_int64, _P, _P, _P, _P, _P]),
     "voxe_allreduce_grads_peer": (ctypes.c_int, [ctypes.POINTER(VoxePeerDesc), ctypes.c_int64, _P, _P]),
+    "voxe_peer_touched_bytes": (ctypes.c_int64, [_GD]),
+    "voxe_allreduce_grads_peer_sparse": (ctypes.c_int, [ctypes.POINTER(VoxePeerDesc), _GD, ctypes.POINTER(ctypes.c_void_p), ctypes.c_int32, _P, _P]),
     "voxe_nccl_unique_id": (ctypes.c_int, [_P]),
     "voxe_nccl_comm_create": (ctypes.c_int, [ctypes.POINTER(ctypes.c_void_p), ctypes.c_int32, ctypes.c_int32, _P]),
     "voxe_nccl_comm_destroy": (ctypes.c_int, [_P]),

@@ -216,6 +216,36 @@ class PeerGradVolume:
             self._nat.check(self._lib.voxe_allreduce_grads_peer(self._desc, self.n_floats, self._fail.data_ptr(),
                                                                 torch.cuda.current_stream(dev).cuda_stream), "voxe_allreduce_grads_peer")
 
+    def enable_sparse(self, gspec) -> Tensor:
+        """Allocate (collectively, on every rank) the peer-mapped brick-flag array of ``gspec``'s packed volume and return it:
+        pass it to the backward kernels as ``touched`` (``voxe_render_bwd``), then :meth:`allreduce_sparse` exchanges only the
+        bricks some rank touched.  The volume must be the packed gradient volume of that grid."""
+        import ctypes
+
+        import torch.distributed._symmetric_memory as symm_mem
+
+        gd = gspec.to_native()
+        if int(self._lib.voxe_packed_floats(gd)) != self.n_floats:
+            raise ValueError("the peer volume is not the packed gradient volume of this grid")
+        n = int(self._lib.voxe_peer_touched_bytes(gd))
+        self.touched = symm_mem.empty(n, dtype=torch.uint8, device=self.buffer.device)
+        self.touched.zero_()
+        h = symm_mem.rendezvous(self.touched, self.group)
+        self._touched_ptrs = (ctypes.c_void_p * self.world_size)(*[int(h.buffer_ptrs[k]) for k in range(self.world_size)])
+        self._handles = self._handles + (h,)
+        self._gd = gd
+        torch.cuda.synchronize(self.buffer.device)
+        dist.barrier(self.group)
+        return self.touched
+
+    def allreduce_sparse(self, tag: int) -> None:
+        """buffer <- sum over ranks on the bricks whose flag carries ``tag`` on some rank (``voxe_allreduce_grads_peer_sparse``;
+        two launches on the current stream, every rank with the same tag); afterwards ``touched`` holds the union."""
+        dev = self.buffer.device
+        with torch.cuda.device(dev):
+            self._nat.check(self._lib.voxe_allreduce_grads_peer_sparse(self._desc, self._gd, self._touched_ptrs, int(tag), self._fail.data_ptr(),
+                                                                       torch.cuda.current_stream(dev).cuda_stream), "voxe_allreduce_grads_peer_sparse")
+
     def failed(self) -> bool:
         """True when a launch gave up waiting for a peer (synchronises)."""
         return bool(self._fail.item())
