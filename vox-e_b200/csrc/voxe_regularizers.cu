@@ -8,6 +8,7 @@
 // each as ~10-25 elementwise / reduction launches over [X,Y,Z,C] tensors plus their autograd backward.  Here a loss is
 // one read of the grid (+ one 3-to-5-value reduction) and its gradient is one more read fused with the accumulation
 // into the dense gradient: pure HBM streams.
+#include <algorithm>
 #include <cmath>
 #include <cstdint>
 
@@ -20,6 +21,7 @@ __device__ __forceinline__ float sgn(float d) { return (float)(d > 0.f) - (float
 
 constexpr int kMaxCtas = 148 * 8;   // persistent launch: one wave of 8 resident 256-thread CTAs per SM
 constexpr int kPrefetch = 6;       // iterations (of 256 elements per CTA) the TV kernel prefetches ahead into L2
+constexpr int kStripPrefetch = 6;  // rows the strip kernel prefetches ahead into L2
 constexpr int kTicket = 15;         // workspace slot of the last-CTA ticket
 constexpr int kPartials = 16;       // workspace: [0, 16) results / statistics, then N partial sums per CTA
 
@@ -287,6 +289,142 @@ __global__ void __launch_bounds__(256) tv_vec_kernel(const float* __restrict__ g
   }
 }
 
+// Gradient variant (with or without the loss): a thread owns one 16-byte group of a z-row and walks a STRIP of rows along
+// y.  What the walk saves over tv_vec_kernel, which is issue-bound at ~72 SASS instructions per float:
+//   * the row above is the previous iteration's own row and the row below becomes the next one: one new row group per
+//     step instead of three, and max(., 0) is applied once per loaded value;
+//   * sign(h[y+1] - h[y]) is the forward term of row y and the backward term of row y + 1: carried in registers; along z
+//     the same holds inside the group (C <= 3: the backward sign of element k is the forward sign of element k - C);
+//   * x, the z-group and every face predicate but y's are fixed for the strip: the index arithmetic leaves the loop.
+// The loads of row y + 1 are issued before row y is evaluated (two rows of state in registers).  Strips are SEG rows long,
+// chosen on the host so that the launch has ~150 k threads; a strip that starts inside the grid fetches the group above it
+// once for its first backward sign.
+template <bool RELU>
+__device__ __forceinline__ float tv_act(float v) { return RELU ? fmaxf(v, 0.f) : v; }
+
+template <bool RELU>
+__device__ __forceinline__ void tv_unpack(const float4& a, float (&out)[4]) {
+  out[0] = tv_act<RELU>(a.x); out[1] = tv_act<RELU>(a.y); out[2] = tv_act<RELU>(a.z); out[3] = tv_act<RELU>(a.w);
+}
+
+template <bool RELU, bool DO_SUM, int ZMODE>
+__global__ void __launch_bounds__(256, 4) tv_strip_kernel(const float* __restrict__ g, float* __restrict__ grad, double* __restrict__ ws,
+                                                          int X, int Y, int GR, int C, int64_t sxg, int SEG, int NSEG, int64_t n_strips,
+                                                          float cx, float cy, float cz, const float* __restrict__ upstream,
+                                                          int accumulate, float* __restrict__ loss, double n0, double n1, double n2) {
+  const float4* g4 = reinterpret_cast<const float4*>(g);
+  float4* grad4 = reinterpret_cast<float4*>(grad);
+  const float up = upstream ? __ldg(upstream) : 1.f;
+  const float cxu = cx * up, cyu = cy * up, czu = cz * up;
+  const int ZC = 4 * GR;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+  for (int64_t strip = (int64_t)blockIdx.x * 256 + threadIdx.x; strip < n_strips; strip += (int64_t)gridDim.x * 256) {
+    const int eg = (int)(strip % GR), e0 = 4 * eg;
+    const int64_t t = strip / GR;
+    const int yseg = (int)(t % NSEG), x = (int)(t / NSEG);
+    const int y0 = yseg * SEG, y1 = min(Y, y0 + SEG);
+    const int64_t dxm = x > 0 ? -sxg : 0, dxp = x < X - 1 ? sxg : 0;  // a missing neighbour reads the element itself
+    const float4* r = g4 + ((int64_t)x * Y + y0) * GR + eg;
+    float4* gr = grad4 + ((int64_t)x * Y + y0) * GR + eg;
+    // the strip's lines of the grid and of the gradient, kStripPrefetch rows ahead of the walk, into L2
+#pragma unroll
+    for (int k = 1; k <= kStripPrefetch; ++k)
+      if (y0 + k < Y) {
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(r + (int64_t)k * GR));
+        if (accumulate) asm volatile("prefetch.global.L2 [%0];" ::"l"(gr + (int64_t)k * GR));
+      }
+    float v[4], sy[4] = {0.f, 0.f, 0.f, 0.f};
+    tv_unpack<RELU>(__ldg(r), v);
+    if (y0 > 0) {  // first backward sign of the strip: the row above belongs to another strip
+      float above[4];
+      tv_unpack<RELU>(__ldg(r - GR), above);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) sy[k] = sgn(v[k] - above[k]);
+    }
+    for (int y = y0; y < y1; ++y) {
+      // all loads of the row first: the group below, the x neighbours, the z neighbours, the old gradient
+      const float4 yp4 = __ldg(y < Y - 1 ? r + GR : r);
+      const float4 xm4 = __ldg(r + dxm), xp4 = __ldg(r + dxp);
+      float4 za4, zb4;  // ZMODE 1..3: next / previous group; ZMODE 4: the groups at +-C
+      float zs[8];      // ZMODE 0: scalars
+      if (ZMODE >= 1 && ZMODE <= 3) {
+        za4 = __ldg(eg < GR - 1 ? r + 1 : r);
+        zb4 = __ldg(eg > 0 ? r - 1 : r);
+      } else if (ZMODE == 4) {
+        const int cg = C >> 2;
+        za4 = __ldg(eg + cg < GR ? r + cg : r);
+        zb4 = __ldg(eg >= cg ? r - cg : r);
+      } else {
+        const float* rs = reinterpret_cast<const float*>(r);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          zs[k] = __ldg(e0 + k + C < ZC ? rs + k + C : rs + k);
+          zs[4 + k] = __ldg(e0 + k >= C ? rs + k - C : rs + k);
+        }
+      }
+      const float4 old4 = accumulate ? *gr : make_float4(0.f, 0.f, 0.f, 0.f);
+      if (y + 1 + kStripPrefetch < Y) {
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(r + (int64_t)(1 + kStripPrefetch) * GR));
+        if (accumulate) asm volatile("prefetch.global.L2 [%0];" ::"l"(gr + (int64_t)(1 + kStripPrefetch) * GR));
+      }
+      float yp[4], xm[4], xp[4], zp[4], zm[4];
+      tv_unpack<RELU>(yp4, yp);
+      tv_unpack<RELU>(xm4, xm);
+      tv_unpack<RELU>(xp4, xp);
+      if (ZMODE >= 1 && ZMODE <= 3) {
+        float nx[4], pv[4];
+        tv_unpack<RELU>(za4, nx);
+        tv_unpack<RELU>(zb4, pv);
+        const float w[12] = {pv[0], pv[1], pv[2], pv[3], v[0], v[1], v[2], v[3], nx[0], nx[1], nx[2], nx[3]};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          zp[k] = (e0 + k + ZMODE < ZC) ? w[4 + k + ZMODE] : v[k];
+          zm[k] = (e0 + k >= ZMODE) ? w[4 + k - ZMODE] : v[k];
+        }
+      } else if (ZMODE == 4) {
+        tv_unpack<RELU>(za4, zp);
+        tv_unpack<RELU>(zb4, zm);
+      } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          zp[k] = tv_act<RELU>(zs[k]);
+          zm[k] = tv_act<RELU>(zs[4 + k]);
+        }
+      }
+      float out[4] = {old4.x, old4.y, old4.z, old4.w};
+      float fz[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float dzp = zp[k] - v[k], dyp = yp[k] - v[k], dxpk = xp[k] - v[k];
+        if (DO_SUM) {
+          s2 += fabsf(dzp);
+          s1 += fabsf(dyp);
+          s0 += fabsf(dxpk);
+        }
+        fz[k] = sgn(dzp);
+        // along z inside the group the backward sign of element k is the forward sign of element k - C
+        const float bz = (ZMODE >= 1 && ZMODE <= 3 && k >= ZMODE) ? fz[k >= ZMODE ? k - ZMODE : 0] : sgn(v[k] - zm[k]);
+        const float fy = sgn(dyp), by = sy[k];
+        sy[k] = fy;  // ... and along y it is the forward sign of the row above: carried to the next iteration
+        const float gx = sgn(v[k] - xm[k]) - sgn(dxpk);
+        float tt = fmaf(cxu, gx, fmaf(cyu, by - fy, czu * (bz - fz[k])));
+        if (RELU && !(v[k] > 0.f)) tt = 0.f;
+        out[k] += tt;
+      }
+      *gr = make_float4(out[0], out[1], out[2], out[3]);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) v[k] = yp[k];
+      r += GR;
+      gr += GR;
+    }
+  }
+  if (DO_SUM) {
+    double v[3] = {(double)s0, (double)s1, (double)s2};
+    block_store<3>(v, ws);
+    if (last_cta_done(ws)) tv_finalize(ws, loss, n0, n1, n2);
+  }
+}
+
 // Last CTA of a TV launch: fold the partials into the loss.
 __device__ __forceinline__ void tv_finalize(const double* __restrict__ ws, float* __restrict__ loss, double n0, double n1,
                                             double n2) {
@@ -443,7 +581,37 @@ cudaError_t launch_tv(const float* grid, const int dims[3], int channels, bool r
   *launches = 0;
   const bool do_sum = loss != nullptr, do_grad = grad != nullptr;
   const int acc = accumulate ? 1 : 0;
-  if (vec) {
+  if (vec && do_grad) {  // strips along y (see tv_strip_kernel)
+    const int zmode = C <= 3 ? C : (C % 4 == 0 ? 4 : 0);
+    const int GR = ZC / 4;
+    const int64_t columns = (int64_t)X * GR;
+    const int64_t nseg_want = std::max<int64_t>(1, (int64_t)148 * 4 * 256 / columns);
+    int SEG = (int)std::max<int64_t>(4, (Y + nseg_want - 1) / nseg_want);
+    if (SEG > Y) SEG = Y;
+    if (const char* v = getenv("VOXE_TV_SEG")) { SEG = std::min(Y, std::max(1, atoi(v))); }
+    const int NSEG = (Y + SEG - 1) / SEG;
+    const int64_t n_strips = columns * NSEG;
+    const int64_t want = (n_strips + 255) / 256;
+    const int ctas = (int)(want < kMaxCtas ? want : kMaxCtas);
+#define VOXE_TV_STRIP(R_, S_, Z_)                                                                                            \
+  tv_strip_kernel<R_, S_, Z_><<<ctas, 256, 0, stream>>>(grid, grad, workspace, X, Y, GR, C, (int64_t)Y * GR, SEG, NSEG, n_strips, \
+                                                        cx, cy, cz, upstream, acc, loss, n0, n1, n2)
+#define VOXE_TV_STRIP_Z(R_, S_)             \
+  switch (zmode) {                          \
+    case 1: VOXE_TV_STRIP(R_, S_, 1); break; \
+    case 2: VOXE_TV_STRIP(R_, S_, 2); break; \
+    case 3: VOXE_TV_STRIP(R_, S_, 3); break; \
+    case 4: VOXE_TV_STRIP(R_, S_, 4); break; \
+    default: VOXE_TV_STRIP(R_, S_, 0);       \
+  }
+    if (relu) {
+      if (do_sum) { VOXE_TV_STRIP_Z(true, true) } else { VOXE_TV_STRIP_Z(true, false) }
+    } else {
+      if (do_sum) { VOXE_TV_STRIP_Z(false, true) } else { VOXE_TV_STRIP_Z(false, false) }
+    }
+#undef VOXE_TV_STRIP_Z
+#undef VOXE_TV_STRIP
+  } else if (vec) {
     const int zmode = C <= 3 ? C : (C % 4 == 0 ? 4 : 0);
 #define VOXE_TV_VEC(R_, S_, G_, Z_)                                                                                          \
   tv_vec_kernel<R_, S_, G_, Z_><<<n_ctas, 256, 0, stream>>>(grid, grad, workspace, X, Y, ZC / 4, C, (int64_t)Y * (ZC / 4), units, \
