@@ -1361,6 +1361,45 @@ def run_check(args):
     except Exception as exc:  # noqa: BLE001
         api = {"error": str(exc)[:300]}
     results["API path (VolumetricModel + PeerGradients)"] = api
+    # the API path with deferred gradients in a peer-mapped packed sink that keeps a brick trail: reduce_deferred() is the
+    # brick-wise exchange, the optimiser-side hand-over follows the union of the flags (a part of the frame, two steps)
+    if world > 1 and "error" not in api:
+        sink = {}
+        try:
+            from voxe_b200.dist import VoxelGradAllReducer
+
+            grid2 = VoxelGrid(bench.dens.clone(), bench.feat.clone(), VoxelSize(*(w / n for w, n in zip(WL["world"], WL["dims"]))),
+                              density_preactivation=torch.nn.Identity(), density_postactivation=torch.nn.ReLU(),
+                              expected_density_scale=WL["density_scale"], tunable=True)
+            vm2 = VolumetricModel(grid2, render_sh_voxel_grid, vm.render_config, device=device)
+            grid2.accumulate_render_gradients()
+            spec = grid2.fused_spec()
+            vol = PeerGradVolume(int(lib.voxe_packed_floats(spec.to_native())), device, multicast=world > 4)
+            vol.adopt(grid2.render_gradient_accumulator, sparse_spec=spec)
+            reducer = VoxelGradAllReducer([grid2.densities, grid2.features], grids=[grid2])
+            errs = []
+            for step, part in enumerate((bench.batches[: max(world, len(bench.batches) // 6)], bench.batches[len(bench.batches) // 2:][: 2 * world])):
+                grid.densities.grad = grid.features.grad = None
+                api_grads(part)  # unsharded, through the plain API path
+                grid2.densities.grad = grid2.features.grad = None
+                for b0, b1 in part[rank::world]:
+                    vm2.render_rays(Rays(o[b0:b1], d[b0:b1])).colour.backward(bench.G[b0:b1])
+                assert grid2.densities.grad is None
+                reducer.reduce_deferred()
+                grid2.materialize_render_gradients()
+                torch.cuda.synchronize(device)
+                assert not vol.failed(), "a peer did not arrive"
+                for got, want in ((grid2.densities.grad, grid.densities.grad), (grid2.features.grad, grid.features.grad)):
+                    t = torch.tensor([float((got - want).abs().max()) / float(want.abs().max()), float(vol.buffer.abs().max())], device=device)
+                    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                    errs.append((float(t[0]), float(t[1])))
+            sink = {"max_abs_over_inf": max(e for e, _ in errs), "sink_volume_left": max(v for _, v in errs),
+                    "ok": max(e for e, _ in errs) <= 1e-5 and max(v for _, v in errs) == 0.0,
+                    "path": "deferred gradients in a peer-mapped sink with a brick trail, VoxelGradAllReducer.reduce_deferred() = "
+                            "voxe_allreduce_grads_peer_sparse, materialize = voxe_consume_grad along the union; two steps"}
+        except Exception as exc:  # noqa: BLE001
+            sink = {"error": str(exc)[:300]}
+        results["API path (deferred sink + brick-wise exchange)"] = sink
     if rank == 0:
         ok = all(r.get("ok", True) and "error" not in r for r in results.values())
         print(json.dumps({"check": "rank-sum of render_bwd_kernel gradients", "n_gpus": world, "frame": f"pose {pose}, {len(bench.batches)} batches dealt round-robin",

@@ -95,6 +95,34 @@ def test_deferred_gradients_equal_autograd_gradients():
     assert torch.equal(before, deferred.features.grad)
 
 
+def test_deferred_gradients_with_a_brick_trail_equal_autograd_gradients():
+    """`accumulate_render_gradients(trail=True)`: every backward of a step tags the bricks it scatters into and the
+    hand-over visits only those -- same `.grad` as autograd, over several steps (fresh tag per step, flags never cleared),
+    and the sink volume is all-zero after each hand-over."""
+    from _product import make_grid
+
+    meta, a = load_case("softplus_white")
+    regular = make_grid(meta, a["densities"], a["features"], "cuda")
+    deferred = make_grid(meta, a["densities"], a["features"], "cuda")
+    deferred.accumulate_render_gradients(trail=True)
+    acc = deferred.render_gradient_accumulator
+    assert acc.sparse_sink and acc.touched is not None and int(acc.touch_tag[0]) == 1
+    for step, sels in enumerate([(slice(0, 70), slice(70, None)), (slice(10, 40),), (slice(0, None),)]):
+        for g in (regular, deferred):
+            g.densities.grad = g.features.grad = None
+        for sel in sels:
+            _render_loss(regular, meta, a, sel).backward()
+            _render_loss(deferred, meta, a, sel).backward()
+        assert deferred.densities.grad is None and acc.dirty
+        assert int((acc.touched == int(acc.touch_tag[0])).sum()) > 0  # this step's trail
+        deferred.materialize_render_gradients()
+        assert int(acc.touch_tag[0]) == step + 2 and not acc.dirty
+        assert float(acc.buffer.abs().max()) == 0.0
+        for got, want in ((deferred.densities.grad, regular.densities.grad), (deferred.features.grad, regular.features.grad)):
+            l2, linf = grad_errors(got.cpu(), want.cpu())
+            assert l2 <= 1e-6 and linf <= 1e-6, (step, l2, linf)
+
+
 def _train(grid, optimizer, meta, a, steps, tv_weight=0.05, scheduler=None):
     losses = []
     for _ in range(steps):
@@ -116,14 +144,15 @@ def test_training_loops_agree_across_the_three_step_paths():
     from voxe_b200.optim import FusedVoxelAdam
 
     meta, a = load_case("blob_softplus_all_grads_black")
-    grids = [make_grid(meta, a["densities"], a["features"], "cuda") for _ in range(3)]
+    grids = [make_grid(meta, a["densities"], a["features"], "cuda") for _ in range(4)]
     grids[1].accumulate_render_gradients()
+    grids[3].accumulate_render_gradients(trail=True)  # (4) as (2), the hand-over following the brick flags
     mk = lambda g: torch.optim.Adam([{"params": g.parameters(), "lr": 0.03}], betas=(0.9, 0.999))  # noqa: E731
-    opts = [mk(grids[0]), mk(grids[1]), FusedVoxelAdam(grids[2], lr=0.03)]
+    opts = [mk(grids[0]), mk(grids[1]), FusedVoxelAdam(grids[2], lr=0.03), mk(grids[3])]
     scheds = [torch.optim.lr_scheduler.ExponentialLR(o, gamma=0.9) for o in opts]
     runs = [_train(g, o, meta, a, 5, scheduler=s) for g, o, s in zip(grids, opts, scheds)]
     assert runs[0][-1] < runs[0][0]  # the loss <colour, G> goes down
-    for other in (1, 2):
+    for other in (1, 2, 3):
         assert max(abs(x - y) for x, y in zip(runs[0], runs[other])) <= 1e-4 * max(1.0, abs(runs[0][0]))
         for p, q in ((grids[0].densities, grids[other].densities), (grids[0].features, grids[other].features)):
             # 5 steps of lr 0.03: compare against the step size, the sign-like Adam update amplifies 1e-7 gradient noise

@@ -162,14 +162,20 @@ struct RenderNode : public torch::autograd::Node {
     // Sparse hand-over: the kernel tags the bricks it scatters into and voxe_consume_grad visits only those.  A fresh tag
     // per backward; stale tags of earlier calls only cost the consume pass a few reads (it skips all-zero vectors), so the
     // flags are never cleared.
+    // A sink that keeps a trail (deferred gradients on a large grid: the step's exchange and its hand-over follow the flags,
+    // PackedGradAccumulator.sparse_sink) tags every backward of an optimiser step alike; the accumulator advances the tag.
     const bool sparse = mode != kSink && touched.defined() && grad_volume.defined();
+    const bool sink_trail = mode == kSink && touched.defined() && touch_tag.defined() && grad_volume.defined();
     int32_t tag = 0;
     if (sparse) {
       int64_t* last = touch_tag.data_ptr<int64_t>();
       *last = (*last % 255) + 1;
       tag = (int32_t)*last;
+    } else if (sink_trail) {
+      tag = (int32_t)touch_tag.data_ptr<int64_t>()[0];
+      TORCH_CHECK(tag >= 1 && tag <= 255, "the gradient sink's brick-flag tag must be in 1..255 (got ", tag, ")");
     }
-    uint8_t* touched_ptr = sparse ? touched.data_ptr<uint8_t>() : nullptr;
+    uint8_t* touched_ptr = (sparse || sink_trail) ? touched.data_ptr<uint8_t>() : nullptr;
     check(voxe_render_bwd(&gd, &rd, cptr(packed), cptr(rays_o), cptr(rays_d), cptr(jitter), cptr(noise), cptr(work),
                           cptr(g[0]), cptr(g[1]), cptr(g[2]), cptr(g[3]), mptr(volume), touched_ptr, tag, R, stream),
           "voxe_render_bwd");

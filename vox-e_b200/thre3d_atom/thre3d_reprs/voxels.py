@@ -275,7 +275,7 @@ class VoxelGrid(Module):
         self._packed.invalidate()
         self._packed_attn.invalidate()
 
-    def accumulate_render_gradients(self, enabled: bool = True) -> None:
+    def accumulate_render_gradients(self, enabled: bool = True, trail: bool = False) -> None:
         """Opt into deferred gradients: render backward passes scatter into one persistent packed volume instead of
         producing dense ``.grad`` tensors per call; ``materialize_render_gradients()`` (called automatically before any
         ``torch.optim`` step once ``voxe_b200.optim`` is imported, or replaced by ``FusedVoxelAdam``) makes them visible."""
@@ -284,6 +284,9 @@ class VoxelGrid(Module):
 
             self._grad_accumulator = PackedGradAccumulator()
             optim.track_grid(self)
+            if trail:  # large grids: remember which bricks a step touched; the hand-over into .grad then visits only those
+                spec = self.fused_spec()
+                self._grad_accumulator.enable_trail(spec, self._packed.get(spec, self._densities, self._features))
         elif not enabled and self._grad_accumulator is not None:
             self.materialize_render_gradients()
             self._grad_accumulator = None

@@ -109,7 +109,15 @@ class VoxelGradAllReducer:
                 spec = grid.fused_spec()
                 acc.get(grid.packed_cache().get(spec, grid.densities, grid.features))
             if world > 1:
-                self.reduce_flat(acc.buffer)
+                peer = getattr(acc, "peer_volume", None)
+                if peer is not None and acc.buffer is peer.buffer:  # the library's own kernel, in place on the sink volume
+                    if acc.sparse_sink:
+                        peer.allreduce_sparse(int(acc.touch_tag[0]))
+                    else:
+                        peer.allreduce()
+                    self.num_collectives += 1
+                else:
+                    self.reduce_flat(acc.buffer)
                 acc.dirty = True  # the sum may be non-zero even where this rank's share was
             n += 1
         return n
@@ -250,11 +258,22 @@ class PeerGradVolume:
         """True when a launch gave up waiting for a peer (synchronises)."""
         return bool(self._fail.item())
 
-    def adopt(self, accumulator) -> None:
-        """Make this volume the gradient volume of a ``PackedGradAccumulator`` (a grid's deferred-gradient sink)."""
+    def adopt(self, accumulator, sparse_spec=None) -> None:
+        """Make this volume the gradient volume of a ``PackedGradAccumulator`` (a grid's deferred-gradient sink).
+        ``sparse_spec`` (the grid's ``fused_spec()``): also keep the brick-flag trail in peer-mapped memory, so that
+        ``VoxelGradAllReducer.reduce_deferred()`` exchanges only the bricks some rank touched in the step
+        (``allreduce_sparse``) and the hand-over into ``.grad`` follows the union -- for grids of which a step writes a small
+        part.  Collective when ``sparse_spec`` is given."""
         accumulator.buffer = self.buffer
         accumulator.touched = None
+        accumulator.sparse_sink = False
         accumulator.dirty = False
+        accumulator.peer_volume = self
+        if sparse_spec is not None:
+            touched = getattr(self, "touched", None)
+            if touched is None:
+                touched = self.enable_sparse(sparse_spec)
+            accumulator.enable_trail(sparse_spec, self.buffer, touched=touched)
 
 
 class PeerGradients:

@@ -125,6 +125,8 @@ class FusedVoxelAdam(Optimizer):
             )
         if acc is not None:
             acc.dirty = False  # the kernel zeroed what it consumed
+            if acc.sparse_sink:
+                acc._next_tag()  # the next step leaves a fresh trail
         # the parameters changed behind autograd's back: bump their version counters, then vouch for the packed copy
         torch.autograd.graph.increment_version([dens, feat])
         cache.mark_fresh(spec, dens, feat)

@@ -224,6 +224,10 @@ class PackedGradAccumulator:
         # handed out for it; used by the sparse direct hand-over, ignored by the deferred mode
         self.touched: Optional[Tensor] = None
         self.touch_tag = torch.zeros(1, dtype=torch.int64)
+        # deferred mode on a large grid: keep the trail as well, so that the step's exchange (PeerGradVolume.allreduce_sparse)
+        # and the hand-over into .grad follow the bricks the step touched instead of sweeping the volume (enable_trail)
+        self.sparse_sink = False
+        self.peer_volume = None  # set by PeerGradVolume.adopt: the volume lives in peer-mapped memory
 
     @property
     def dirty(self) -> bool:
@@ -246,9 +250,25 @@ class PackedGradAccumulator:
             self.touched = torch.zeros(n, dtype=torch.uint8, device=self.buffer.device)
         return self.touched
 
+    def enable_trail(self, spec: "FusedGridSpec", like: Tensor, touched: Optional[Tensor] = None) -> None:
+        """Deferred gradients with a brick-flag trail: every backward of an optimiser step tags the bricks it scatters into
+        with the step's tag, and :meth:`materialize` visits only those.  ``touched``: a caller-owned flag array (the
+        peer-mapped one of ``PeerGradVolume.enable_sparse``), else a local one is allocated."""
+        self.get(like)
+        self.touched = touched if touched is not None else None
+        if self.touched is None:
+            self.get_touched(spec)
+        self.sparse_sink = True
+        self.touch_tag[0] = 1
+
+    def _next_tag(self) -> None:
+        self.touch_tag[0] = int(self.touch_tag[0]) % 255 + 1
+
     def zero(self) -> None:
         if self.buffer is not None and self.dirty:
             self.buffer.zero_()
+            if self.sparse_sink:
+                self._next_tag()
         self.dirty = False
 
     def materialize(self, spec: "FusedGridSpec", densities: Tensor, features: Tensor) -> None:
@@ -257,6 +277,21 @@ class PackedGradAccumulator:
             return
         lib = nat.load_library()
         dev = self.buffer.device
+        if self.sparse_sink:  # along the trail: adds into .grad and zeroes what it read, so the volume is clean afterwards
+            ptrs = []
+            for p in (densities, features):
+                if p.requires_grad and p.grad is None:
+                    p.grad = torch.zeros_like(p, memory_format=torch.contiguous_format)
+                ptrs.append(p.grad.data_ptr() if p.requires_grad else None)
+            if ptrs[0] is not None or ptrs[1] is not None:
+                with torch.cuda.device(dev):
+                    nat.check(lib.voxe_consume_grad(spec.to_native(), self.buffer.data_ptr(), ptrs[0], ptrs[1], self.touched.data_ptr(),
+                                                    int(self.touch_tag[0]), _stream_ptr(dev)), "voxe_consume_grad")
+            else:
+                self.buffer.zero_()
+            self._next_tag()
+            self.dirty = False
+            return
         outs = []
         for p in (densities, features):
             if not p.requires_grad:
@@ -326,6 +361,8 @@ def fused_render(
     if torch.is_grad_enabled() and (densities.requires_grad or features.requires_grad):
         if grad_sink is not None:  # deferred gradients (opt-in): leave them in the grid's persistent volume
             volume, flag, mode = grad_sink.get(packed), grad_sink.flag, ext.MODE_SINK
+            if grad_sink.sparse_sink:  # ... and a trail of the bricks this step touches
+                touched, tag = grad_sink.touched, grad_sink.touch_tag
         elif grad_scratch is not None:  # persistent all-zero-between-calls volume: no allocation / zero-fill per call
             volume = grad_scratch.get(packed)
             touched, tag = grad_scratch.touched, grad_scratch.touch_tag
