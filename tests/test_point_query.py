@@ -156,3 +156,34 @@ def test_query_agrees_with_grid_sample_on_a_training_sized_grid():
     (sample(f2) * gout[:, :3]).sum().backward()
     l2, linf = grad_errors(grid.features.grad.cpu(), f2.grad.cpu())
     assert l2 <= 2e-5 and linf <= 1e-4, (l2, linf)  # same coordinate rounding, seen through the trilinear weights
+
+
+@pytest.mark.gpu
+def test_edge_cases_empty_single_and_frozen():
+    from thre3d_atom.thre3d_reprs.voxels import VoxelGrid, VoxelSize
+
+    dev = torch.device("cuda")
+    g = torch.Generator().manual_seed(9)
+    dens, feat = torch.randn((3, 4, 5, 1), generator=g).to(dev), torch.randn((3, 4, 5, 12), generator=g).to(dev)
+    grid = VoxelGrid(dens, feat, VoxelSize(0.5, 0.5, 0.5), density_preactivation=torch.nn.Identity(),
+                     density_postactivation=torch.nn.Softplus(), expected_density_scale=2.0, tunable=True)
+    out = grid(torch.zeros((0, 3), device=dev))
+    assert out.shape == (0, 13)
+    out.sum().backward()  # an empty query contributes zero gradients of the right shape
+    assert float(grid.features.grad.abs().max()) == 0.0 and grid.densities.grad.shape == dens.shape
+    one = grid(torch.tensor([[0.1, -0.2, 0.3]], device=dev))
+    want = query_points_oracle(dens.cpu(), feat.cpu(), OracleGrid((0.5, 0.5, 0.5), density_scale=2.0, preact="identity", postact="softplus"),
+                               torch.tensor([[0.1, -0.2, 0.3]]))
+    assert one.shape == (1, 13) and float((one.detach().cpu().double() - want).abs().max()) <= 1e-5
+    # the voxel centres themselves: the interpolation returns the stored values
+    ax = [(torch.arange(n) + 0.5) * 0.5 - n * 0.25 for n in (3, 4, 5)]
+    centres = torch.stack(torch.meshgrid(*ax, indexing="ij"), dim=-1).reshape(-1, 3).to(dev)
+    at = grid(centres).detach()
+    assert float((at[:, :12] - feat.reshape(-1, 12)).abs().max()) <= 1e-5
+    assert float((at[:, 12] - torch.nn.functional.softplus(dens.reshape(-1) * 2.0)).abs().max()) <= 1e-5
+    # frozen densities: only the features receive a gradient; NaN coordinates propagate instead of reading out of bounds
+    frozen = VoxelGrid(dens.clone(), torch.nn.Parameter(feat.clone()), VoxelSize(0.5, 0.5, 0.5), tunable=False)
+    res = frozen(torch.tensor([[0.0, 0.0, 0.0], [float("nan"), 0.0, 0.0], [1e30, -1e30, 0.0]], device=dev))
+    assert torch.isfinite(res[0]).all() and torch.isnan(res[1]).any() and float(res[2, :12].abs().max()) == 0.0
+    res[0].sum().backward()
+    assert frozen.features.grad is not None and float(frozen.features.grad.abs().max()) > 0.0
