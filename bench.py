@@ -360,14 +360,22 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+FULL_AFFINITY = os.sched_getaffinity(0) if hasattr(os, "sched_getaffinity") else None  # before any pinning
+
+
 def reference_subprocess(device, steps, warmup, timeout_s=240):
     """Run the reference arm in a child process (the staged reference and this repository's mirror cannot share one
     interpreter) and return its JSON line, or a dict with "error"."""
     cmd = [sys.executable, str(Path(__file__).resolve()), "--impl", "reference", "--ref-device", device, "--steps", str(steps),
            "--warmup", str(warmup)]
     env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")}
+
+    def all_cpus():  # the child is the reference with every host thread it can use, whatever this process pinned itself to
+        if FULL_AFFINITY and hasattr(os, "sched_setaffinity"):
+            os.sched_setaffinity(0, FULL_AFFINITY)
+
     try:
-        r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout_s, env=env, cwd=str(ROOT))
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout_s, env=env, cwd=str(ROOT), preexec_fn=all_cpus)
         lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
         if r.returncode != 0 or not lines:
             return {"error": (r.stderr or r.stdout)[-400:]}
@@ -1437,7 +1445,7 @@ def run_ours(args):
     torch.cuda.set_device(device)
     dist = None
     pinned_cpus = None
-    if world > 1 and not args.no_pin and hasattr(os, "sched_setaffinity"):
+    if not args.no_pin and hasattr(os, "sched_setaffinity"):
         # one rank per GPU on a shared host: give every rank its own slice of the host's CPUs (what numactl / taskset
         # would do), so that eight Python loops, their autograd worker threads and NCCL helper threads do not migrate over
         # each other.  Slices are made of whole physical cores (both hyper-threads of a core go to the same rank): with
