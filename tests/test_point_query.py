@@ -187,3 +187,7 @@ def test_edge_cases_empty_single_and_frozen():
     assert torch.isfinite(res[0]).all() and torch.isnan(res[1]).any() and float(res[2, :12].abs().max()) == 0.0
     res[0].sum().backward()
     assert frozen.features.grad is not None and float(frozen.features.grad.abs().max()) > 0.0
+    with pytest.raises(NotImplementedError, match="detach the points"):
+        frozen(torch.zeros((2, 3), device=dev, requires_grad=True))
+    with pytest.raises(AssertionError, match="attention grid"):
+        frozen.forward_attn(torch.zeros((2, 3), device=dev))

@@ -287,6 +287,10 @@ class VoxelGrid(Module):
             if trail:  # large grids: remember which bricks a step touched; the hand-over into .grad then visits only those
                 spec = self.fused_spec()
                 self._grad_accumulator.enable_trail(spec, self._packed.get(spec, self._densities, self._features))
+        elif enabled and trail and not self._grad_accumulator.sparse_sink:  # already deferred: start keeping the trail now
+            self.materialize_render_gradients()
+            spec = self.fused_spec()
+            self._grad_accumulator.enable_trail(spec, self._packed.get(spec, self._densities, self._features))
         elif not enabled and self._grad_accumulator is not None:
             self.materialize_render_gradients()
             self._grad_accumulator = None
@@ -317,6 +321,7 @@ class VoxelGrid(Module):
         reads the densities kept by ``update_orig_densities``."""
         from voxe_b200.render_function import query_points
 
+        assert self.attn is not None, "forward_attn needs the attention grid (add_attn_params / attn=...)"
         densities = self.orig_densities if orig_densities else self._densities
         out = query_points(self.fused_spec(n_features=1), densities, self.attn, points, cache=self._packed_attn)
         return self._with_radiance(out, viewdirs)

@@ -523,6 +523,9 @@ def query_points(gspec: FusedGridSpec, densities: Tensor, features: Tensor, poin
     interpolated density at ``points`` [N, 3] (world coordinates, anywhere: zeros padding, no inside mask)."""
     assert points.dim() == 2 and points.shape[-1] == 3, f"points should be of shape [N x 3] as opposed to ({tuple(points.shape)})"
     _require_cuda(densities, features)
+    if points.requires_grad and torch.is_grad_enabled():
+        raise NotImplementedError("voxe_query_points differentiates the grid tensors only; detach the points (no caller of the "
+                                  "reference differentiates a query w.r.t. its coordinates)")
     if points.device != densities.device:
         raise RuntimeError(f"all render inputs must live on one device (got {points.device} and {densities.device})")
     packed = (cache or PackedVolumeCache()).get(gspec, densities, features)
