@@ -274,14 +274,21 @@ __global__ void __launch_bounds__(kThreads, 1) allreduce_sparse_kernel(const __g
       } else {
 #pragma unroll
         for (int u = 0; u < U; ++u) acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int k = 0; k < p.base.world; ++k) {  // fixed rank order: the same sum on every rank and run
-          float4 v[U];
+        constexpr int G = 4;  // peers whose loads are in flight together (G * U 16-byte requests per thread)
+        for (int k0 = 0; k0 < p.base.world; k0 += G) {
+          float4 v[G][U];
 #pragma unroll
-          for (int u = 0; u < U; ++u)
-            if (off[u] >= 0) v[u] = ld_peer(p.base.buf[k] + off[u]);
+          for (int k = 0; k < G; ++k)
 #pragma unroll
-          for (int u = 0; u < U; ++u)
-            if (off[u] >= 0) { acc[u].x += v[u].x; acc[u].y += v[u].y; acc[u].z += v[u].z; acc[u].w += v[u].w; }
+            for (int u = 0; u < U; ++u)
+              if (k0 + k < p.base.world && off[u] >= 0) v[k][u] = ld_peer(p.base.buf[k0 + k] + off[u]);
+#pragma unroll
+          for (int k = 0; k < G; ++k)  // fixed rank order: the same sum on every rank and run
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+              if (k0 + k < p.base.world && off[u] >= 0) {
+                acc[u].x += v[k][u].x; acc[u].y += v[k][u].y; acc[u].z += v[k][u].z; acc[u].w += v[k][u].w;
+              }
         }
         for (int k = 0; k < p.base.world; ++k) {
           const int dst = (p.base.rank + k) % p.base.world;
