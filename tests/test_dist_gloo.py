@@ -109,3 +109,75 @@ def test_shard_helpers():
     assert torch.equal(a, o[4:8])
     assert vd.world_info() == (0, 1)
     assert vd.global_mean_scale(5) == 1.0
+
+
+class _StubPeerVolume:
+    """Stands in for PeerGradVolume on the CPU: same surface, the exchange done by gloo."""
+
+    def __init__(self, buffer):
+        self.buffer, self.calls = buffer, []
+
+    def allreduce(self):
+        self.calls.append("dense")
+        dist.all_reduce(self.buffer)
+
+    def allreduce_sparse(self, tag):
+        self.calls.append(("sparse", tag))
+        dist.all_reduce(self.buffer)
+
+
+class _StubGrid:
+    def __init__(self, acc, params):
+        self.render_gradient_accumulator = acc
+        self.densities, self.features = params
+
+
+def _deferred_worker(rank, world, port, tmp):
+    for p in (ROOT, ROOT / "vox-e_b200"):
+        sys.path.insert(0, str(p))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from voxe_b200 import dist as vd
+        from voxe_b200.render_function import PackedGradAccumulator
+
+        params = [torch.nn.Parameter(torch.zeros(4)), torch.nn.Parameter(torch.zeros(4))]
+        record = {}
+        for mode in ("flat", "peer_dense", "peer_sparse"):
+            acc = PackedGradAccumulator()
+            acc.buffer = torch.full((16,), float(rank + 1))
+            if mode != "flat":
+                acc.peer_volume = _StubPeerVolume(acc.buffer)
+            if mode == "peer_sparse":
+                acc.sparse_sink = True
+                acc.touch_tag[0] = 7
+            reducer = vd.VoxelGradAllReducer(params, grids=[_StubGrid(acc, params)])
+            assert reducer.reduce_deferred() == 1 and reducer.num_collectives == 1
+            record[mode] = (acc.buffer.clone(), None if mode == "flat" else list(acc.peer_volume.calls), acc.dirty)
+        # a sink that was re-allocated (no longer the peer's buffer) must not be exchanged through the peer volume
+        acc = PackedGradAccumulator()
+        acc.buffer = torch.full((16,), float(rank + 1))
+        acc.peer_volume = _StubPeerVolume(torch.zeros(16))
+        vd.VoxelGradAllReducer(params, grids=[_StubGrid(acc, params)]).reduce_deferred()
+        record["stale_peer"] = (acc.buffer.clone(), list(acc.peer_volume.calls), acc.dirty)
+        torch.save(record, os.path.join(tmp, f"deferred_{rank}.pt"))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_reduce_deferred_takes_the_peer_volume_when_the_sink_lives_in_it(tmp_path):
+    """Host logic of the deferred-gradient exchange at world size 2: the packed sink is reduced through the library's peer
+    kernel when it IS the peer-mapped volume (brick-wise when the sink keeps a trail, with the step's tag), through
+    torch.distributed otherwise; the sink is marked dirty so that the optimiser-side hand-over runs on every rank."""
+    import socket
+
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_deferred_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    for r in range(2):
+        rec = torch.load(tmp_path / f"deferred_{r}.pt")
+        for mode, calls in (("flat", None), ("peer_dense", ["dense"]), ("peer_sparse", [("sparse", 7)]), ("stale_peer", [])):
+            buf, got_calls, dirty = rec[mode]
+            assert torch.equal(buf, torch.full((16,), 3.0)), (r, mode)  # 1 + 2 on both ranks
+            assert got_calls == calls and dirty, (r, mode, got_calls)
