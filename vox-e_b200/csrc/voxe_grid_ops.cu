@@ -163,7 +163,10 @@ __global__ void __launch_bounds__(256) consume_touched_kernel(float4* __restrict
 // brick in 112-byte strides while its neighbours do the same 896 bytes further on -- every load instruction touches 32
 // lines.  Here a warp takes 32 consecutive bricks, one lane per brick for the flag test, ballots, and then all lanes
 // together stream the vectors of the flagged bricks: consecutive lanes read consecutive 16-byte vectors, and the adds of a
-// voxel's channels land in one contiguous row of the dense gradient.
+// voxel's channels land in one contiguous row of the dense gradient.  The adds stay fire-and-forget REDs although every
+// dense element belongs to exactly one thread of the launch: a plain load-add-store was measured slower (cfg 5: 1.39 ms
+// against 1.20 ms; the round trip of the load costs more than the L2 atomic unit's 140 M sectors,
+// profiles/r2_cfg5_handover_kernel_metrics.txt).
 __global__ void __launch_bounds__(256) consume_touched_tiles_kernel(float4* __restrict__ pg, float* __restrict__ d_dens,
                                                                     float* __restrict__ d_feat,
                                                                     const unsigned char* __restrict__ touched, int tag,
