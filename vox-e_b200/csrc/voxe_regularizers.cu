@@ -588,7 +588,7 @@ cudaError_t launch_tv(const float* grid, const int dims[3], int channels, bool r
     const int64_t nseg_want = std::max<int64_t>(1, (int64_t)148 * 4 * 256 / columns);
     int SEG = (int)std::max<int64_t>(4, (Y + nseg_want - 1) / nseg_want);
     if (SEG > Y) SEG = Y;
-    if (const char* v = getenv("VOXE_TV_SEG")) { SEG = std::min(Y, std::max(1, atoi(v))); }
+    if (const char* v = getenv("VOXE_TV_SEG")) { SEG = std::min(Y, std::max(1, atoi(v))); }  // tuning runs: rows per strip
     const int NSEG = (Y + SEG - 1) / SEG;
     const int64_t n_strips = columns * NSEG;
     const int64_t want = (n_strips + 255) / 256;
