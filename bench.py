@@ -1855,7 +1855,7 @@ def main():
     ap.add_argument("--handover", choices=["dense", "sparse"], default="",
                     help="gradient hand-over of the device leg: 'dense' = zero-fill + whole-volume all-reduce + unpack; 'sparse' = follow the "
                          "backward's brick flags (default for cfg5, whose batch touches a few percent of a 15 GB volume)")
-    ap.add_argument("--lanes", type=int, default=3, help="ray batches in flight within a frame (streams)")
+    ap.add_argument("--lanes", type=int, default=4, help="ray batches in flight within a frame (streams)")
     ap.add_argument("--jitter", choices=["kernel", "buffer"], default="kernel",
                     help="stratified jitter of the device leg: generated inside the kernels (counter-based hash) or torch-drawn [R,S] buffers")
     ap.add_argument("--sweep", type=str, default="", help="tuning sweep: 'L,rpc,cap;L,rpc,cap;...'")
